@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the xtensor hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): effective HBM GB/s of the fused broadcast assignment
+    c(1024,1024,64) = sin(a) * b(1,1024,1) + 2.0f * d          (fp32, BASELINE cfg2)
+= algorithmic bytes (each distinct input element read once, each
+output element written once: 3 x 256 MiB + 4 KiB = 805,310,464 B) / device time.
+One "step" = one evaluation of that expression through the C ABI (xtb_assign).
+At N > 1 every rank evaluates its own cfg2-sized shard of a leading-axis-sharded
+c(1024*N,1024,64) (weak scaling, no data-path collective); the sharded cfg5
+pipeline with its NCCL allreduce is timed next to it and reported under "cfg5".
+
+The JSON line also carries: roofline (dominant kernel vs the measured copy peak),
+cpu_baseline (the reference's CPU evaluation of a bounded sample, timed here),
+e2e (host buffers, H2D + D2H inside the timed region), clocks, gpu_launches.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = dict(shape=(1024, 1024, 64), workload="cfg2: fp32 c(1024,1024,64) = sin(a) * b(1,1024,1) + 2.0f * d")
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def cfg2_bytes(shape):
+    n = int(np.prod(shape))
+    return 3 * n * 4 + shape[1] * 4
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev, self.proc, self.lines = device_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- our arm -----------------------------------------------------------------------------------
+def device_time_ms(lib, fn, iters):
+    from xtensor_b200 import capi
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    capi.check(lib.xtb_event_create(C.byref(e0)))
+    capi.check(lib.xtb_event_create(C.byref(e1)))
+    capi.check(lib.xtb_sync())
+    capi.check(lib.xtb_event_record(e0))
+    for _ in range(iters):
+        fn()
+    capi.check(lib.xtb_event_record(e1))
+    ms = C.c_float()
+    capi.check(lib.xtb_event_elapsed_ms(e0, e1, C.byref(ms)))
+    capi.check(lib.xtb_sync())
+    lib.xtb_event_destroy(e0); lib.xtb_event_destroy(e1)
+    return float(ms.value)
+
+
+def make_inputs(shape, rank):
+    rng = np.random.default_rng(3 + 100 * rank)
+    a = rng.uniform(-np.pi, np.pi, shape).astype(np.float32)
+    b = np.random.default_rng(4).uniform(0.5, 1.5, (1, shape[1], 1)).astype(np.float32)
+    d = np.random.default_rng(5 + 100 * rank).uniform(-np.pi, np.pi, shape).astype(np.float32)
+    return a, b, d
+
+
+def cpu_baseline_cfg2(sample_rows=24):
+    """The reference's CPU evaluation (oracle restatement, or oracle/_ref when built) on a bounded
+    sample of cfg2: the first `sample_rows` leading rows.  cfg2 selects the single-threaded
+    stepper_assigner in xtensor, so cores = 1."""
+    from oracle import oracle
+    xt = oracle.install()
+    ref = None
+    try:
+        from oracle import refbin
+        ref = refbin.run_cfg2(sample_rows)
+    except Exception:
+        ref = None
+    shape = (sample_rows,) + CFG2["shape"][1:]
+    if ref is not None:
+        return {"value": ref["gbs"], "unit": "GB/s", "cores": ref["cores"], "kind": "reference",
+                "sample": f"cfg2 on the first {sample_rows} of 1024 leading rows ({ref['seconds']:.2f} s), {ref['how']}"}
+    a, b, d = make_inputs(shape, 0)
+    H = xt.HostArray.from_numpy
+    A, B, D_ = H(a), H(b), H(d)
+    out = xt.HostArray.empty(shape, xt.F32)
+    t0 = time.perf_counter()
+    xt.assign(out, xt.sin(A) * B + np.float32(2.0) * D_)
+    dt = time.perf_counter() - t0
+    return {"value": cfg2_bytes(shape) / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"cfg2 on the first {sample_rows} of 1024 leading rows ({dt:.2f} s), oracle/xtb_oracle.cpp "
+                      "(scalar restatement of stepper_assigner, -O2 -ffp-contract=off)"}
+
+
+def run_ours(args):
+    from xtensor_b200 import capi
+    from xtensor_b200 import expr as xt
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+    lib = capi.lib()
+    capi.check(lib.xtb_init(local_rank))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ident = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            capi.check(lib.xtb_comm_unique_id(buf))
+            ident[0] = buf.raw
+        dist.broadcast_object_list(ident, src=0)
+        capi.check(lib.xtb_comm_init(rank, world, C.create_string_buffer(ident[0], 128)))
+
+    shape = CFG2["shape"]
+    a, b, d = make_inputs(shape, rank)
+    A, B, D_ = (xt.DeviceArray.from_numpy(x) for x in (a, b, d))
+    out = xt.DeviceArray.empty(shape, xt.F32)
+    expr_ = xt.sin(A) * B + np.float32(2.0) * D_
+    lw = xt.lower(expr_)
+    prog, ops, oop = lw.program(), lw.operands(), out.operand()
+
+    def step():
+        capi.check(lib.xtb_assign(C.byref(prog), C.byref(oop), ops))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    capi.check(lib.xtb_sync())
+    kernel_name = lib.xtb_last_kernel().decode()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    lib.xtb_launch_count(1)
+    sampler.start()
+    ms = device_time_ms(lib, step, args.steps)
+    clocks = sampler.stop()
+    launches = int(lib.xtb_launch_count(0))
+    barrier()
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    step_bytes = cfg2_bytes(shape)
+    value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # per-launch duration of the dominant kernel, measured live (one launch per step)
+    peak, peak_src = peak_hbm()
+    achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("cfg2_assign_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": kernel_name,
+                "algorithmic_bytes_per_launch": step_bytes, "peak_source": peak_src}
+
+    # end to end: pinned host buffers -> H2D -> xtb_assign -> D2H of the result, every step
+    e2e_steps = max(1, min(args.steps, 5))
+    hp = []
+    for x in (a, b, d, np.empty(shape, np.float32)):
+        p = C.c_void_p()
+        capi.check(lib.xtb_host_alloc(x.nbytes, C.byref(p)))
+        C.memmove(p, x.ctypes.data, x.nbytes)
+        hp.append((p, x.nbytes))
+
+    def e2e_step():
+        for (p, n), dev in zip(hp[:3], (A, B, D_)):
+            capi.check(lib.xtb_memcpy(C.c_void_p(dev.owner.ptr), p, n, capi.H2D))
+        step()
+        capi.check(lib.xtb_memcpy(hp[3][0], C.c_void_p(out.owner.ptr), hp[3][1], capi.D2H))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    capi.check(lib.xtb_sync())
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    res_host = np.ctypeslib.as_array(C.cast(hp[3][0], C.POINTER(C.c_float)), shape=(int(np.prod(shape)),))
+    checksum = float(res_host[:: 4097].astype(np.float64).sum())
+    e2e = {"value": round(world * step_bytes / e2e_s / 1e9, 2), "unit": "GB/s",
+           "h2d_bytes_per_step": int(a.nbytes + b.nbytes + d.nbytes), "d2h_bytes_per_step": int(hp[3][1]),
+           "steps": e2e_steps, "result_checksum": checksum}
+    for p, _ in hp:
+        lib.xtb_host_free(p)
+
+    extra = {}
+    if not args.no_extra:
+        extra = other_configs(lib, xt, capi, world, rank, dist, args)
+
+    if rank == 0:
+        line = {
+            "metric": "effective HBM GB/s, fused broadcast assign (algorithmic bytes / device time)",
+            "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CFG2["workload"] + (f", one such shard per GPU x{world} along the leading axis" if world > 1 else ""),
+                       "l2": "inputs+output 768 MiB per step, larger than the 126 MB L2 (no flush needed)",
+                       "pct_of_8TBs": round(100 * value / world / 8000.0, 2)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_cfg2()
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        lib.xtb_comm_destroy()
+        dist.destroy_process_group()
+
+
+def other_configs(lib, xt, capi, world, rank, dist, args):
+    """The other BASELINE configs, timed outside the headline region (reported, not the metric)."""
+    out = {}
+    peak, _ = peak_hbm()
+
+    def timed(fn, nbytes, iters=10):
+        for _ in range(3):
+            fn()
+        ms = device_time_ms(lib, fn, iters) / iters
+        return {"ms": round(ms, 4), "GBs": round(nbytes / ms / 1e6, 1), "frac_of_measured_peak": round(nbytes / ms / 1e6 / peak, 4),
+                "kernel": lib.xtb_last_kernel().decode()}
+
+    try:
+        if world == 1:
+            rng = np.random.default_rng(1)
+            # cfg1: fp64 1-D 2^24 a + b
+            n = 1 << 24
+            a, b = (xt.DeviceArray.from_numpy(rng.uniform(-1, 1, n)) for _ in range(2))
+            c = xt.DeviceArray.empty((n,), xt.F64)
+            out["cfg1_add_f64"] = timed(lambda: xt.assign(c, a + b), 3 * n * 8)
+            del a, b, c
+            # cfg3: fp32 (4096,4096,16) sum / amax over axis 0 and axis 2
+            x = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (4096, 4096, 16)).astype(np.float32))
+            nb = 4096 * 4096 * 16 * 4
+            out["cfg3_sum_axis0"] = timed(lambda: xt.evaluate(xt.sum(x, [0])), nb + 4096 * 16 * 4)
+            out["cfg3_amax_axis0"] = timed(lambda: xt.evaluate(xt.amax(x, [0])), nb + 4096 * 16 * 4)
+            out["cfg3_sum_axis2"] = timed(lambda: xt.evaluate(xt.sum(x, [2])), nb + 4096 * 4096 * 4)
+            out["cfg3_amax_axis2"] = timed(lambda: xt.evaluate(xt.amax(x, [2])), nb + 4096 * 4096 * 4)
+            del x
+            # cfg4: fp64 (8192,8192) transpose(a) + view(b, range(0,_,2), all())
+            a = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (8192, 8192)))
+            b = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (16384, 8192)))
+            o = xt.DeviceArray.empty((8192, 8192), xt.F64)
+            e = xt.transpose(a) + xt.view(b, slice(0, None, 2), slice(None))
+            out["cfg4_transpose_view_f64"] = timed(lambda: xt.assign(o, e), 3 * 8192 * 8192 * 8, iters=5)
+            del a, b, o, e
+        # cfg5: sharded (262144, 8192) fp32: mean / variance over axis 0 (allreduce) + exp(a - mean)
+        rows = 262144 // world
+        cols = 8192
+        blk = np.random.default_rng(9 + rank).uniform(-1, 1, (4096, cols)).astype(np.float32)
+        a = xt.DeviceArray.empty((rows, cols), xt.F32)
+        for r0 in range(0, rows, 4096):
+            capi.check(lib.xtb_memcpy(C.c_void_p(a.owner.ptr + r0 * cols * 4), C.c_void_p(blk.ctypes.data), blk.nbytes, capi.H2D))
+        capi.check(lib.xtb_sync())
+        o = xt.DeviceArray.empty((rows, cols), xt.F32)
+        total_rows = np.float32(rows * world)
+
+        def pipeline():
+            s = xt._run_reducer(xt.sum(a, [0]), xt.DeviceArray, allreduce=world > 1)
+            m = xt.evaluate(s / total_rows)                                  # mean<float>
+            v = xt._run_reducer(xt.sum(xt.square(a - m), [0]), xt.DeviceArray, allreduce=world > 1)
+            var = xt.evaluate(v / total_rows)
+            xt.assign(o, xt.exp(a - m))
+            return var
+
+        nbytes = world * (4 * rows * cols * 4)  # 2 reduce passes + map read + map write
+        for _ in range(2):
+            pipeline()
+        if dist is not None:
+            dist.barrier()
+        ms = device_time_ms(lib, pipeline, 3) / 3
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        out["cfg5_sharded_pipeline"] = {"ms": round(ms, 4), "GBs_aggregate": round(nbytes / ms / 1e6, 1),
+                                        "frac_of_measured_peak_per_gpu": round(nbytes / ms / 1e6 / peak / world, 4),
+                                        "rows_per_gpu": rows, "scaling": "strong", "allreduce": world > 1}
+    except Exception as ex:  # the headline number must survive a failure of the side measurements
+        out["other_configs_error"] = repr(ex)
+    return {"other_configs": out}
+
+
+# ---- reference arm -------------------------------------------------------------------------------
+def run_reference(args):
+    """xtensor's own CPU evaluation of cfg2 on the box's host cores (bounded sample per step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, info = [], None
+    for i in range(args.warmup + args.steps):
+        info = cpu_baseline_cfg2(sample_rows=8)
+        if i >= args.warmup:
+            vals.append(info["value"])
+    v = float(np.mean(vals))
+    ms = cfg2_bytes((8,) + CFG2["shape"][1:]) / (v * 1e9) * 1e3
+    info["value"] = round(v, 4)
+    line = {"impl": "reference", "metric": "effective HBM GB/s, fused broadcast assign (algorithmic bytes / device time)",
+            "value": round(v, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": CFG2["workload"]},
+            "cpu_baseline": info,
+            "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of cfg1/3/4/5")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

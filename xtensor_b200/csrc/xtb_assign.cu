@@ -1,0 +1,124 @@
+// xtb_assign.cu -- xtb_assign: evaluate a lowered xfunction tree into a container.
+// Host side: validation, broadcast alignment (xt::broadcast_shape,
+// include/xtensor/core/xstrides.hpp:737-780), iteration-space collapsing, kernel
+// selection.  Kernels: xtb_ew.cuh.
+#include <cstdlib>
+#include "xtb_ew.cuh"
+
+namespace xtb {
+
+template <class S, int V> static int launch_interp(const EwParams& p, DeviceCtx* ctx) {
+    return launch_ew_generic<InterpEval, S, V>(p, ctx, "interp");
+}
+
+static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ctx, bool w64, int V) {
+    const bool no_static = getenv("XTB_NO_STATIC") != nullptr;  // tests toggle this per call
+    if (!no_static && ew_nd_ok(p)) {
+        const StaticEntry* e = find_static(prog);
+        if (e) {
+            const bool k64 = sprogs::is64(*e->prog);
+            if (k64 == w64 && V == (k64 ? 2 : 4)) return e->launch_ew(p, ctx);
+        }
+    }
+    if (w64) return V == 2 ? launch_interp<uint64_t, 2>(p, ctx) : launch_interp<uint64_t, 1>(p, ctx);
+    return V == 4 ? launch_interp<uint32_t, 4>(p, ctx) : launch_interp<uint32_t, 1>(p, ctx);
+}
+
+}  // namespace xtb
+
+using namespace xtb;
+
+extern "C" int xtb_assign(const xtb_program* prog, const xtb_operand* out, const xtb_operand* leaves) {
+    if (!prog || !out) XTB_FAIL(XTB_ERR_INVALID, "null argument");
+    if (prog->n_leaves > 0 && !leaves) XTB_FAIL(XTB_ERR_INVALID, "null leaves");
+    if (out->ndim < 0 || out->ndim > XTB_MAX_DIM) XTB_FAIL(XTB_ERR_INVALID, "out rank %d", out->ndim);
+    if (out->dtype < 0 || out->dtype >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "bad out dtype");
+    int32_t leaf_dt[XTB_MAX_LEAVES];
+    for (int k = 0; k < prog->n_leaves && k < XTB_MAX_LEAVES; ++k) leaf_dt[k] = leaves[k].dtype;
+    int rt = 0;
+    bool w64 = false;
+    XTB_TRY(validate_program(prog, leaf_dt, &rt, &w64));
+    if (dtype_size(out->dtype) == 8) w64 = true;
+
+    Space s;
+    s.ndim = out->ndim;
+    s.n_ops = prog->n_leaves + 1;
+    const int OUT = prog->n_leaves;
+    for (int d = 0; d < out->ndim; ++d) {
+        if (out->shape[d] < 0) XTB_FAIL(XTB_ERR_INVALID, "negative extent");
+        s.shape[d] = out->shape[d];
+        s.stride[OUT][d] = out->shape[d] == 1 ? 0 : out->stride[d];
+    }
+    for (int k = 0; k < prog->n_leaves; ++k) {
+        char what[32];
+        snprintf(what, sizeof(what), "leaf %d", k);
+        XTB_TRY(align_operand(&leaves[k], s.ndim, s.shape, s.stride[k], what));
+    }
+    for (int d = 0; d < s.ndim; ++d)
+        if (s.shape[d] == 0) return XTB_OK;  // nothing to assign
+    DeviceCtx* ctx;
+    XTB_TRY(get_ctx(&ctx));
+
+    sort_space_by(&s, OUT);
+    collapse_space(&s);
+    if (s.ndim == 0) {  // 0-d / single element
+        s.ndim = 1;
+        s.shape[0] = 1;
+        for (int k = 0; k < s.n_ops; ++k) s.stride[k][0] = 0;
+    }
+
+    EwParams p;
+    memset(&p, 0, sizeof(p));
+    p.prog.n_insns = prog->n_insns;
+    p.prog.result_type = rt;
+    memcpy(p.prog.insns, prog->insns, sizeof(xtb_insn) * prog->n_insns);
+    memcpy(p.prog.imms, prog->imms, sizeof(uint64_t) * XTB_MAX_IMMS);
+    p.ndim = s.ndim;
+    p.n_leaves = prog->n_leaves;
+    p.out_rt = rt;
+    for (int d = 0; d < s.ndim; ++d) p.shape[d] = s.shape[d];
+
+    // vector width: 16 bytes of the widest element type on the path
+    int V = w64 ? 2 : 4;
+    const int inner = s.ndim - 1;
+    auto classify = [&](const char* base, int dtype, const int64_t* st, bool is_out) -> int {
+        const int sz = dtype_size(dtype);
+        if (s.shape[inner] == 1) return is_out ? MODE_GATHER : MODE_BCAST;
+        if (st[inner] == 0 && !is_out) return MODE_BCAST;
+        if (st[inner] != 1) return MODE_GATHER;
+        const int64_t vb = (int64_t) V * sz;
+        if (((uintptr_t) base) % vb != 0) return MODE_GATHER;
+        for (int d = 0; d < inner; ++d)
+            if ((st[d] * sz) % vb != 0) return MODE_GATHER;
+        return MODE_VEC;
+    };
+    for (int k = 0; k < prog->n_leaves; ++k) {
+        EwLeaf& L = p.leaf[k];
+        L.dtype = leaves[k].dtype;
+        L.ptr = operand_ptr(&leaves[k], dtype_size(L.dtype));
+        for (int d = 0; d < s.ndim; ++d) L.stride[d] = s.stride[k][d];
+        L.mode = classify(L.ptr, L.dtype, L.stride, false);
+    }
+    p.out.dtype = out->dtype;
+    p.out.ptr = operand_ptr(out, dtype_size(out->dtype));
+    for (int d = 0; d < s.ndim; ++d) p.out.stride[d] = s.stride[OUT][d];
+    p.out.mode = classify(p.out.ptr, p.out.dtype, p.out.stride, true);
+
+    // If nothing can use vector access, one element per thread keeps accesses coalesced.
+    bool any_vec = p.out.mode == MODE_VEC;
+    for (int k = 0; k < prog->n_leaves; ++k) any_vec |= p.leaf[k].mode == MODE_VEC;
+    if (!any_vec) {
+        V = 1;
+        for (int k = 0; k < prog->n_leaves; ++k)
+            if (p.leaf[k].mode == MODE_VEC) p.leaf[k].mode = MODE_GATHER;
+    }
+    const int64_t vpr = (s.shape[inner] + V - 1) / V;
+    int64_t rows = 1;
+    for (int d = 0; d < inner; ++d) rows *= s.shape[d];
+    p.vec_per_row = (uint32_t) vpr;
+    p.total_vec = rows * vpr;
+    if (vpr > 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "inner extent too large");
+    p.div_vpr = make_fastdiv((uint32_t) vpr);
+    for (int d = 0; d < s.ndim; ++d) p.div_dim[d] = make_fastdiv((uint32_t) std::min<int64_t>(s.shape[d], 0x7fffffff));
+    return dispatch_ew(prog, p, ctx, w64, V);
+}

@@ -1,0 +1,80 @@
+// xtb_common.hpp -- host-side plumbing shared by the translation units of
+// libxtb200: per-thread error state, per-device context (stream, SM count,
+// scratch), launch accounting and the operand canonicaliser.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "../../include/xtb200.h"
+
+namespace xtb {
+
+// ---- error state -------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+#define XTB_FAIL(code, ...) return ::xtb::set_error((code), __VA_ARGS__)
+#define XTB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return ::xtb::set_error(e__ == cudaErrorMemoryAllocation ? XTB_ERR_OOM : XTB_ERR_CUDA, \
+                                    "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                                    __FILE__, __LINE__);                                       \
+    } while (0)
+#define XTB_TRY(call)             \
+    do {                          \
+        int r__ = (call);         \
+        if (r__ != XTB_OK) return r__; \
+    } while (0)
+
+// ---- device context ----------------------------------------------------------
+struct DeviceCtx {
+    int device = -1;
+    bool ready = false;
+    cudaStream_t own_stream = nullptr;   // created by the library
+    cudaStream_t stream = nullptr;       // stream in use (own or adopted)
+    int sm_count = 0;
+    size_t l2_bytes = 0;
+    void* scratch = nullptr;             // reduction partials / scan state
+    size_t scratch_bytes = 0;
+};
+// Context of the calling thread's device; fails with XTB_ERR_NO_DEVICE when
+// there is no GPU.  (No CPU fallback by design.)
+int get_ctx(DeviceCtx** ctx);
+int ensure_scratch(DeviceCtx* ctx, size_t bytes, void** ptr);
+void note_launch(const char* kernel_name, int n = 1);
+int check_launch(const char* what);
+
+// ---- iteration-space canonicaliser --------------------------------------------
+// Operands (leaves + out) are re-expressed over one common iteration space:
+// extent-1 dims dropped, dims optionally permuted, adjacent dims merged when
+// every operand walks them with one stride.  This replaces the per-element
+// stepper bookkeeping of xiterator.hpp:484-631 by a handful of integers.
+struct Space {
+    int ndim = 0;
+    int64_t shape[XTB_MAX_DIM] = {0};
+    int n_ops = 0;                                        // operands tracked
+    int64_t stride[XTB_MAX_LEAVES + 2][XTB_MAX_DIM] = {{0}};  // elements
+    bool reduced[XTB_MAX_DIM] = {false};                  // reduce planning only
+    int64_t total = 1;                                    // number of points
+};
+
+// Broadcast-align `op` (rank <= ndim, right aligned) against shape[ndim] and
+// write its per-dimension strides (0 where broadcast). Returns XTB_ERR_SHAPE if
+// not broadcastable.
+int align_operand(const xtb_operand* op, int ndim, const int64_t* shape, int64_t* stride_out,
+                  const char* what);
+// Drop extent-1 dims; merge adjacent dims (never across a reduced/kept boundary).
+void collapse_space(Space* s);
+// Sort dims so that operand `key` has non-increasing |stride| (elementwise only).
+void sort_space_by(Space* s, int key);
+
+inline char* operand_ptr(const xtb_operand* op, int elem_size) {
+    return (char*) op->base + op->offset * (int64_t) elem_size;
+}
+
+int validate_program(const xtb_program* p, const int32_t* leaf_dtypes, int* result_type,
+                     bool* needs64);
+
+}  // namespace xtb

@@ -1,0 +1,259 @@
+// xtb_ew.cuh -- the fused N-ary broadcast elementwise kernels behind xtb_assign.
+//
+// Replaces the three CPU loops selected by
+// xexpression_assigner_base<xtensor_expression_tag>::assign_data
+// (include/xtensor/core/xassign.hpp:439-478):
+//   linear_assigner::run        xassign.hpp:701-849   -> k_ew<ND=1>   (contiguous, 128-bit)
+//   strided_loop_assigner::run  xassign.hpp:1100-1344 -> k_ew<ND=2,3> (broadcast rows)
+//   stepper_assigner::run       xassign.hpp:644-695   -> k_ew_generic (any rank / strides)
+// The stepper odometer of xiterator.hpp:589-631 becomes closed-form index math:
+//   addr_k(i) = base_k + sum_d i_d * stride_k[d],  stride 0 on broadcast dims.
+#pragma once
+#include <algorithm>
+#include "xtb_common.hpp"
+#include "xtb_ops.cuh"
+#include "xtb_static_programs.cuh"
+
+namespace xtb {
+
+enum LeafMode : int32_t { MODE_VEC = 0, MODE_BCAST = 1, MODE_GATHER = 2 };
+
+struct EwLeaf {
+    const char* ptr;
+    int64_t stride[XTB_MAX_DIM];  // elements, per collapsed dim
+    int32_t dtype;
+    int32_t mode;
+};
+
+struct EwParams {
+    DevProgram prog;
+    int32_t ndim;
+    int32_t n_leaves;
+    int64_t shape[XTB_MAX_DIM];
+    int64_t total_vec;      // number of V-wide vectors (rows * vec_per_row)
+    uint32_t vec_per_row;
+    uint32_t out_rt;        // register type of the value to store
+    FastDiv div_vpr;
+    FastDiv div_dim[XTB_MAX_DIM];
+    EwLeaf leaf[XTB_MAX_LEAVES];
+    EwLeaf out;
+};
+
+// Leaf access for one thread position: coordinates of the row + column of the
+// first element of its vector.
+template <int ND> struct EwFetch {
+    const EwParams& p;
+    int64_t idx[ND > 1 ? ND - 1 : 1];
+    int64_t col;
+    int nvalid;
+
+    XTB_DEV int64_t offset_of(const EwLeaf& L) const {
+        int64_t off = col * L.stride[ND - 1];
+#pragma unroll
+        for (int d = 0; d < ND - 1; ++d) off += idx[d] * L.stride[d];
+        return off;
+    }
+    template <class S, int V> XTB_DEV void load(int k, int dt, S (&x)[V]) const {
+        const EwLeaf& L = p.leaf[k];
+        const int sz = dtype_size(dt);
+        const char* ptr = L.ptr + offset_of(L) * sz;
+        if (L.mode == MODE_BCAST) {
+            S s = load_elem<S>(ptr, dt);
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = s;
+        } else if (L.mode == MODE_VEC && nvalid == V) {
+            load_vec<S, V>(ptr, dt, x);
+        } else {
+            const int64_t step = L.stride[ND - 1] * sz;
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = (v < nvalid) ? load_elem<S>(ptr + v * step, dt) : S(0);
+        }
+    }
+};
+
+// generic rank: run-time ndim, 64-bit coordinates
+struct EwFetchN {
+    const EwParams& p;
+    int64_t idx[XTB_MAX_DIM];
+    int64_t col;
+    int nvalid;
+    XTB_DEV int64_t offset_of(const EwLeaf& L) const {
+        const int nd = p.ndim;
+        int64_t off = col * L.stride[nd - 1];
+        for (int d = 0; d < nd - 1; ++d) off += idx[d] * L.stride[d];
+        return off;
+    }
+    template <class S, int V> XTB_DEV void load(int k, int dt, S (&x)[V]) const {
+        const EwLeaf& L = p.leaf[k];
+        const int sz = dtype_size(dt);
+        const char* ptr = L.ptr + offset_of(L) * sz;
+        if (L.mode == MODE_BCAST) {
+            S s = load_elem<S>(ptr, dt);
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = s;
+        } else if (L.mode == MODE_VEC && nvalid == V) {
+            load_vec<S, V>(ptr, dt, x);
+        } else {
+            const int64_t step = L.stride[p.ndim - 1] * sz;
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = (v < nvalid) ? load_elem<S>(ptr + v * step, dt) : S(0);
+        }
+    }
+};
+
+struct InterpEval {
+    static constexpr int kUnroll = 1;
+    template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
+        interpret<S, V>(prog, f, r);
+    }
+};
+// Tbl: struct with a static constexpr array `progs` of SProg; ID indexes it.
+template <class Tbl, int ID> struct StaticEval {
+    static constexpr int kUnroll = 4;
+    template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
+        eval_static<Tbl, ID, S, V>(prog.imms, f, r);
+    }
+};
+
+template <class S, int V, class Fetch>
+XTB_DEV void ew_store(const EwParams& p, const Fetch& f, const S (&r)[V]) {
+    const EwLeaf& O = p.out;
+    const int sz = dtype_size(O.dtype);
+    char* ptr = (char*) O.ptr + f.offset_of(O) * sz;
+    if (O.mode == MODE_VEC && f.nvalid == V) {
+        store_vec<S, V>(ptr, O.dtype, (int) p.out_rt, r);
+    } else {
+        const int nd = p.ndim;
+        const int64_t step = O.stride[nd - 1] * sz;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (v < f.nvalid) store_elem<S>(ptr + v * step, O.dtype, (int) p.out_rt, r[v]);
+    }
+}
+
+// One thread evaluates ITEMS vectors of V consecutive inner-dim elements; within
+// a block consecutive threads take consecutive vectors (coalesced 128-bit access).
+template <class Eval, class S, int V, int ND, int ITEMS>
+__global__ void __launch_bounds__(256) k_ew(const __grid_constant__ EwParams p) {
+    const int64_t inner = p.shape[ND - 1];
+    const uint32_t base = blockIdx.x * (256u * ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const uint32_t vec = base + it * 256u;
+        if ((int64_t) vec >= p.total_vec) break;
+        EwFetch<ND> f{p, {0}, 0, V};
+        uint32_t cv = vec;
+        if constexpr (ND > 1) {
+            uint32_t row = fd_div(vec, p.div_vpr);
+            cv = vec - row * p.vec_per_row;
+#pragma unroll
+            for (int d = ND - 2; d >= 0; --d) {
+                if (d == 0) {
+                    f.idx[0] = row;
+                } else {
+                    uint32_t q = fd_div(row, p.div_dim[d]);
+                    f.idx[d] = row - q * (uint32_t) p.shape[d];
+                    row = q;
+                }
+            }
+        }
+        f.col = (int64_t) cv * V;
+        const int64_t rem = inner - f.col;
+        f.nvalid = rem < V ? (int) rem : V;
+        S r[V];
+        Eval::template run<S, V>(p.prog, f, r);
+        ew_store<S, V>(p, f, r);
+    }
+}
+
+// Any rank, 64-bit indices (slow path: rank > 3 after collapsing, or >= 2^31 vectors).
+template <class Eval, class S, int V>
+__global__ void __launch_bounds__(256) k_ew_generic(const __grid_constant__ EwParams p) {
+    const int nd = p.ndim;
+    const int64_t inner = p.shape[nd - 1];
+    for (int64_t vec = (int64_t) blockIdx.x * 256 + threadIdx.x; vec < p.total_vec; vec += (int64_t) gridDim.x * 256) {
+        EwFetchN f{p, {0}, 0, V};
+        int64_t row = vec / p.vec_per_row;
+        f.col = (vec - row * p.vec_per_row) * V;
+        for (int d = nd - 2; d >= 0; --d) {
+            const int64_t q = row / p.shape[d];
+            f.idx[d] = row - q * p.shape[d];
+            row = q;
+        }
+        const int64_t rem = inner - f.col;
+        f.nvalid = rem < V ? (int) rem : V;
+        S r[V];
+        Eval::template run<S, V>(p.prog, f, r);
+        ew_store<S, V>(p, f, r);
+    }
+}
+
+
+// ---- launch ---------------------------------------------------------------------
+// Rank-specialised kernels (compile-time programs): 32-bit index math, ND <= 3.
+template <class Eval, class S, int V>
+static int launch_ew_nd(const EwParams& p, DeviceCtx* ctx, const char* evname) {
+    const int nd = p.ndim;
+    constexpr int ITEMS = 2;
+    const int64_t per_block = 256 * ITEMS;
+    const unsigned grid = (unsigned) ((p.total_vec + per_block - 1) / per_block);
+    char name[96];
+    snprintf(name, sizeof(name), "k_ew<%s,S%d,V%d,ND%d>", evname, (int) sizeof(S) * 8, V, nd);
+    switch (nd) {
+        case 1: k_ew<Eval, S, V, 1, ITEMS><<<grid, 256, 0, ctx->stream>>>(p); break;
+        case 2: k_ew<Eval, S, V, 2, ITEMS><<<grid, 256, 0, ctx->stream>>>(p); break;
+        default: k_ew<Eval, S, V, 3, ITEMS><<<grid, 256, 0, ctx->stream>>>(p); break;
+    }
+    note_launch(name);
+    return check_launch(name);
+}
+static inline bool ew_nd_ok(const EwParams& p) { return p.ndim <= 3 && p.total_vec < (int64_t) 0x7fffffff; }
+
+// Any rank / any size.
+template <class Eval, class S, int V>
+static int launch_ew_generic(const EwParams& p, DeviceCtx* ctx, const char* evname) {
+    const int64_t blocks = (p.total_vec + 255) / 256;
+    const int64_t cap = (int64_t) ctx->sm_count * 64;
+    const unsigned grid = (unsigned) std::min(blocks, cap);
+    char name[96];
+    snprintf(name, sizeof(name), "k_ew_generic<%s,S%d,V%d>", evname, (int) sizeof(S) * 8, V);
+    k_ew_generic<Eval, S, V><<<grid, 256, 0, ctx->stream>>>(p);
+    note_launch(name);
+    return check_launch(name);
+}
+
+// ---- registry of compile-time programs ---------------------------------------------
+// Programs whose instruction stream equals a pre-instantiated SProg run a fully
+// unrolled kernel; anything else runs the interpreter.  Both paths share every
+// line of functor code (xtb_ops.cuh).
+struct StaticEntry {
+    const sprogs::SP* prog;
+    const char* name;
+    int (*launch_ew)(const EwParams&, DeviceCtx*);
+};
+struct StaticTable {
+    const StaticEntry* entries;
+    int n;
+};
+StaticTable static_table_f32();
+StaticTable static_table_f64();
+StaticTable static_table_i32();
+
+inline bool sprog_matches(const sprogs::SP& sp, const xtb_program* prog) {
+    if (prog->n_insns != sp.n) return false;
+    for (int i = 0; i < sp.n; ++i) {
+        const xtb_insn in = prog->insns[i];
+        if (in.op != sp.ins[i].op || in.type != sp.ins[i].type || in.src != sp.ins[i].src || in.arg != sp.ins[i].arg)
+            return false;
+    }
+    return true;
+}
+inline const StaticEntry* find_static(const xtb_program* prog) {
+    const StaticTable tables[3] = {static_table_f32(), static_table_f64(), static_table_i32()};
+    for (const StaticTable& t : tables)
+        for (int i = 0; i < t.n; ++i)
+            if (sprog_matches(*t.entries[i].prog, prog)) return &t.entries[i];
+    return nullptr;
+}
+
+}  // namespace xtb

@@ -1,0 +1,372 @@
+// xtb_reduce.cu -- xtb_reduce: host-side planning of axis reductions.
+// Follows the contract of reduce_immediate (include/xtensor/reducers/xreducer.hpp:289-565):
+// axes sorted / unique / in range (:336-350), output shape with or without
+// keep_dims (shape_computation :190-239), empty axes = elementwise reduce(init, x)
+// (:316-325), zero-size reduced extent yields init (:1782-1785), xt::initial merged
+// once at the end (:552-563).  Kernels: xtb_reduce.cuh.
+#include <cfloat>
+#include <climits>
+#include <cstdlib>
+#include "xtb_reduce.cuh"
+
+namespace xtb {
+
+int comm_allreduce(DeviceCtx* ctx, void* buf, size_t count, int dtype, int op);  // xtb_comm.cu
+
+static uint64_t identity_bits(int op, int rt) {
+    union { uint64_t u; double d; float f[2]; int32_t i32[2]; uint32_t u32[2]; int64_t i64; } v;
+    v.u = 0;
+    switch (op) {
+        case XTB_RED_SUM: break;
+        case XTB_RED_PROD:
+            switch (rt) {
+                case XTB_F32: v.f[0] = 1.0f; break;
+                case XTB_F64: v.d = 1.0; break;
+                default: v.u = 1; break;
+            }
+            break;
+        case XTB_RED_MAX:  // numeric_limits<T>::lowest()
+            switch (rt) {
+                case XTB_F32: v.f[0] = -FLT_MAX; break;
+                case XTB_F64: v.d = -DBL_MAX; break;
+                case XTB_I32: v.i32[0] = INT32_MIN; break;
+                case XTB_I64: v.i64 = INT64_MIN; break;
+                default: v.u = 0; break;
+            }
+            break;
+        case XTB_RED_MIN:  // numeric_limits<T>::max()
+            switch (rt) {
+                case XTB_F32: v.f[0] = FLT_MAX; break;
+                case XTB_F64: v.d = DBL_MAX; break;
+                case XTB_I32: v.i32[0] = INT32_MAX; break;
+                case XTB_U32: v.u32[0] = UINT32_MAX; break;
+                case XTB_I64: v.i64 = INT64_MAX; break;
+                default: v.u = UINT64_MAX; break;
+            }
+            break;
+    }
+    return v.u;
+}
+
+static int binop_of(int op) {
+    switch (op) {
+        case XTB_RED_SUM: return XTB_OP_ADD;
+        case XTB_RED_PROD: return XTB_OP_MUL;
+        case XTB_RED_MAX: return XTB_OP_MAXIMUM;
+        case XTB_RED_MIN: return XTB_OP_MINIMUM;
+        default: return -1;
+    }
+}
+
+static int run_reduce_kernel(const xtb_program* prog, const RdParams& p, DeviceCtx* ctx, bool inner, bool w64, int V) {
+    const bool no_static = getenv("XTB_NO_STATIC") != nullptr;  // tests toggle this per call
+    if (!no_static && p.in_rt == p.acc_rt && V == (w64 ? 2 : 4) && p.K < 0x7fffffff) {
+        const StaticReduceTable t = static_reduce_table();
+        for (int i = 0; i < t.n; ++i) {
+            const StaticReduceEntry& e = t.entries[i];
+            if (e.binop == p.binop && e.acc_rt == p.acc_rt && sprogs::is64(*e.prog) == w64 && sprog_matches(*e.prog, prog))
+                return e.launch(p, ctx, inner);
+        }
+    }
+    if (w64) {
+        if (V == 2) return launch_reduce<InterpEval, DynAcc, uint64_t, 2>(p, ctx, inner, "interp");
+        return launch_reduce<InterpEval, DynAcc, uint64_t, 1>(p, ctx, inner, "interp");
+    }
+    if (V == 4) return launch_reduce<InterpEval, DynAcc, uint32_t, 4>(p, ctx, inner, "interp");
+    return launch_reduce<InterpEval, DynAcc, uint32_t, 1>(p, ctx, inner, "interp");
+}
+
+struct ReducePlanIn {
+    const xtb_program* prog;
+    xtb_program own_prog;  // storage for the merge pass's program
+    bool empty = false;    // a reduced extent is 0: every output is init
+    int n_leaves;
+    const char* leaf_ptr[XTB_MAX_LEAVES];
+    int leaf_dtype[XTB_MAX_LEAVES];
+    Space space;       // operands: leaves..., out (index n_leaves); reduced[] flags set
+    int binop, acc_rt, in_rt;
+    bool w64;
+    char* out_ptr;
+    int out_dtype;
+    bool has_initial;
+    uint64_t initial_bits, identity;
+};
+
+static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth);
+
+// second pass over partials[K][nsplit]: an inner (contiguous) reduction per output
+static int merge_partials(const ReducePlanIn& first, const RdParams& fp, DeviceCtx* ctx, int depth) {
+    ReducePlanIn in;
+    memset(&in.own_prog, 0, sizeof(in.own_prog));
+    in.own_prog.n_insns = 1;
+    in.own_prog.n_leaves = 1;
+    in.own_prog.insns[0] = xtb_insn{XTB_OP_PUSH, (uint8_t) first.acc_rt, XTB_SRC_LEAF, 0};  // PUSH leaf0
+    in.prog = &in.own_prog;
+    in.n_leaves = 1;
+    in.leaf_ptr[0] = fp.part_ptr;
+    in.leaf_dtype[0] = first.acc_rt;
+    Space& s = in.space;
+    s = Space();
+    s.ndim = fp.nk + 1;
+    s.n_ops = 2;
+    int64_t st = fp.nsplit;
+    for (int d = fp.nk - 1; d >= 0; --d) {
+        s.shape[d] = fp.kshape[d];
+        s.reduced[d] = false;
+        s.stride[0][d] = st;
+        s.stride[1][d] = fp.out_kstride[d];
+        st *= fp.kshape[d];
+    }
+    s.shape[fp.nk] = fp.nsplit;
+    s.reduced[fp.nk] = true;
+    s.stride[0][fp.nk] = 1;
+    s.stride[1][fp.nk] = 0;
+    in.binop = first.binop;
+    in.acc_rt = in.in_rt = first.acc_rt;
+    in.w64 = first.w64;
+    in.out_ptr = first.out_ptr;
+    in.out_dtype = first.out_dtype;
+    in.has_initial = first.has_initial;
+    in.initial_bits = first.initial_bits;
+    in.identity = first.identity;
+    return plan_and_launch(in, ctx, depth + 1);
+}
+
+static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
+    Space& s = in.space;
+    const int OUT = in.n_leaves;
+    // NOTE: no collapse_space() on the merge pass's kept dims beyond what is exact
+    collapse_space(&s);
+    RdParams p;
+    memset(&p, 0, sizeof(p));
+    p.prog.n_insns = in.prog->n_insns;
+    p.prog.result_type = in.in_rt;
+    memcpy(p.prog.insns, in.prog->insns, sizeof(xtb_insn) * in.prog->n_insns);
+    memcpy(p.prog.imms, in.prog->imms, sizeof(uint64_t) * XTB_MAX_IMMS);
+    p.binop = in.binop;
+    p.acc_rt = in.acc_rt;
+    p.in_rt = in.in_rt;
+    p.n_leaves = in.n_leaves;
+    p.identity_bits = in.identity;
+    p.initial_bits = in.initial_bits;
+    p.has_initial = in.has_initial;
+    p.out_ptr = in.out_ptr;
+    p.out_dtype = in.out_dtype;
+
+    // split dims into kept / reduced lists (order preserved)
+    int kd[XTB_MAX_DIM], rd[XTB_MAX_DIM];
+    int nk = 0, nr = 0;
+    for (int d = 0; d < s.ndim; ++d) (s.reduced[d] ? rd[nr++] : kd[nk++]) = d;
+    const bool inner = !in.empty && s.ndim > 0 && s.reduced[s.ndim - 1];
+    p.K = 1;
+    p.R = 1;
+    // always at least one kept and one reduced dim (dummy extent-1 dims in front)
+    int ko = 0, ro = 0;
+    if (nk == 0) { p.kshape[0] = 1; ko = 1; }
+    if (nr == 0) { p.rshape[0] = 1; ro = 1; }
+    for (int i = 0; i < nk; ++i) {
+        p.kshape[ko + i] = s.shape[kd[i]];
+        p.K *= s.shape[kd[i]];
+        p.out_kstride[ko + i] = s.stride[OUT][kd[i]];
+        for (int k = 0; k < in.n_leaves; ++k) p.leaf[k].kstride[ko + i] = s.stride[k][kd[i]];
+    }
+    for (int i = 0; i < nr; ++i) {
+        p.rshape[ro + i] = s.shape[rd[i]];
+        p.R *= s.shape[rd[i]];
+        for (int k = 0; k < in.n_leaves; ++k) p.leaf[k].rstride[ro + i] = s.stride[k][rd[i]];
+    }
+    p.nk = nk + ko;
+    p.nr = nr + ro;
+    if (p.K >= 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "more than 2^31 reduction outputs");
+    if (p.nr > 1 && p.R >= 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "non-mergeable reduced axes with more than 2^31 elements");
+    for (int d = 0; d < p.nk; ++d) p.kdiv[d] = make_fastdiv((uint32_t) p.kshape[d]);
+    for (int d = 0; d < p.nr; ++d) p.rdiv[d] = make_fastdiv((uint32_t) std::min<int64_t>(p.rshape[d], 0x7fffffff));
+
+    int V = in.w64 ? 2 : 4;
+    const int64_t vlen = inner ? p.rshape[p.nr - 1] : p.kshape[p.nk - 1];
+    auto classify = [&](const char* base, int dtype, const int64_t* kst, const int64_t* rst) -> int {
+        const int sz = dtype_size(dtype);
+        const int64_t vs = inner ? rst[p.nr - 1] : kst[p.nk - 1];
+        if (vlen == 1 || vs == 0) return MODE_BCAST;
+        if (vs != 1) return MODE_GATHER;
+        const int64_t vb = (int64_t) V * sz;
+        if (((uintptr_t) base) % vb != 0) return MODE_GATHER;
+        for (int d = 0; d < p.nk; ++d)
+            if (!(d == p.nk - 1 && !inner) && (kst[d] * sz) % vb != 0) return MODE_GATHER;
+        for (int d = 0; d < p.nr; ++d)
+            if (!(d == p.nr - 1 && inner) && (rst[d] * sz) % vb != 0) return MODE_GATHER;
+        return MODE_VEC;
+    };
+    bool any_vec = false;
+    for (int k = 0; k < in.n_leaves; ++k) {
+        RdLeaf& L = p.leaf[k];
+        L.ptr = in.leaf_ptr[k];
+        L.dtype = in.leaf_dtype[k];
+        L.mode = classify(L.ptr, L.dtype, L.kstride, L.rstride);
+        any_vec |= L.mode == MODE_VEC;
+    }
+    if (!any_vec) V = 1;
+    p.out_vec_ok = 0;
+    if (!inner && V > 1) {
+        const int osz = dtype_size(p.out_dtype);
+        bool ok = p.out_kstride[p.nk - 1] == 1 && ((uintptr_t) p.out_ptr) % ((int64_t) V * osz) == 0;
+        for (int d = 0; d < p.nk - 1 && ok; ++d) ok = (p.out_kstride[d] * osz) % ((int64_t) V * osz) == 0;
+        p.out_vec_ok = ok;
+    }
+
+    if (in.empty) p.R = 0;
+    // parallelisation
+    const int64_t target_threads = (int64_t) ctx->sm_count * 2048;
+    p.nsplit = 1;
+    if (inner) {
+        const int64_t RL = p.rshape[p.nr - 1];
+        const int64_t vpr = (RL + V - 1) / V;
+        if (vpr > 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "reduced extent too large");
+        p.vpr = (uint32_t) vpr;
+        p.vpr_div = make_fastdiv(p.vpr);
+        p.rvec_total = (p.R / RL) * vpr;
+        if (p.nr > 1 && p.rvec_total >= 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "reduction too large for split axes");
+        int G = 1;
+        while (G < 32 && G < p.rvec_total) G <<= 1;
+        if (p.rvec_total > 32 * 8 && p.K * 32 < target_threads) G = 256;
+        p.G = G;
+        p.chunk = p.rvec_total;
+        if (G == 256 && depth == 0 && p.K * 256 < target_threads && p.rvec_total > 256 * 16) {
+            int64_t want = target_threads / (p.K * 256);
+            int64_t maxsplit = p.rvec_total / (256 * 8);
+            int64_t ns = std::max<int64_t>(1, std::min(want, maxsplit));
+            ns = std::min<int64_t>(ns, 1024);
+            if (ns > 1) {
+                p.chunk = (p.rvec_total + ns - 1) / ns;
+                p.chunk = (p.chunk + 255) / 256 * 256;  // whole block strides
+                p.nsplit = (int) ((p.rvec_total + p.chunk - 1) / p.chunk);
+            }
+        }
+    } else {
+        const int64_t KL = p.kshape[p.nk - 1];
+        const int64_t kvpr = (KL + V - 1) / V;
+        if (kvpr > 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "kept extent too large");
+        p.kvpr = (uint32_t) kvpr;
+        p.kvpr_div = make_fastdiv(p.kvpr);
+        p.kvec_total = (p.K / KL) * kvpr;
+        if (p.kvec_total >= 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "too many outputs");
+        p.chunk = p.R;
+        if (depth == 0 && p.kvec_total < target_threads && p.R > 32) {
+            int64_t want = target_threads / std::max<int64_t>(p.kvec_total, 1);
+            int64_t maxsplit = p.R / 16;
+            int64_t ns = std::max<int64_t>(1, std::min(want, maxsplit));
+            ns = std::min<int64_t>(ns, 4096);
+            if (ns > 1) {
+                p.chunk = (p.R + ns - 1) / ns;
+                p.nsplit = (int) ((p.R + p.chunk - 1) / p.chunk);
+            }
+        }
+    }
+    if (p.nsplit > 1) {
+        void* scratch = nullptr;
+        const size_t bytes = (size_t) p.nsplit * (size_t) p.K * dtype_size(p.acc_rt);
+        XTB_TRY(ensure_scratch(ctx, bytes, &scratch));
+        p.part_ptr = (char*) scratch;
+    }
+    XTB_TRY(run_reduce_kernel(in.prog, p, ctx, inner, in.w64, V));
+    if (p.nsplit > 1) return merge_partials(in, p, ctx, depth);
+    return XTB_OK;
+}
+
+}  // namespace xtb
+
+using namespace xtb;
+
+extern "C" int xtb_reduce(int op, int acc_type, const xtb_program* prog, const xtb_operand* leaves, int ndim,
+                          const int64_t* shape, int n_axes, const int32_t* axes, int keep_dims, const void* initial,
+                          const xtb_operand* out, int allreduce) {
+    if (!prog || !out || (ndim > 0 && !shape)) XTB_FAIL(XTB_ERR_INVALID, "null argument");
+    if (ndim < 0 || ndim > XTB_MAX_DIM) XTB_FAIL(XTB_ERR_INVALID, "rank %d out of range", ndim);
+    if (n_axes < 0 || n_axes > ndim) XTB_FAIL(XTB_ERR_AXIS, "%d axes for rank %d", n_axes, ndim);
+    if (n_axes > 0 && !axes) XTB_FAIL(XTB_ERR_INVALID, "null axes");
+    const int binop = binop_of(op);
+    if (binop < 0) XTB_FAIL(XTB_ERR_INVALID, "unknown reducer %d", op);
+    if (acc_type < XTB_I32 || acc_type > XTB_F64) XTB_FAIL(XTB_ERR_INVALID, "accumulator must be a register type");
+    // xreducer.hpp:336-350
+    for (int i = 1; i < n_axes; ++i) {
+        if (axes[i] < axes[i - 1]) XTB_FAIL(XTB_ERR_AXIS, "Reducing axes should be sorted.");
+        if (axes[i] == axes[i - 1]) XTB_FAIL(XTB_ERR_AXIS, "Reducing axes should not contain duplicates.");
+    }
+    if (n_axes > 0 && (axes[0] < 0 || axes[n_axes - 1] > ndim - 1))
+        XTB_FAIL(XTB_ERR_AXIS, "Axis %d out of bounds for reduction.", axes[n_axes - 1]);
+    int32_t leaf_dt[XTB_MAX_LEAVES];
+    for (int k = 0; k < prog->n_leaves && k < XTB_MAX_LEAVES; ++k) leaf_dt[k] = leaves[k].dtype;
+    int rt = 0;
+    bool w64 = false;
+    XTB_TRY(validate_program(prog, leaf_dt, &rt, &w64));
+    if (dtype_size(acc_type) == 8 || dtype_size(out->dtype) == 8) w64 = true;
+    if (out->dtype < 0 || out->dtype >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "bad out dtype");
+
+    ReducePlanIn in;
+    in.prog = prog;
+    in.n_leaves = prog->n_leaves;
+    Space& s = in.space;
+    s = Space();
+    s.ndim = ndim;
+    s.n_ops = prog->n_leaves + 1;
+    const int OUT = prog->n_leaves;
+    bool red[XTB_MAX_DIM] = {false};
+    for (int i = 0; i < n_axes; ++i) red[axes[i]] = true;
+    // output shape check (shape_computation, xreducer.hpp:190-239)
+    const int out_rank = keep_dims ? ndim : ndim - n_axes;
+    if (out->ndim != out_rank) XTB_FAIL(XTB_ERR_SHAPE, "reducer output has rank %d, expected %d", out->ndim, out_rank);
+    int64_t K = 1, R = 1;
+    for (int d = 0, od = 0; d < ndim; ++d) {
+        if (shape[d] < 0) XTB_FAIL(XTB_ERR_INVALID, "negative extent");
+        s.shape[d] = shape[d];
+        s.reduced[d] = red[d];
+        if (red[d]) {
+            R *= shape[d];
+            if (keep_dims) {
+                if (out->shape[od] != 1) XTB_FAIL(XTB_ERR_SHAPE, "keep_dims output must have extent 1 on axis %d", d);
+                ++od;
+            }
+            s.stride[OUT][d] = 0;
+        } else {
+            K *= shape[d];
+            if (out->shape[od] != shape[d])
+                XTB_FAIL(XTB_ERR_SHAPE, "reducer output extent %lld on dim %d, expected %lld", (long long) out->shape[od], od,
+                         (long long) shape[d]);
+            s.stride[OUT][d] = shape[d] == 1 ? 0 : out->stride[od];
+            ++od;
+        }
+    }
+    for (int k = 0; k < prog->n_leaves; ++k) {
+        char what[32];
+        snprintf(what, sizeof(what), "leaf %d", k);
+        XTB_TRY(align_operand(&leaves[k], ndim, s.shape, s.stride[k], what));
+        in.leaf_ptr[k] = operand_ptr(&leaves[k], dtype_size(leaves[k].dtype));
+        in.leaf_dtype[k] = leaves[k].dtype;
+    }
+    if (K == 0) return XTB_OK;
+    DeviceCtx* ctx;
+    XTB_TRY(get_ctx(&ctx));
+    in.binop = binop;
+    in.acc_rt = acc_type;
+    in.in_rt = rt;
+    in.w64 = w64;
+    in.out_ptr = operand_ptr(out, dtype_size(out->dtype));
+    in.out_dtype = out->dtype;
+    in.has_initial = initial != nullptr;
+    in.initial_bits = 0;
+    if (initial) memcpy(&in.initial_bits, initial, dtype_size(acc_type));
+    in.identity = identity_bits(op, acc_type);
+    if (R == 0) {
+        // zero-size reduction: every output is init (xreducer.hpp:1782-1785); drop the
+        // empty axes so that the kernel loops zero times.
+        for (int d = 0; d < ndim; ++d)
+            if (red[d]) s.shape[d] = 1;
+        in.empty = true;
+    }
+    XTB_TRY(plan_and_launch(in, ctx, 0));
+    if (allreduce) {
+        // out must be dense for the in-place collective
+        XTB_TRY(comm_allreduce(ctx, in.out_ptr, (size_t) K, out->dtype, op));
+    }
+    return XTB_OK;
+}

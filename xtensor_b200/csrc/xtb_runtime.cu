@@ -1,0 +1,430 @@
+// xtb_runtime.cu -- runtime of libxtb200: device contexts and streams, the
+// device-resident storage behind xtb::device_uvector (uvector contract of
+// include/xtensor/containers/xstorage.hpp:33-345: uninitialised contents,
+// resize discards), stream-ordered copies, program validation and the
+// operand canonicaliser used by every compute entry point.
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include "xtb_common.hpp"
+#include "xtb_ops.cuh"
+
+namespace xtb {
+
+// ---- error state -------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local char g_last_kernel[128] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void note_launch(const char* kernel_name, int n) {
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    if (kernel_name) {
+        strncpy(g_last_kernel, kernel_name, sizeof(g_last_kernel) - 1);
+        g_last_kernel[sizeof(g_last_kernel) - 1] = 0;
+    }
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(XTB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return XTB_OK;
+}
+
+// ---- device contexts ---------------------------------------------------------
+static constexpr int kMaxDevices = 16;
+static DeviceCtx g_ctx[kMaxDevices];
+static std::mutex g_ctx_mutex;
+static thread_local int t_device = -1;
+static int g_device_count = -2;  // -2 = not probed
+
+static int probe_devices() {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    if (g_device_count == -2) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            (void) cudaGetLastError();
+            n = 0;
+        }
+        g_device_count = n;
+    }
+    return g_device_count;
+}
+
+static int init_device(int device) {
+    int n = probe_devices();
+    if (n <= 0)
+        XTB_FAIL(XTB_ERR_NO_DEVICE,
+                 "no CUDA device available: libxtb200 has no CPU fallback (hot path is sm_100a only)");
+    if (device < 0) {
+        if (t_device >= 0) device = t_device;
+        else {
+            int cur = 0;
+            XTB_CUDA(cudaGetDevice(&cur));
+            device = cur;
+        }
+    }
+    if (device >= n || device >= kMaxDevices) XTB_FAIL(XTB_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    XTB_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    DeviceCtx& c = g_ctx[device];
+    if (!c.ready) {
+        c.device = device;
+        cudaDeviceProp prop;
+        XTB_CUDA(cudaGetDeviceProperties(&prop, device));
+        c.sm_count = prop.multiProcessorCount;
+        c.l2_bytes = (size_t) prop.l2CacheSize;
+        XTB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+        c.stream = c.own_stream;
+        // caching, stream-ordered allocator: keep freed blocks in the pool
+        cudaMemPool_t pool;
+        XTB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t threshold = UINT64_MAX;
+        XTB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        c.ready = true;
+    }
+    t_device = device;
+    return XTB_OK;
+}
+
+int get_ctx(DeviceCtx** ctx) {
+    if (t_device < 0 || !g_ctx[t_device].ready) XTB_TRY(init_device(-1));
+    else {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != t_device) XTB_CUDA(cudaSetDevice(t_device));
+    }
+    *ctx = &g_ctx[t_device];
+    return XTB_OK;
+}
+
+int ensure_scratch(DeviceCtx* ctx, size_t bytes, void** ptr) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) XTB_CUDA(cudaFreeAsync(ctx->scratch, ctx->stream));
+        size_t want = std::max(bytes, (size_t) 1 << 20);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        XTB_CUDA(cudaMallocAsync(&ctx->scratch, want, ctx->stream));
+        ctx->scratch_bytes = want;
+    }
+    *ptr = ctx->scratch;
+    return XTB_OK;
+}
+
+// ---- canonicaliser -----------------------------------------------------------
+int align_operand(const xtb_operand* op, int ndim, const int64_t* shape, int64_t* stride_out, const char* what) {
+    if (op->ndim < 0 || op->ndim > XTB_MAX_DIM) XTB_FAIL(XTB_ERR_INVALID, "%s: rank %d out of range", what, op->ndim);
+    if (op->ndim > ndim) XTB_FAIL(XTB_ERR_SHAPE, "%s: rank %d exceeds iteration rank %d", what, op->ndim, ndim);
+    if (op->dtype < 0 || op->dtype >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "%s: bad dtype %d", what, op->dtype);
+    const int shift = ndim - op->ndim;
+    for (int d = 0; d < ndim; ++d) {
+        if (d < shift) {
+            stride_out[d] = 0;
+            continue;
+        }
+        const int64_t ext = op->shape[d - shift];
+        if (ext == shape[d]) stride_out[d] = (ext == 1) ? 0 : op->stride[d - shift];
+        else if (ext == 1) stride_out[d] = 0;
+        else
+            XTB_FAIL(XTB_ERR_SHAPE, "%s: extent %lld of dim %d is not broadcastable to %lld", what, (long long) ext,
+                     d - shift, (long long) shape[d]);
+    }
+    return XTB_OK;
+}
+
+void collapse_space(Space* s) {
+    // drop extent-1 dims
+    int w = 0;
+    for (int d = 0; d < s->ndim; ++d) {
+        if (s->shape[d] == 1) continue;
+        s->shape[w] = s->shape[d];
+        s->reduced[w] = s->reduced[d];
+        for (int k = 0; k < s->n_ops; ++k) s->stride[k][w] = s->stride[k][d];
+        ++w;
+    }
+    s->ndim = w;
+    // merge (d, d+1) when stride[d] == shape[d+1] * stride[d+1] for every operand
+    int o = 0;
+    for (int d = 1; d < s->ndim; ++d) {
+        bool ok = s->reduced[o] == s->reduced[d];
+        for (int k = 0; k < s->n_ops && ok; ++k) ok = s->stride[k][o] == s->shape[d] * s->stride[k][d];
+        if (ok) {
+            s->shape[o] *= s->shape[d];
+            for (int k = 0; k < s->n_ops; ++k) s->stride[k][o] = s->stride[k][d];
+        } else {
+            ++o;
+            s->shape[o] = s->shape[d];
+            s->reduced[o] = s->reduced[d];
+            for (int k = 0; k < s->n_ops; ++k) s->stride[k][o] = s->stride[k][d];
+        }
+    }
+    if (s->ndim > 0) s->ndim = o + 1;
+    s->total = 1;
+    for (int d = 0; d < s->ndim; ++d) s->total *= s->shape[d];
+}
+
+void sort_space_by(Space* s, int key) {
+    // stable insertion sort on |stride[key]| descending
+    for (int i = 1; i < s->ndim; ++i) {
+        for (int j = i; j > 0; --j) {
+            int64_t a = s->stride[key][j - 1], b = s->stride[key][j];
+            if (a < 0) a = -a;
+            if (b < 0) b = -b;
+            if (a >= b) break;
+            std::swap(s->shape[j - 1], s->shape[j]);
+            std::swap(s->reduced[j - 1], s->reduced[j]);
+            for (int k = 0; k < s->n_ops; ++k) std::swap(s->stride[k][j - 1], s->stride[k][j]);
+        }
+    }
+}
+
+// ---- program validation --------------------------------------------------------
+static bool is_reg_type(int t) { return t >= XTB_I32 && t <= XTB_F64; }
+static bool is64(int t) { return t == XTB_I64 || t == XTB_U64 || t == XTB_F64; }
+static bool float_only_unary(int op) {
+    return (op >= XTB_OP_EXP && op <= XTB_OP_RINT) || op == XTB_OP_DEG2RAD || op == XTB_OP_RAD2DEG;
+}
+static bool float_only_binary(int op) { return op >= XTB_OP_FMOD && op <= XTB_OP_ATAN2; }
+static bool int_only_binary(int op) {
+    return op == XTB_OP_MOD || (op >= XTB_OP_BOR && op <= XTB_OP_SHR);
+}
+
+int validate_program(const xtb_program* p, const int32_t* leaf_dtypes, int* result_type, bool* needs64) {
+    if (!p) XTB_FAIL(XTB_ERR_INVALID, "null program");
+    if (p->n_insns <= 0 || p->n_insns > XTB_MAX_INSNS) XTB_FAIL(XTB_ERR_INVALID, "program has %d instructions", p->n_insns);
+    if (p->n_leaves < 0 || p->n_leaves > XTB_MAX_LEAVES) XTB_FAIL(XTB_ERR_INVALID, "program has %d leaves", p->n_leaves);
+    if (p->n_imms < 0 || p->n_imms > XTB_MAX_IMMS) XTB_FAIL(XTB_ERR_INVALID, "program has %d immediates", p->n_imms);
+    int st[XTB_MAX_STACK];
+    int n = 0;
+    bool w64 = false;
+    for (int pc = 0; pc < p->n_insns; ++pc) {
+        const xtb_insn in = p->insns[pc];
+        const int op = in.op;
+        if (op == XTB_OP_PUSH) {
+            if (n >= XTB_MAX_STACK) XTB_FAIL(XTB_ERR_INVALID, "insn %d: stack overflow", pc);
+            if (in.src == XTB_SRC_LEAF) {
+                if (in.arg >= p->n_leaves) XTB_FAIL(XTB_ERR_INVALID, "insn %d: leaf %d out of range", pc, in.arg);
+                if (in.type >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "insn %d: bad leaf dtype", pc);
+                if (leaf_dtypes && leaf_dtypes[in.arg] != in.type)
+                    XTB_FAIL(XTB_ERR_INVALID, "insn %d: leaf %d has dtype %d, program says %d", pc, in.arg,
+                             leaf_dtypes[in.arg], in.type);
+                st[n++] = regtype_of(in.type);
+            } else if (in.src == XTB_SRC_IMM) {
+                if (in.arg >= p->n_imms) XTB_FAIL(XTB_ERR_INVALID, "insn %d: imm %d out of range", pc, in.arg);
+                if (!is_reg_type(in.type)) XTB_FAIL(XTB_ERR_INVALID, "insn %d: imm must have a register type", pc);
+                st[n++] = in.type;
+            } else
+                XTB_FAIL(XTB_ERR_INVALID, "insn %d: bad PUSH source", pc);
+            w64 |= is64(st[n - 1]);
+            continue;
+        }
+        if (!is_reg_type(in.type)) XTB_FAIL(XTB_ERR_INVALID, "insn %d: type %d is not a register type", pc, in.type);
+        w64 |= is64(in.type);
+        if (op < XTB_OP_ADD) {  // unary
+            if (op < XTB_OP_CAST || op > XTB_OP_CUBE) XTB_FAIL(XTB_ERR_INVALID, "insn %d: unknown opcode %d", pc, op);
+            if (n < 1) XTB_FAIL(XTB_ERR_INVALID, "insn %d: stack underflow", pc);
+            if (st[n - 1] != in.type)
+                XTB_FAIL(XTB_ERR_INVALID, "insn %d: operand has type %d, insn says %d", pc, st[n - 1], in.type);
+            if (op == XTB_OP_CAST) {
+                if (in.arg >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "insn %d: bad cast target", pc);
+                st[n - 1] = regtype_of(in.arg);
+                w64 |= is64(st[n - 1]);
+            } else if (is_pred_op(op)) {
+                st[n - 1] = XTB_I32;
+            } else {
+                if (float_only_unary(op) && !is_float_type(in.type))
+                    XTB_FAIL(XTB_ERR_INVALID, "insn %d: opcode %d needs a floating type (lowering must cast)", pc, op);
+                if (op == XTB_OP_BITNOT && is_float_type(in.type)) XTB_FAIL(XTB_ERR_INVALID, "insn %d: ~ on float", pc);
+            }
+        } else if (op < XTB_OP_WHERE) {  // binary
+            if (op > XTB_OP_MINIMUM) XTB_FAIL(XTB_ERR_INVALID, "insn %d: unknown opcode %d", pc, op);
+            const int kind = in.src & 3;
+            int ty;
+            if (kind == XTB_SRC_STACK) {
+                if (n < 2) XTB_FAIL(XTB_ERR_INVALID, "insn %d: stack underflow", pc);
+                ty = st[n - 1];
+                --n;
+            } else if (kind == XTB_SRC_LEAF) {
+                if (in.arg >= p->n_leaves) XTB_FAIL(XTB_ERR_INVALID, "insn %d: leaf %d out of range", pc, in.arg);
+                if (!leaf_dtypes) XTB_FAIL(XTB_ERR_INVALID, "insn %d: fused leaf operand needs leaf dtypes", pc);
+                if (n < 1) XTB_FAIL(XTB_ERR_INVALID, "insn %d: stack underflow", pc);
+                if (leaf_dtypes[in.arg] != in.type)
+                    XTB_FAIL(XTB_ERR_INVALID, "insn %d: fused leaf %d must be stored as the insn type", pc, in.arg);
+                ty = in.type;
+            } else if (kind == XTB_SRC_IMM) {
+                if (in.arg >= p->n_imms) XTB_FAIL(XTB_ERR_INVALID, "insn %d: imm %d out of range", pc, in.arg);
+                if (n < 1) XTB_FAIL(XTB_ERR_INVALID, "insn %d: stack underflow", pc);
+                ty = in.type;
+            } else
+                XTB_FAIL(XTB_ERR_INVALID, "insn %d: bad operand source", pc);
+            if (st[n - 1] != in.type || ty != in.type)
+                XTB_FAIL(XTB_ERR_INVALID, "insn %d: operand types (%d,%d) differ from insn type %d", pc, st[n - 1], ty, in.type);
+            if (float_only_binary(op) && !is_float_type(in.type)) XTB_FAIL(XTB_ERR_INVALID, "insn %d: needs floating type", pc);
+            if (int_only_binary(op) && is_float_type(in.type)) XTB_FAIL(XTB_ERR_INVALID, "insn %d: needs integer type", pc);
+            if (is_cmp_op(op)) st[n - 1] = XTB_I32;
+        } else {  // ternary
+            if (op > XTB_OP_CLAMP) XTB_FAIL(XTB_ERR_INVALID, "insn %d: unknown opcode %d", pc, op);
+            if (n < 3) XTB_FAIL(XTB_ERR_INVALID, "insn %d: stack underflow", pc);
+            if (st[n - 1] != in.type || st[n - 2] != in.type) XTB_FAIL(XTB_ERR_INVALID, "insn %d: operand types differ", pc);
+            if (op == XTB_OP_WHERE) {
+                if (st[n - 3] != XTB_I32) XTB_FAIL(XTB_ERR_INVALID, "insn %d: condition must be bool/int", pc);
+            } else if (st[n - 3] != in.type)
+                XTB_FAIL(XTB_ERR_INVALID, "insn %d: operand types differ", pc);
+            n -= 2;
+            st[n - 1] = in.type;
+        }
+    }
+    if (n != 1) XTB_FAIL(XTB_ERR_INVALID, "program leaves %d values on the stack", n);
+    if (result_type) *result_type = st[0];
+    if (needs64) *needs64 = w64;
+    return XTB_OK;
+}
+
+}  // namespace xtb
+
+using namespace xtb;
+
+extern "C" {
+
+int xtb_abi_version(void) { return XTB_ABI_VERSION; }
+
+int xtb_init(int device) { return init_device(device); }
+
+int xtb_device_count(int* count) {
+    if (!count) XTB_FAIL(XTB_ERR_INVALID, "null count");
+    *count = std::max(0, probe_devices());
+    return XTB_OK;
+}
+
+int xtb_sync(void) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    XTB_CUDA(cudaStreamSynchronize(c->stream));
+    return XTB_OK;
+}
+
+const char* xtb_last_error(void) { return g_err; }
+
+int xtb_set_stream(void* cuda_stream) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    c->stream = cuda_stream ? (cudaStream_t) cuda_stream : c->own_stream;
+    return XTB_OK;
+}
+
+void* xtb_get_stream(void) {
+    DeviceCtx* c;
+    if (get_ctx(&c) != XTB_OK) return nullptr;
+    return (void*) c->stream;
+}
+
+int xtb_malloc(size_t bytes, void** ptr) {
+    if (!ptr) XTB_FAIL(XTB_ERR_INVALID, "null ptr");
+    *ptr = nullptr;
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    if (bytes == 0) return XTB_OK;
+    XTB_CUDA(cudaMallocAsync(ptr, bytes, c->stream));
+    return XTB_OK;
+}
+
+int xtb_free(void* ptr) {
+    if (!ptr) return XTB_OK;
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    XTB_CUDA(cudaFreeAsync(ptr, c->stream));
+    return XTB_OK;
+}
+
+int xtb_memcpy(void* dst, const void* src, size_t bytes, int kind) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    if (bytes == 0) return XTB_OK;
+    cudaMemcpyKind k;
+    switch (kind) {
+        case XTB_H2D: k = cudaMemcpyHostToDevice; break;
+        case XTB_D2H: k = cudaMemcpyDeviceToHost; break;
+        case XTB_D2D: k = cudaMemcpyDeviceToDevice; break;
+        default: XTB_FAIL(XTB_ERR_INVALID, "bad copy kind %d", kind);
+    }
+    XTB_CUDA(cudaMemcpyAsync(dst, src, bytes, k, c->stream));
+    if (kind == XTB_D2H) XTB_CUDA(cudaStreamSynchronize(c->stream));
+    return XTB_OK;
+}
+
+int xtb_memset(void* dst, int byte, size_t bytes) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    if (bytes == 0) return XTB_OK;
+    XTB_CUDA(cudaMemsetAsync(dst, byte, bytes, c->stream));
+    return XTB_OK;
+}
+
+int xtb_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr) XTB_FAIL(XTB_ERR_INVALID, "null ptr");
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    XTB_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return XTB_OK;
+}
+
+int xtb_host_free(void* ptr) {
+    if (!ptr) return XTB_OK;
+    XTB_CUDA(cudaFreeHost(ptr));
+    return XTB_OK;
+}
+
+int xtb_event_create(void** event) {
+    if (!event) XTB_FAIL(XTB_ERR_INVALID, "null event");
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    cudaEvent_t e;
+    XTB_CUDA(cudaEventCreate(&e));
+    *event = (void*) e;
+    return XTB_OK;
+}
+
+int xtb_event_record(void* event) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    XTB_CUDA(cudaEventRecord((cudaEvent_t) event, c->stream));
+    return XTB_OK;
+}
+
+int xtb_event_elapsed_ms(void* start, void* stop, float* ms) {
+    if (!ms) XTB_FAIL(XTB_ERR_INVALID, "null ms");
+    XTB_CUDA(cudaEventSynchronize((cudaEvent_t) stop));
+    XTB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t) start, (cudaEvent_t) stop));
+    return XTB_OK;
+}
+
+int xtb_event_destroy(void* event) {
+    if (event) XTB_CUDA(cudaEventDestroy((cudaEvent_t) event));
+    return XTB_OK;
+}
+
+int64_t xtb_launch_count(int reset) {
+    int64_t v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+const char* xtb_last_kernel(void) { return g_last_kernel; }
+
+int xtb_program_result_type(const xtb_program* program, const int32_t* leaf_dtypes) {
+    int rt = -1;
+    bool w64 = false;
+    int r = validate_program(program, leaf_dtypes, &rt, &w64);
+    if (r != XTB_OK) return r;
+    return rt;
+}
+
+}  // extern "C"
