@@ -124,7 +124,7 @@ def make_inputs(shape, rank):
     return a, b, d
 
 
-def cpu_baseline_cfg2(sample_rows=24):
+def cpu_baseline_cfg2(sample_rows=512):
     """The reference's CPU evaluation (oracle restatement, or oracle/_ref when built) on a bounded
     sample of cfg2: the first `sample_rows` leading rows.  cfg2 selects the single-threaded
     stepper_assigner in xtensor, so cores = 1."""
@@ -371,11 +371,11 @@ def run_reference(args):
         return
     vals, info = [], None
     for i in range(args.warmup + args.steps):
-        info = cpu_baseline_cfg2(sample_rows=8)
+        info = cpu_baseline_cfg2(sample_rows=64)
         if i >= args.warmup:
             vals.append(info["value"])
     v = float(np.mean(vals))
-    ms = cfg2_bytes((8,) + CFG2["shape"][1:]) / (v * 1e9) * 1e3
+    ms = cfg2_bytes((64,) + CFG2["shape"][1:]) / (v * 1e9) * 1e3
     info["value"] = round(v, 4)
     line = {"impl": "reference", "metric": "effective HBM GB/s, fused broadcast assign (algorithmic bytes / device time)",
             "value": round(v, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

@@ -33,7 +33,7 @@ def both(xt, build, a, mode=0):
 
 def test_reducer_fixture_12_24_732(xt, gpu):
     a = np.ones((3, 2, 4, 6, 5), dtype=F64)
-    a[1, 1, :, 1, 1] = 2
+    a[1, :, 1, :, 1] = 2        # m_a(1, i, 1, j, 1) = 2 (test_xreducer.cpp:77-83)
     for kind in (xt.DeviceArray, xt.HostArray):
         A = kind.from_numpy(a)
         r = xt.evaluate(xt.sum(A, [1, 3])).numpy()

@@ -11,17 +11,22 @@ template <class S, int V> static int launch_interp(const EwParams& p, DeviceCtx*
     return launch_ew_generic<InterpEval, S, V>(p, ctx, "interp");
 }
 
+static bool ew_nd_ok_rank(int nd) { return nd <= 3; }
+
 static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ctx, bool w64, int V) {
     const bool no_static = getenv("XTB_NO_STATIC") != nullptr;  // tests toggle this per call
     if (!no_static && ew_nd_ok(p)) {
         const StaticEntry* e = find_static(prog);
         if (e) {
             const bool k64 = sprogs::is64(*e->prog);
-            if (k64 == w64 && V == (k64 ? 2 : 4)) return e->launch_ew(p, ctx);
+            if (k64 == w64 && V == (k64 ? 2 : 4) && p.out.dtype == sprogs::result_type(*e->prog)) return e->launch_ew(p, ctx);
         }
     }
-    if (w64) return V == 2 ? launch_interp<uint64_t, 2>(p, ctx) : launch_interp<uint64_t, 1>(p, ctx);
-    return V == 4 ? launch_interp<uint32_t, 4>(p, ctx) : launch_interp<uint32_t, 1>(p, ctx);
+    EwParams q = p;  // the generic kernel does not know MODE_LINEAR
+    for (int k = 0; k < q.n_leaves; ++k) if (q.leaf[k].mode == MODE_LINEAR) q.leaf[k].mode = MODE_VEC;
+    if (q.out.mode == MODE_LINEAR) q.out.mode = MODE_VEC;
+    if (w64) return V == 2 ? launch_interp<uint64_t, 2>(q, ctx) : launch_interp<uint64_t, 1>(q, ctx);
+    return V == 4 ? launch_interp<uint32_t, 4>(q, ctx) : launch_interp<uint32_t, 1>(q, ctx);
 }
 
 }  // namespace xtb
@@ -111,6 +116,34 @@ extern "C" int xtb_assign(const xtb_program* prog, const xtb_operand* out, const
         V = 1;
         for (int k = 0; k < prog->n_leaves; ++k)
             if (p.leaf[k].mode == MODE_VEC) p.leaf[k].mode = MODE_GATHER;
+    }
+    // 32-bit offsets + linear shortcut for the rank <= 3 kernels
+    {
+        bool ok32 = s.ndim <= 3;
+        auto fill32 = [&](EwLeaf& L, bool is_out) {
+            int64_t span = 0, dense = 1;
+            bool linear = (L.mode == MODE_VEC);
+            for (int d = s.ndim - 1; d >= 0; --d) {
+                const int64_t st = L.stride[d];
+                span += (st < 0 ? -st : st) * (s.shape[d] - 1);
+                if (st != dense) linear = false;
+                dense *= s.shape[d];
+                if (d < 4) L.s32[d] = (int32_t) st;
+            }
+            if (span >= 0x7fffffffLL) ok32 = false;
+            if (linear && s.total < 0x7fffffffLL) L.mode = MODE_LINEAR;
+            (void) is_out;
+        };
+        if (s.ndim <= 3) {
+            for (int k = 0; k < prog->n_leaves; ++k) fill32(p.leaf[k], false);
+            fill32(p.out, true);
+        }
+        p.idx32 = ok32;
+        if (!ok32 || !ew_nd_ok_rank(s.ndim)) {
+            // the generic kernel does not know MODE_LINEAR
+            for (int k = 0; k < prog->n_leaves; ++k) if (p.leaf[k].mode == MODE_LINEAR) p.leaf[k].mode = MODE_VEC;
+            if (p.out.mode == MODE_LINEAR) p.out.mode = MODE_VEC;
+        }
     }
     const int64_t vpr = (s.shape[inner] + V - 1) / V;
     int64_t rows = 1;

@@ -16,11 +16,14 @@
 
 namespace xtb {
 
-enum LeafMode : int32_t { MODE_VEC = 0, MODE_BCAST = 1, MODE_GATHER = 2 };
+// MODE_LINEAR: MODE_VEC and additionally dense over the whole collapsed space, so the
+// element offset is just the linear index (no coordinate math).
+enum LeafMode : int32_t { MODE_VEC = 0, MODE_BCAST = 1, MODE_GATHER = 2, MODE_LINEAR = 3 };
 
 struct EwLeaf {
     const char* ptr;
     int64_t stride[XTB_MAX_DIM];  // elements, per collapsed dim
+    int32_t s32[4];               // the same for the rank <= 3 kernels (valid when EwParams::idx32)
     int32_t dtype;
     int32_t mode;
 };
@@ -33,38 +36,41 @@ struct EwParams {
     int64_t total_vec;      // number of V-wide vectors (rows * vec_per_row)
     uint32_t vec_per_row;
     uint32_t out_rt;        // register type of the value to store
+    int32_t idx32;          // every operand offset fits in int32: rank <= 3 kernels may run
     FastDiv div_vpr;
     FastDiv div_dim[XTB_MAX_DIM];
     EwLeaf leaf[XTB_MAX_LEAVES];
     EwLeaf out;
 };
 
-// Leaf access for one thread position: coordinates of the row + column of the
-// first element of its vector.
+// Leaf access for one thread position in the rank <= 3 kernels: 32-bit coordinates
+// and offsets (host guarantees every operand spans < 2^31 elements).
 template <int ND> struct EwFetch {
     const EwParams& p;
-    int64_t idx[ND > 1 ? ND - 1 : 1];
-    int64_t col;
+    uint32_t idx[ND > 1 ? ND - 1 : 1];  // outer coordinates
+    uint32_t col;                       // first inner-dim element of this thread's vector
+    uint32_t lin;                       // linear element index of that element
     int nvalid;
 
-    XTB_DEV int64_t offset_of(const EwLeaf& L) const {
-        int64_t off = col * L.stride[ND - 1];
+    XTB_DEV int32_t offset_of(const EwLeaf& L) const {
+        if (L.mode == MODE_LINEAR) return (int32_t) lin;
+        int32_t off = (int32_t) col * L.s32[ND - 1];
 #pragma unroll
-        for (int d = 0; d < ND - 1; ++d) off += idx[d] * L.stride[d];
+        for (int d = 0; d < ND - 1; ++d) off += (int32_t) idx[d] * L.s32[d];
         return off;
     }
     template <class S, int V> XTB_DEV void load(int k, int dt, S (&x)[V]) const {
         const EwLeaf& L = p.leaf[k];
         const int sz = dtype_size(dt);
-        const char* ptr = L.ptr + offset_of(L) * sz;
-        if (L.mode == MODE_BCAST) {
+        const char* ptr = L.ptr + (int64_t) offset_of(L) * sz;
+        if ((L.mode == MODE_VEC || L.mode == MODE_LINEAR) && nvalid == V) {
+            load_vec<S, V>(ptr, dt, x);
+        } else if (L.mode == MODE_BCAST) {
             S s = load_elem<S>(ptr, dt);
 #pragma unroll
             for (int v = 0; v < V; ++v) x[v] = s;
-        } else if (L.mode == MODE_VEC && nvalid == V) {
-            load_vec<S, V>(ptr, dt, x);
         } else {
-            const int64_t step = L.stride[ND - 1] * sz;
+            const int64_t step = (int64_t) L.s32[ND - 1] * sz;
 #pragma unroll
             for (int v = 0; v < V; ++v) x[v] = (v < nvalid) ? load_elem<S>(ptr + v * step, dt) : S(0);
         }
@@ -103,6 +109,7 @@ struct EwFetchN {
 
 struct InterpEval {
     static constexpr int kUnroll = 1;
+    static constexpr int kResultType = -1;  // run-time (EwParams::out_rt)
     template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
         interpret<S, V>(prog, f, r);
     }
@@ -110,6 +117,7 @@ struct InterpEval {
 // Tbl: struct with a static constexpr array `progs` of SProg; ID indexes it.
 template <class Tbl, int ID> struct StaticEval {
     static constexpr int kUnroll = 4;
+    static constexpr int kResultType = sprogs::result_type(Tbl::progs[ID]);
     template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
         eval_static<Tbl, ID, S, V>(prog.imms, f, r);
     }
@@ -131,21 +139,40 @@ XTB_DEV void ew_store(const EwParams& p, const Fetch& f, const S (&r)[V]) {
     }
 }
 
+// Rank <= 3 kernel for compile-time programs: the output dtype equals the program's
+// result type (host checks), so the store is a plain vector store.
+template <int RT, class S, int V, int ND>
+XTB_DEV void ew_store_static(const EwParams& p, const EwFetch<ND>& f, const S (&r)[V]) {
+    const EwLeaf& O = p.out;
+    constexpr int sz = dtype_size(RT);
+    char* ptr = (char*) O.ptr + (int64_t) f.offset_of(O) * sz;
+    if ((O.mode == MODE_VEC || O.mode == MODE_LINEAR) && f.nvalid == V) {
+        store_vec<S, V>(ptr, RT, RT, r);
+    } else {
+        const int64_t step = (int64_t) O.s32[ND - 1] * sz;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (v < f.nvalid) store_elem<S>(ptr + v * step, RT, RT, r[v]);
+    }
+}
+
 // One thread evaluates ITEMS vectors of V consecutive inner-dim elements; within
 // a block consecutive threads take consecutive vectors (coalesced 128-bit access).
 template <class Eval, class S, int V, int ND, int ITEMS>
 __global__ void __launch_bounds__(256) k_ew(const __grid_constant__ EwParams p) {
-    const int64_t inner = p.shape[ND - 1];
+    const uint32_t inner = (uint32_t) p.shape[ND - 1];
+    const uint32_t total = (uint32_t) p.total_vec;
     const uint32_t base = blockIdx.x * (256u * ITEMS) + threadIdx.x;
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const uint32_t vec = base + it * 256u;
-        if ((int64_t) vec >= p.total_vec) break;
-        EwFetch<ND> f{p, {0}, 0, V};
+        if (vec >= total) break;
+        EwFetch<ND> f{p, {0}, 0, 0, V};
         uint32_t cv = vec;
         if constexpr (ND > 1) {
             uint32_t row = fd_div(vec, p.div_vpr);
             cv = vec - row * p.vec_per_row;
+            f.lin = row * inner + cv * V;
 #pragma unroll
             for (int d = ND - 2; d >= 0; --d) {
                 if (d == 0) {
@@ -156,13 +183,15 @@ __global__ void __launch_bounds__(256) k_ew(const __grid_constant__ EwParams p) 
                     row = q;
                 }
             }
+        } else {
+            f.lin = vec * V;
         }
-        f.col = (int64_t) cv * V;
-        const int64_t rem = inner - f.col;
-        f.nvalid = rem < V ? (int) rem : V;
+        f.col = cv * V;
+        const uint32_t rem = inner - f.col;
+        f.nvalid = rem < (uint32_t) V ? (int) rem : V;
         S r[V];
         Eval::template run<S, V>(p.prog, f, r);
-        ew_store<S, V>(p, f, r);
+        ew_store_static<Eval::kResultType, S, V, ND>(p, f, r);
     }
 }
 
@@ -207,7 +236,7 @@ static int launch_ew_nd(const EwParams& p, DeviceCtx* ctx, const char* evname) {
     note_launch(name);
     return check_launch(name);
 }
-static inline bool ew_nd_ok(const EwParams& p) { return p.ndim <= 3 && p.total_vec < (int64_t) 0x7fffffff; }
+static inline bool ew_nd_ok(const EwParams& p) { return p.ndim <= 3 && p.idx32 && p.total_vec < (int64_t) 0x7fffffff; }
 
 // Any rank / any size.
 template <class Eval, class S, int V>

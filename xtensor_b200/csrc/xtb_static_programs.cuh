@@ -40,6 +40,27 @@ constexpr bool is64(const SP& p) {
     return false;
 }
 
+// register type of the value a program leaves on the stack
+constexpr int result_type(const SP& p) {
+    int st[XTB_MAX_STACK + 1] = {0};
+    int n = 0;
+    for (int i = 0; i < p.n; ++i) {
+        const SInsn in = p.ins[i];
+        if (in.op == XTB_OP_PUSH) st[n++] = (in.src == XTB_SRC_LEAF) ? regtype_of(in.type) : in.type;
+        else if (in.op < XTB_OP_ADD) {
+            if (in.op == XTB_OP_CAST) st[n - 1] = regtype_of(in.arg);
+            else if (is_pred_op(in.op)) st[n - 1] = XTB_I32;
+        } else if (in.op < XTB_OP_WHERE) {
+            if ((in.src & 3) == XTB_SRC_STACK) --n;
+            st[n - 1] = is_cmp_op(in.op) ? (int) XTB_I32 : in.type;
+        } else {
+            n -= 2;
+            st[n - 1] = in.type;
+        }
+    }
+    return st[0];
+}
+
 #define XTB_SP_TYPED(NAME, T)                                                                      \
     /* out = a */                                                                                   \
     inline constexpr SP copy_##NAME = make({push_leaf(0, T)}, 1, 0);                                \

@@ -347,7 +347,7 @@ class HostArray(Array):
 
     @staticmethod
     def from_numpy(a: np.ndarray) -> "HostArray":
-        a = np.ascontiguousarray(a)
+        a = np.asarray(a, order="C")
         return HostArray(a.shape, compute_strides(a.shape), 0, DT_OF[a.dtype], a.reshape(-1).copy())
 
     @staticmethod
@@ -397,7 +397,7 @@ class DeviceArray(Array):
 
     @staticmethod
     def from_numpy(a: np.ndarray) -> "DeviceArray":
-        a = np.ascontiguousarray(a)
+        a = np.asarray(a, order="C")
         d = DeviceArray.empty(a.shape, DT_OF[a.dtype])
         if a.nbytes:
             capi.check(capi.lib().xtb_memcpy(C.c_void_p(d.owner.ptr), C.c_void_p(a.ctypes.data), a.nbytes, capi.H2D))
