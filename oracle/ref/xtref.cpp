@@ -1,0 +1,291 @@
+// xtref.cpp -- C entry points over the REAL reference (xtensor 0.27.1 headers under
+// /root/reference/include, compiled through the xtl stand-in oracle/xtl_shim).
+// TEST INFRASTRUCTURE: validates the restatement oracle (oracle/xtb_oracle.cpp),
+// generates tests/golden/*, and is the timed CPU baseline of bench.py
+// (cpu_baseline.kind = "reference").  Nothing here is product code and no reference
+// source is copied: this file only *calls* xtensor's public API on adapted host buffers.
+//
+// Built twice by oracle/ref/Makefile into oracle/_ref/:
+//   libxtref.so      -O2 -ffp-contract=off              parity (no FMA contraction)
+//   libxtref_fast.so -O3 -march=x86-64-v3 -fopenmp -DXTENSOR_USE_OPENMP
+//                    the reference's own threaded loops (xassign.hpp:750-767, 817-825,
+//                    1148-1205), compiler auto-vectorisation instead of xsimd
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <xtensor/containers/xadapt.hpp>
+#include <xtensor/containers/xarray.hpp>
+#include <xtensor/containers/xtensor.hpp>
+#include <xtensor/core/xeval.hpp>
+#include <xtensor/core/xmath.hpp>
+#include <xtensor/core/xnoalias.hpp>
+#include <xtensor/misc/xmanipulation.hpp>
+#include <xtensor/reducers/xaccumulator.hpp>
+#include <xtensor/reducers/xreducer.hpp>
+#include <xtensor/views/xbroadcast.hpp>
+#include <xtensor/views/xstrided_view.hpp>
+#include <xtensor/views/xview.hpp>
+
+namespace
+{
+    using shape_t = std::vector<std::size_t>;
+    shape_t mk_shape(int nd, const int64_t* s) { return shape_t(s, s + nd); }
+    std::size_t count(const shape_t& s) { std::size_t n = 1; for (auto e : s) n *= e; return n; }
+
+    template <class T> auto in_arr(const void* p, const shape_t& s)
+    {
+        return xt::adapt(static_cast<const T*>(p), count(s), xt::no_ownership(), s);
+    }
+    template <class T> auto out_arr(void* p, const shape_t& s)
+    {
+        return xt::adapt(static_cast<T*>(p), count(s), xt::no_ownership(), s);
+    }
+    thread_local std::string g_err;
+}
+
+extern "C"
+{
+    const char* xtref_last_error() { return g_err.c_str(); }
+    int xtref_openmp()
+    {
+#ifdef XTENSOR_USE_OPENMP
+        return 1;
+#else
+        return 0;
+#endif
+    }
+
+    // ---- BASELINE configs ---------------------------------------------------------------
+    // cfg1: xt::noalias(c) = a + b on xtensor<double,1>
+    void xtref_cfg1_add_f64(const double* a, const double* b, double* c, int64_t n)
+    {
+        shape_t s{(std::size_t) n};
+        auto A = in_arr<double>(a, s); auto B = in_arr<double>(b, s); auto C = out_arr<double>(c, s);
+        xt::noalias(C) = A + B;
+    }
+    // cfg2: c(n0,n1,n2) = sin(a) * b(1,n1,1) + 2.0f * d
+    void xtref_cfg2_f32(const float* a, const float* b, const float* d, float* c, int64_t n0, int64_t n1, int64_t n2)
+    {
+        shape_t s{(std::size_t) n0, (std::size_t) n1, (std::size_t) n2}, sb{1, (std::size_t) n1, 1};
+        auto A = in_arr<float>(a, s); auto B = in_arr<float>(b, sb); auto D = in_arr<float>(d, s); auto C = out_arr<float>(c, s);
+        xt::noalias(C) = xt::sin(A) * B + 2.0f * D;
+    }
+    // cfg4: out(n,n) = transpose(a(n,n)) + view(b(2n,n), range(0,_,2), all())
+    void xtref_cfg4_f64(const double* a, const double* b, double* out, int64_t n)
+    {
+        shape_t s{(std::size_t) n, (std::size_t) n}, sb{(std::size_t) (2 * n), (std::size_t) n};
+        auto A = in_arr<double>(a, s); auto B = in_arr<double>(b, sb); auto O = out_arr<double>(out, s);
+        xt::noalias(O) = xt::transpose(A) + xt::view(B, xt::range(0, xt::placeholders::_, 2), xt::all());
+    }
+    // cfg5 map: out(r,c) = exp(a - m(c))
+    void xtref_cfg5_exp_sub_f32(const float* a, const float* m, float* out, int64_t rows, int64_t cols)
+    {
+        shape_t s{(std::size_t) rows, (std::size_t) cols}, sm{(std::size_t) cols};
+        auto A = in_arr<float>(a, s); auto M = in_arr<float>(m, sm); auto O = out_arr<float>(out, s);
+        xt::noalias(O) = xt::exp(A - M);
+    }
+    // benchmark_assign: res = 3.0 * x - 2.0 * y
+    void xtref_axmby_f64(const double* x, const double* y, double* r, int64_t n0, int64_t n1)
+    {
+        shape_t s{(std::size_t) n0, (std::size_t) n1};
+        auto X = in_arr<double>(x, s); auto Y = in_arr<double>(y, s); auto R = out_arr<double>(r, s);
+        xt::noalias(R) = 3.0 * X - 2.0 * Y;
+    }
+
+    // ---- generic broadcast add: out = a + b with arbitrary (broadcastable) shapes ----------
+    int xtref_bcast_add_f64(const double* a, int nda, const int64_t* sa, const double* b, int ndb, const int64_t* sb,
+                            double* out, int ndo, const int64_t* so)
+    {
+        try
+        {
+            auto A = in_arr<double>(a, mk_shape(nda, sa)); auto B = in_arr<double>(b, mk_shape(ndb, sb));
+            xt::xarray<double> r = A + B;
+            if (r.dimension() != (std::size_t) ndo) { g_err = "rank mismatch"; return -2; }
+            for (int d = 0; d < ndo; ++d) if ((int64_t) r.shape()[d] != so[d]) { g_err = "shape mismatch"; return -2; }
+            std::copy(r.begin(), r.end(), out);
+            return 0;
+        }
+        catch (std::exception& e) { g_err = e.what(); return -2; }
+    }
+
+    // ---- unary / binary functors on 1-D buffers -----------------------------------------------
+#define XTREF_UN(NAME, EXPR)                                                                  \
+    if (name == #NAME) { xt::noalias(O) = EXPR; return 0; }
+    extern "C++"
+    {
+        template <class T> int unary_impl(const std::string& name, const void* in, void* out, int64_t n)
+        {
+            shape_t s{(std::size_t) n};
+            auto A = in_arr<T>(in, s); auto O = out_arr<T>(out, s);
+            XTREF_UN(abs, xt::abs(A)) XTREF_UN(exp, xt::exp(A)) XTREF_UN(exp2, xt::exp2(A)) XTREF_UN(expm1, xt::expm1(A))
+            XTREF_UN(log, xt::log(A)) XTREF_UN(log10, xt::log10(A)) XTREF_UN(log2, xt::log2(A)) XTREF_UN(log1p, xt::log1p(A))
+            XTREF_UN(sqrt, xt::sqrt(A)) XTREF_UN(cbrt, xt::cbrt(A)) XTREF_UN(sin, xt::sin(A)) XTREF_UN(cos, xt::cos(A))
+            XTREF_UN(tan, xt::tan(A)) XTREF_UN(asin, xt::asin(A)) XTREF_UN(acos, xt::acos(A)) XTREF_UN(atan, xt::atan(A))
+            XTREF_UN(sinh, xt::sinh(A)) XTREF_UN(cosh, xt::cosh(A)) XTREF_UN(tanh, xt::tanh(A)) XTREF_UN(asinh, xt::asinh(A))
+            XTREF_UN(acosh, xt::acosh(A)) XTREF_UN(atanh, xt::atanh(A)) XTREF_UN(erf, xt::erf(A)) XTREF_UN(erfc, xt::erfc(A))
+            XTREF_UN(tgamma, xt::tgamma(A)) XTREF_UN(lgamma, xt::lgamma(A)) XTREF_UN(ceil, xt::ceil(A)) XTREF_UN(floor, xt::floor(A))
+            XTREF_UN(trunc, xt::trunc(A)) XTREF_UN(round, xt::round(A)) XTREF_UN(nearbyint, xt::nearbyint(A)) XTREF_UN(rint, xt::rint(A))
+            XTREF_UN(sign, xt::sign(A)) XTREF_UN(deg2rad, xt::deg2rad(A)) XTREF_UN(rad2deg, xt::rad2deg(A))
+            XTREF_UN(square, xt::square(A)) XTREF_UN(cube, xt::cube(A)) XTREF_UN(neg, -A)
+            g_err = "unknown unary " + name;
+            return -1;
+        }
+    }
+    int xtref_unary(const char* name, int is_f64, const void* in, void* out, int64_t n)
+    {
+        return is_f64 ? unary_impl<double>(name, in, out, n) : unary_impl<float>(name, in, out, n);
+    }
+    extern "C++"
+    {
+        template <class T> int binary_impl(const std::string& name, const void* a, const void* b, void* out, int64_t n)
+        {
+            shape_t s{(std::size_t) n};
+            auto A = in_arr<T>(a, s); auto B = in_arr<T>(b, s); auto O = out_arr<T>(out, s);
+            XTREF_UN(add, A + B) XTREF_UN(sub, A - B) XTREF_UN(mul, A * B) XTREF_UN(div, A / B)
+            XTREF_UN(fmod, xt::fmod(A, B)) XTREF_UN(remainder, xt::remainder(A, B)) XTREF_UN(fmax, xt::fmax(A, B))
+            XTREF_UN(fmin, xt::fmin(A, B)) XTREF_UN(fdim, xt::fdim(A, B)) XTREF_UN(pow, xt::pow(A, B))
+            XTREF_UN(hypot, xt::hypot(A, B)) XTREF_UN(atan2, xt::atan2(A, B)) XTREF_UN(maximum, xt::maximum(A, B))
+            XTREF_UN(minimum, xt::minimum(A, B))
+            XTREF_UN(where_gt, xt::where(A > B, A, B * T(0.5)))
+            XTREF_UN(clip_fma, xt::clip(A, T(-1), T(1)) + xt::fma(A, B, A))
+            g_err = "unknown binary " + name;
+            return -1;
+        }
+    }
+    int xtref_binary(const char* name, int is_f64, const void* a, const void* b, void* out, int64_t n)
+    {
+        return is_f64 ? binary_impl<double>(name, a, b, out, n) : binary_impl<float>(name, a, b, out, n);
+    }
+    // integer expression of tests/test_gpu_assign.py::test_integer_arithmetic_bit_exact; T in, promoted out
+    extern "C++"
+    {
+        template <class T, class R> void int_expr_impl(const void* a, const void* b, void* out, int64_t n)
+        {
+            shape_t s{(std::size_t) n};
+            auto A = in_arr<T>(a, s); auto B = in_arr<T>(b, s); auto O = out_arr<R>(out, s);
+            xt::noalias(O) = (A + B) * A - (A / B) + (A % B) + (A & B) - (A | B) + (A ^ B);
+        }
+    }
+    int xtref_int_expr(int dtype, const void* a, const void* b, void* out, int64_t n)
+    {
+        switch (dtype)
+        {
+            case 1: int_expr_impl<int8_t, int>(a, b, out, n); return 0;
+            case 2: int_expr_impl<uint8_t, int>(a, b, out, n); return 0;
+            case 3: int_expr_impl<int16_t, int>(a, b, out, n); return 0;
+            case 4: int_expr_impl<uint16_t, int>(a, b, out, n); return 0;
+            case 5: int_expr_impl<int32_t, int32_t>(a, b, out, n); return 0;
+            case 6: int_expr_impl<uint32_t, uint32_t>(a, b, out, n); return 0;
+            case 7: int_expr_impl<int64_t, int64_t>(a, b, out, n); return 0;
+            case 8: int_expr_impl<uint64_t, uint64_t>(a, b, out, n); return 0;
+        }
+        return -1;
+    }
+
+    // ---- reducers ---------------------------------------------------------------------------------
+    // op: 0 sum 1 prod 2 amax 3 amin; mode: 0 lazy (assigned through stepper_assigner), 1 immediate
+    extern "C++"
+    {
+        template <class T> int reduce_impl(int op, const void* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes,
+                                           int keep_dims, int mode, void* out)
+        {
+            try
+            {
+                auto A = in_arr<T>(in, mk_shape(nd, shape));
+                std::vector<std::size_t> ax(axes, axes + n_axes);
+                xt::xarray<T> r;
+    #define XTREF_RED(FN)                                                                                          \
+                if (keep_dims) { if (mode) r = FN(A, ax, xt::keep_dims | xt::evaluation_strategy::immediate); else r = FN(A, ax, xt::keep_dims); } \
+                else { if (mode) r = FN(A, ax, xt::evaluation_strategy::immediate); else r = FN(A, ax); }
+                switch (op)
+                {
+                    case 0: XTREF_RED(xt::sum) break;
+                    case 1: XTREF_RED(xt::prod) break;
+                    case 2: XTREF_RED(xt::amax) break;
+                    default: XTREF_RED(xt::amin) break;
+                }
+                std::copy(r.begin(), r.end(), static_cast<T*>(out));
+                return (int) r.size();
+            }
+            catch (std::exception& e) { g_err = e.what(); return -3; }
+        }
+    }
+    int xtref_reduce(int op, int dtype, const void* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes,
+                     int keep_dims, int mode, void* out)
+    {
+        switch (dtype)
+        {
+            case 5: return reduce_impl<int32_t>(op, in, nd, shape, n_axes, axes, keep_dims, mode, out);
+            case 9: return reduce_impl<float>(op, in, nd, shape, n_axes, axes, keep_dims, mode, out);
+            case 10: return reduce_impl<double>(op, in, nd, shape, n_axes, axes, keep_dims, mode, out);
+        }
+        g_err = "unsupported dtype";
+        return -1;
+    }
+    // sum of uint8 / int16 -> int (no overflow, test_xreducer.cpp:471-472)
+    int xtref_sum_u8(const uint8_t* in, int64_t n) { shape_t s{(std::size_t) n}; auto A = in_arr<uint8_t>(in, s); return xt::sum(A)(); }
+
+    // mean: fp32 input -> double result (test_xmath_result_type.cpp:237-238); variance two-pass
+    int xtref_mean_f32(const float* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes, double* out)
+    {
+        auto A = in_arr<float>(in, mk_shape(nd, shape));
+        std::vector<std::size_t> ax(axes, axes + n_axes);
+        xt::xarray<double> r = xt::mean(A, ax);
+        std::copy(r.begin(), r.end(), out);
+        return (int) r.size();
+    }
+    int xtref_mean_f32_f32(const float* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes, float* out)
+    {
+        auto A = in_arr<float>(in, mk_shape(nd, shape));
+        std::vector<std::size_t> ax(axes, axes + n_axes);
+        xt::xarray<float> r = xt::mean<float>(A, ax);
+        std::copy(r.begin(), r.end(), out);
+        return (int) r.size();
+    }
+    int xtref_variance_f64(const double* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes, int ddof, double* out)
+    {
+        auto A = in_arr<double>(in, mk_shape(nd, shape));
+        std::vector<std::size_t> ax(axes, axes + n_axes);
+        xt::xarray<double> r = xt::variance(A, ax, ddof);
+        std::copy(r.begin(), r.end(), out);
+        return (int) r.size();
+    }
+    int xtref_variance_f32_f32(const float* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes, float* out)
+    {
+        auto A = in_arr<float>(in, mk_shape(nd, shape));
+        std::vector<std::size_t> ax(axes, axes + n_axes);
+        xt::xarray<float> r = xt::variance<float>(A, ax);
+        std::copy(r.begin(), r.end(), out);
+        return (int) r.size();
+    }
+
+    // ---- accumulators --------------------------------------------------------------------------------
+    extern "C++"
+    {
+        template <class T, class R> int cumsum_impl(const void* in, int nd, const int64_t* shape, int axis, void* out)
+        {
+            try
+            {
+                auto A = in_arr<T>(in, mk_shape(nd, shape));
+                xt::xarray<R> r;
+                if (axis < 0) r = xt::cumsum(A); else r = xt::cumsum(A, axis);
+                std::copy(r.begin(), r.end(), static_cast<R*>(out));
+                return (int) r.size();
+            }
+            catch (std::exception& e) { g_err = e.what(); return -3; }
+        }
+    }
+    int xtref_cumsum(int dtype, const void* in, int nd, const int64_t* shape, int axis, void* out)
+    {
+        switch (dtype)
+        {
+            case 3: return cumsum_impl<int16_t, int>(in, nd, shape, axis, out);     // short -> int promotion
+            case 5: return cumsum_impl<int32_t, int32_t>(in, nd, shape, axis, out);
+            case 9: return cumsum_impl<float, float>(in, nd, shape, axis, out);
+            case 10: return cumsum_impl<double, double>(in, nd, shape, axis, out);
+        }
+        return -1;
+    }
+}

@@ -735,29 +735,36 @@ def _size(shape):
     return int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
 
 
-def mean(e, axes=None, dtype=None, ddof=0, keep_dims=False):
-    """sum<T>(e, axes) / static_cast<V>(size / result_size), V = double unless T given
-    (core/xmath.hpp:1827-1852).  ddof is subtracted from e.size() first (:1848-1851)."""
-    e = as_expr(e)
-    s = sum(e, axes, keep_dims=keep_dims, dtype=dtype)
-    n_out = _size(s.shape)
+def _mean_divisor(e, s_shape, axes, dtype, ddof):
+    n_out = _size(s_shape)
     vt = F64 if dtype is None else dtype
     if axes is None:
         div = NP_OF[vt](_size(e.shape) - ddof)
     else:
         div = NP_OF[vt]((_size(e.shape) - ddof) // n_out) if n_out else NP_OF[vt](0)
-    return s / Scalar(div, vt)
+    return Scalar(div, vt)
+
+
+def mean(e, axes=None, dtype=None, ddof=0, keep_dims=False):
+    """sum<T>(e, axes) / static_cast<V>(size / result_size), V = double unless T given
+    (core/xmath.hpp:1827-1852).  ddof is subtracted from e.size() first (:1848-1851)."""
+    e = as_expr(e)
+    s = sum(e, axes, keep_dims=keep_dims, dtype=dtype)
+    return s / _mean_divisor(e, s.shape, axes, dtype, ddof)
 
 
 def variance(e, axes=None, dtype=None, ddof=0):
-    """Two-pass, as the reference (core/xmath.hpp:2082-2105): inner_mean evaluated, reshaped
-    with reduced dims = 1, then mean(square(e - mean), axes, ddof)."""
+    """Two-pass, as the reference (core/xmath.hpp:2082-2105): inner_mean =
+    eval(mean<T>(e, axes, immediate)) -- the *immediate* evaluation order --, reshaped with
+    reduced dims = 1, then the lazy mean<T>(square(e - inner_mean), axes, ddof)."""
     e = as_expr(e)
     nd = len(e.shape)
     ax = list(range(nd)) if axes is None else ([axes] if isinstance(axes, (int, np.integer)) else list(axes))
     ax = [a + nd if a < 0 else a for a in ax]
-    inner_mean = evaluate(mean(e, ax, dtype=dtype))
-    keep = [1 if d in ax else s for d, s in enumerate(e.shape)]
+    s = sum(e, ax, dtype=dtype)
+    s_arr = _run_reducer(s, _leaf_kind(e) or DeviceArray, mode=1)
+    inner_mean = evaluate(s_arr / _mean_divisor(e, s.shape, ax, dtype, 0))
+    keep = [1 if d in ax else sh for d, sh in enumerate(e.shape)]
     mrv = inner_mean.reshape_view(keep)
     return mean(square(e - mrv), ax, dtype=dtype, ddof=ddof)
 

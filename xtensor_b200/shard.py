@@ -1,0 +1,77 @@
+"""Leading-axis sharding of the hot path across GPUs (one process per GPU).
+
+The reference has no distributed layer; its own partial -> merge -> finalize contract is
+xblockwise_reducer (reducers/xblockwise_reducer.hpp:154-185, functors
+xblockwise_reducer_functors.hpp:45-260).  Here:
+  * elementwise assignment and reductions over non-sharded axes need no exchange: every
+    rank evaluates its row block with the single-GPU kernels;
+  * a reduction over the sharded axis 0 produces one partial per rank, merged with ONE
+    allreduce (sum / prod / max / min) -- `allreduce` is NCCL through the C ABI on the
+    device (xtb_reduce(..., allreduce=1)), or any callable in tests (gloo on host arrays);
+  * mean finalises after the merge (divide by the GLOBAL count, cf. mean_functor::finalize,
+    xblockwise_reducer_functors.hpp:175-185); variance is the reference's two-pass form with
+    the merged mean broadcast back to every rank.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+from . import expr as xt
+
+
+def row_block(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of this rank's contiguous block of the leading axis (remainder to low ranks)."""
+    base, rem = divmod(n_rows, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_operand(a: xt.Array, out_rows: int, rank: int, world: int) -> xt.Array:
+    """Slice `a` on axis 0 if it spans the sharded axis, else replicate it (broadcast operand)."""
+    if a.ndim == 0 or a.shape[0] != out_rows or out_rows == 1:
+        return a
+    b, e = row_block(out_rows, rank, world)
+    return a[b:e]
+
+
+HostAllreduce = Callable[[np.ndarray, int], np.ndarray]
+
+
+def sharded_reduce(op: int, local: xt.Expr, axes: Sequence[int], global_rows: int, world: int,
+                   host_allreduce: Optional[HostAllreduce] = None, dtype=None) -> xt.Array:
+    """Reduce a row-sharded expression.  `local` is this rank's block; if axis 0 is reduced the
+    per-rank partials are merged by one allreduce, otherwise the result stays sharded."""
+    r = xt.Reducer(op, local, list(axes), acc_dtype=dtype)
+    kind = xt._leaf_kind(local) or xt.DeviceArray
+    crosses = 0 in r.axes and world > 1
+    if kind is xt.DeviceArray:
+        return xt._run_reducer(r, kind, allreduce=crosses)
+    part = xt._run_reducer(r, kind)
+    if crosses:
+        if host_allreduce is None:
+            raise RuntimeError("host arrays need a host_allreduce callable")
+        merged = host_allreduce(part.numpy(), op)
+        return xt.HostArray.from_numpy(merged)
+    return part
+
+
+def sharded_mean(local: xt.Expr, axes: Sequence[int], global_rows: int, world: int,
+                 host_allreduce: Optional[HostAllreduce] = None, dtype=None) -> xt.Array:
+    """mean over `axes` of a row-sharded expression: merged sum / GLOBAL count."""
+    s = sharded_reduce(capi.RED_SUM, local, axes, global_rows, world, host_allreduce, dtype)
+    full_shape = (global_rows,) + tuple(local.shape[1:])
+    n = int(np.prod([full_shape[a] for a in axes], dtype=np.int64))
+    vt = xt.F64 if dtype is None else dtype
+    return xt.evaluate(s / xt.Scalar(xt.NP_OF[vt](n), vt))
+
+
+def sharded_variance(local: xt.Expr, axes: Sequence[int], global_rows: int, world: int,
+                     host_allreduce: Optional[HostAllreduce] = None, dtype=None) -> xt.Array:
+    """Two-pass variance (core/xmath.hpp:2082-2105) on a row-sharded expression."""
+    m = sharded_mean(local, axes, global_rows, world, host_allreduce, dtype)
+    keep = [1 if d in axes else s for d, s in enumerate(local.shape)]
+    mrv = m.reshape_view(keep)
+    return sharded_mean(xt.square(local - mrv), axes, global_rows, world, host_allreduce, dtype)
