@@ -29,49 +29,33 @@ static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ct
     return V == 4 ? launch_interp<uint32_t, 4>(q, ctx) : launch_interp<uint32_t, 1>(q, ctx);
 }
 
-}  // namespace xtb
-
-using namespace xtb;
-
-extern "C" int xtb_assign(const xtb_program* prog, const xtb_operand* out, const xtb_operand* leaves) {
-    if (!prog || !out) XTB_FAIL(XTB_ERR_INVALID, "null argument");
-    if (prog->n_leaves > 0 && !leaves) XTB_FAIL(XTB_ERR_INVALID, "null leaves");
-    if (out->ndim < 0 || out->ndim > XTB_MAX_DIM) XTB_FAIL(XTB_ERR_INVALID, "out rank %d", out->ndim);
-    if (out->dtype < 0 || out->dtype >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "bad out dtype");
-    int32_t leaf_dt[XTB_MAX_LEAVES];
-    for (int k = 0; k < prog->n_leaves && k < XTB_MAX_LEAVES; ++k) leaf_dt[k] = leaves[k].dtype;
-    int rt = 0;
-    bool w64 = false;
-    XTB_TRY(validate_program(prog, leaf_dt, &rt, &w64));
-    if (dtype_size(out->dtype) == 8) w64 = true;
-
-    Space s;
-    s.ndim = out->ndim;
-    s.n_ops = prog->n_leaves + 1;
+static int launch_space(const xtb_program* prog, const Space& s, const char* const* leaf_ptr, const int* leaf_dtype,
+                        char* out_ptr, int out_dtype, int rt, bool w64, DeviceCtx* ctx, int depth) {
     const int OUT = prog->n_leaves;
-    for (int d = 0; d < out->ndim; ++d) {
-        if (out->shape[d] < 0) XTB_FAIL(XTB_ERR_INVALID, "negative extent");
-        s.shape[d] = out->shape[d];
-        s.stride[OUT][d] = out->shape[d] == 1 ? 0 : out->stride[d];
+    // Rank <= 3 kernels use 32-bit offsets: if an operand spans >= 2^31 elements, evaluate the
+    // leading dimension in pieces (pointers advance, descriptors stay the same).
+    if (s.ndim <= 3 && s.shape[0] >= 2 && depth < 16) {
+        bool too_big = s.total >= 0x7fffffffLL;
+        for (int k = 0; k <= prog->n_leaves && !too_big; ++k) {
+            int64_t span = 0;
+            for (int d = 0; d < s.ndim; ++d) span += (s.stride[k][d] < 0 ? -s.stride[k][d] : s.stride[k][d]) * (s.shape[d] - 1);
+            too_big = span >= 0x7fffffffLL;
+        }
+        if (too_big) {
+            const int64_t half = s.shape[0] / 2;
+            for (int piece = 0; piece < 2; ++piece) {
+                Space h = s;
+                h.shape[0] = piece == 0 ? half : s.shape[0] - half;
+                h.total = s.total / s.shape[0] * h.shape[0];
+                const char* lp[XTB_MAX_LEAVES];
+                for (int k = 0; k < prog->n_leaves; ++k)
+                    lp[k] = leaf_ptr[k] + (piece ? half * s.stride[k][0] * dtype_size(leaf_dtype[k]) : 0);
+                char* op = out_ptr + (piece ? half * s.stride[OUT][0] * dtype_size(out_dtype) : 0);
+                XTB_TRY(launch_space(prog, h, lp, leaf_dtype, op, out_dtype, rt, w64, ctx, depth + 1));
+            }
+            return XTB_OK;
+        }
     }
-    for (int k = 0; k < prog->n_leaves; ++k) {
-        char what[32];
-        snprintf(what, sizeof(what), "leaf %d", k);
-        XTB_TRY(align_operand(&leaves[k], s.ndim, s.shape, s.stride[k], what));
-    }
-    for (int d = 0; d < s.ndim; ++d)
-        if (s.shape[d] == 0) return XTB_OK;  // nothing to assign
-    DeviceCtx* ctx;
-    XTB_TRY(get_ctx(&ctx));
-
-    sort_space_by(&s, OUT);
-    collapse_space(&s);
-    if (s.ndim == 0) {  // 0-d / single element
-        s.ndim = 1;
-        s.shape[0] = 1;
-        for (int k = 0; k < s.n_ops; ++k) s.stride[k][0] = 0;
-    }
-
     EwParams p;
     memset(&p, 0, sizeof(p));
     p.prog.n_insns = prog->n_insns;
@@ -99,13 +83,13 @@ extern "C" int xtb_assign(const xtb_program* prog, const xtb_operand* out, const
     };
     for (int k = 0; k < prog->n_leaves; ++k) {
         EwLeaf& L = p.leaf[k];
-        L.dtype = leaves[k].dtype;
-        L.ptr = operand_ptr(&leaves[k], dtype_size(L.dtype));
+        L.dtype = leaf_dtype[k];
+        L.ptr = leaf_ptr[k];
         for (int d = 0; d < s.ndim; ++d) L.stride[d] = s.stride[k][d];
         L.mode = classify(L.ptr, L.dtype, L.stride, false);
     }
-    p.out.dtype = out->dtype;
-    p.out.ptr = operand_ptr(out, dtype_size(out->dtype));
+    p.out.dtype = out_dtype;
+    p.out.ptr = out_ptr;
     for (int d = 0; d < s.ndim; ++d) p.out.stride[d] = s.stride[OUT][d];
     p.out.mode = classify(p.out.ptr, p.out.dtype, p.out.stride, true);
 
@@ -154,4 +138,56 @@ extern "C" int xtb_assign(const xtb_program* prog, const xtb_operand* out, const
     p.div_vpr = make_fastdiv((uint32_t) vpr);
     for (int d = 0; d < s.ndim; ++d) p.div_dim[d] = make_fastdiv((uint32_t) std::min<int64_t>(s.shape[d], 0x7fffffff));
     return dispatch_ew(prog, p, ctx, w64, V);
+}
+
+}  // namespace xtb
+
+using namespace xtb;
+
+extern "C" int xtb_assign(const xtb_program* prog, const xtb_operand* out, const xtb_operand* leaves) {
+    if (!prog || !out) XTB_FAIL(XTB_ERR_INVALID, "null argument");
+    if (prog->n_leaves > 0 && !leaves) XTB_FAIL(XTB_ERR_INVALID, "null leaves");
+    if (out->ndim < 0 || out->ndim > XTB_MAX_DIM) XTB_FAIL(XTB_ERR_INVALID, "out rank %d", out->ndim);
+    if (out->dtype < 0 || out->dtype >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "bad out dtype");
+    int32_t leaf_dt[XTB_MAX_LEAVES];
+    for (int k = 0; k < prog->n_leaves && k < XTB_MAX_LEAVES; ++k) leaf_dt[k] = leaves[k].dtype;
+    int rt = 0;
+    bool w64 = false;
+    XTB_TRY(validate_program(prog, leaf_dt, &rt, &w64));
+    if (dtype_size(out->dtype) == 8) w64 = true;
+
+    Space s;
+    s.ndim = out->ndim;
+    s.n_ops = prog->n_leaves + 1;
+    const int OUT = prog->n_leaves;
+    for (int d = 0; d < out->ndim; ++d) {
+        if (out->shape[d] < 0) XTB_FAIL(XTB_ERR_INVALID, "negative extent");
+        s.shape[d] = out->shape[d];
+        s.stride[OUT][d] = out->shape[d] == 1 ? 0 : out->stride[d];
+    }
+    for (int k = 0; k < prog->n_leaves; ++k) {
+        char what[32];
+        snprintf(what, sizeof(what), "leaf %d", k);
+        XTB_TRY(align_operand(&leaves[k], s.ndim, s.shape, s.stride[k], what));
+    }
+    for (int d = 0; d < s.ndim; ++d)
+        if (s.shape[d] == 0) return XTB_OK;  // nothing to assign
+    DeviceCtx* ctx;
+    XTB_TRY(get_ctx(&ctx));
+
+    sort_space_by(&s, OUT);
+    collapse_space(&s);
+    if (s.ndim == 0) {  // 0-d / single element
+        s.ndim = 1;
+        s.shape[0] = 1;
+        for (int k = 0; k < s.n_ops; ++k) s.stride[k][0] = 0;
+    }
+
+    const char* leaf_ptr[XTB_MAX_LEAVES];
+    int leaf_dtype[XTB_MAX_LEAVES];
+    for (int k = 0; k < prog->n_leaves; ++k) {
+        leaf_dtype[k] = leaves[k].dtype;
+        leaf_ptr[k] = operand_ptr(&leaves[k], dtype_size(leaves[k].dtype));
+    }
+    return launch_space(prog, s, leaf_ptr, leaf_dtype, operand_ptr(out, dtype_size(out->dtype)), out->dtype, rt, w64, ctx, 0);
 }

@@ -110,6 +110,7 @@ struct EwFetchN {
 struct InterpEval {
     static constexpr int kUnroll = 1;
     static constexpr int kResultType = -1;  // run-time (EwParams::out_rt)
+    static constexpr int kLeaves = XTB_MAX_LEAVES;
     template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
         interpret<S, V>(prog, f, r);
     }
@@ -118,6 +119,7 @@ struct InterpEval {
 template <class Tbl, int ID> struct StaticEval {
     static constexpr int kUnroll = 4;
     static constexpr int kResultType = sprogs::result_type(Tbl::progs[ID]);
+    static constexpr int kLeaves = Tbl::progs[ID].n_leaves;
     template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
         eval_static<Tbl, ID, S, V>(prog.imms, f, r);
     }

@@ -240,6 +240,8 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
                 p.chunk = (p.rvec_total + ns - 1) / ns;
                 p.chunk = (p.chunk + 255) / 256 * 256;  // whole block strides
                 p.nsplit = (int) ((p.rvec_total + p.chunk - 1) / p.chunk);
+                const int q = 16 / dtype_size(p.acc_rt);
+                p.nsplit = (p.nsplit + q - 1) / q * q;
             }
         }
     } else {
@@ -259,6 +261,10 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
             if (ns > 1) {
                 p.chunk = (p.R + ns - 1) / ns;
                 p.nsplit = (int) ((p.R + p.chunk - 1) / p.chunk);
+                // the merge pass reads partials[K][nsplit] with 128-bit loads: keep rows 16-byte multiples
+                // (trailing empty splits write the identity)
+                const int q = 16 / dtype_size(p.acc_rt);
+                p.nsplit = (p.nsplit + q - 1) / q * q;
             }
         }
     }

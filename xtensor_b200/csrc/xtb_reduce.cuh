@@ -58,39 +58,54 @@ struct RdParams {
     int64_t kvec_total;
 };
 
-// position of one thread: kept coords + reduced coords (+ column along the vector dim)
-struct RdFetch {
+// Leaf access of one thread.  The kept part of every leaf's offset is folded into a
+// per-leaf base pointer once per output (or once per thread in the outer kernel); the
+// loops over the reduced dims then only add `reduced index * stride`.
+// NL = number of leaves known at compile time (static programs) or XTB_MAX_LEAVES.
+template <int NL> struct RdFetch {
     const RdParams& p;
-    int64_t koff_idx[XTB_MAX_DIM];  // kept coordinates
-    int64_t ridx[XTB_MAX_DIM];      // reduced coordinates
-    int64_t col;                    // first element along the vector dim
+    const char* cur[NL];   // address of the current vector of each leaf
     int nvalid;
     bool vec_is_reduced;
 
-    XTB_DEV int64_t offset_of(const RdLeaf& L) const {
-        int64_t off = 0;
-        for (int d = 0; d < p.nk; ++d) off += koff_idx[d] * L.kstride[d];
-        for (int d = 0; d < p.nr; ++d) off += ridx[d] * L.rstride[d];
-        return off;
-    }
     template <class S, int V> XTB_DEV void load(int k, int dt, S (&x)[V]) const {
         const RdLeaf& L = p.leaf[k];
         const int sz = dtype_size(dt);
-        const int64_t vstride = vec_is_reduced ? L.rstride[p.nr - 1] : L.kstride[p.nk - 1];
-        const char* ptr = L.ptr + (offset_of(L) + col * vstride) * sz;
-        if (L.mode == MODE_BCAST) {
+        const char* ptr = cur[k];
+        if (L.mode == MODE_VEC && nvalid == V) {
+            load_vec<S, V>(ptr, dt, x);
+        } else if (L.mode == MODE_BCAST) {
             S s = load_elem<S>(ptr, dt);
 #pragma unroll
             for (int v = 0; v < V; ++v) x[v] = s;
-        } else if (L.mode == MODE_VEC && nvalid == V) {
-            load_vec<S, V>(ptr, dt, x);
         } else {
-            const int64_t step = vstride * sz;
+            const int64_t step = (vec_is_reduced ? L.rstride[p.nr - 1] : L.kstride[p.nk - 1]) * sz;
 #pragma unroll
             for (int v = 0; v < V; ++v) x[v] = (v < nvalid) ? load_elem<S>(ptr + v * step, dt) : S(0);
         }
     }
 };
+
+// element offset of kept position `ko` (row-major over the kept dims) for one stride table
+XTB_DEV int64_t rd_kept_offset(const RdParams& p, uint32_t ko, const int64_t* kstride) {
+    int64_t off = 0;
+    for (int d = p.nk - 1; d > 0; --d) {
+        const uint32_t q = fd_div(ko, p.kdiv[d]);
+        off += (int64_t) (ko - q * (uint32_t) p.kshape[d]) * kstride[d];
+        ko = q;
+    }
+    return off + (int64_t) ko * kstride[0];
+}
+// element offset of reduced position `r` over the first n reduced dims
+XTB_DEV int64_t rd_reduced_offset(const RdParams& p, uint32_t r, int n, const int64_t* rstride) {
+    int64_t off = 0;
+    for (int d = n - 1; d > 0; --d) {
+        const uint32_t q = fd_div(r, p.rdiv[d]);
+        off += (int64_t) (r - q * (uint32_t) p.rshape[d]) * rstride[d];
+        r = q;
+    }
+    return off + (int64_t) r * rstride[0];
+}
 
 // accumulate policies: run-time (interpreter) and compile-time (static programs)
 struct DynAcc {
@@ -108,13 +123,9 @@ template <int BINOP, int ACC_RT> struct StaticAcc {
     }
 };
 
-template <class S> XTB_DEV void rd_decompose(uint32_t lin, int n, const int64_t* shape, const FastDiv* div, int64_t* idx) {
-    for (int d = n - 1; d > 0; --d) {
-        const uint32_t q = fd_div(lin, div[d]);
-        idx[d] = lin - q * (uint32_t) shape[d];
-        lin = q;
-    }
-    idx[0] = lin;
+template <class S> XTB_DEV S shfl_xor(S v, int o) {
+    if constexpr (sizeof(S) == 8) return (S) __shfl_xor_sync(0xffffffffu, (unsigned long long) v, o);
+    else return (S) __shfl_xor_sync(0xffffffffu, v, o);
 }
 
 // final value -> (merge initial) -> cast -> store
@@ -127,113 +138,174 @@ template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S 
     store_elem<S>(dst, p.out_dtype, p.acc_rt, a[0]);
 }
 
-// ---- innermost dim reduced ------------------------------------------------------
+// one lane's share of the reduced elements of output `ko`: vectors j = jbeg + lane, += stride
+template <class Eval, class Acc, class S, int V, int NL>
+XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t jend, int lane, int stride) {
+    RdFetch<NL> f{p, {nullptr}, V, true};
+    const char* base[NL];
+    int64_t vstep[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        if (k < p.n_leaves) {
+            const RdLeaf& L = p.leaf[k];
+            const int sz = dtype_size(L.dtype);
+            base[k] = L.ptr + rd_kept_offset(p, ko, L.kstride) * sz;
+            vstep[k] = L.rstride[p.nr - 1] * (int64_t) (V * sz);
+        }
+    }
+    S acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = (S) p.identity_bits;
+    const int64_t RL = p.rshape[p.nr - 1];
+    for (int64_t j = jbeg + lane; j < jend; j += stride) {
+        int64_t cv = j;
+        if (p.nr > 1) {
+            const uint32_t ro = fd_div((uint32_t) j, p.vpr_div);
+            cv = j - (int64_t) ro * p.vpr;
+#pragma unroll
+            for (int k = 0; k < NL; ++k)
+                if (k < p.n_leaves)
+                    f.cur[k] = base[k] + rd_reduced_offset(p, ro, p.nr - 1, p.leaf[k].rstride) * dtype_size(p.leaf[k].dtype) + cv * vstep[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NL; ++k)
+                if (k < p.n_leaves) f.cur[k] = base[k] + cv * vstep[k];
+        }
+        const int64_t rem = RL - cv * V;
+        f.nvalid = rem < V ? (int) rem : V;
+        S x[V];
+        Eval::template run<S, V>(p.prog, f, x);
+        Acc::template cast_in<S, V>(p, x);
+        if (f.nvalid < V) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (v >= f.nvalid) x[v] = (S) p.identity_bits;
+        }
+        Acc::template step<S, V>(p, acc, x);
+    }
+    S r[1] = {acc[0]};
+#pragma unroll
+    for (int v = 1; v < V; ++v) {
+        S y[1] = {acc[v]};
+        Acc::template step<S, 1>(p, r, y);
+    }
+    return r[0];
+}
+
+// ---- innermost dim reduced, G <= 32 lanes per output ---------------------------------
+// A warp produces 32 consecutive outputs per round: its 32/G groups each reduce G outputs
+// one after the other (output g*G + it in iteration it), lane g*G + it keeps that result,
+// so the round ends with ONE coalesced store of 32 results.
 template <class Eval, class Acc, class S, int V>
-__global__ void __launch_bounds__(256) k_reduce_inner(const __grid_constant__ RdParams p) {
-    __shared__ S smem[8];
+__global__ void __launch_bounds__(256) k_reduce_inner_warp(const __grid_constant__ RdParams p) {
+    constexpr int NL = Eval::kLeaves;
     const int G = p.G;
-    const int tid = threadIdx.x;
-    const int lane_in_group = (G >= 256) ? tid : (tid & (G - 1));
-    const int groups_per_block = (G >= 256) ? 1 : 256 / G;
-    const int group = (G >= 256) ? 0 : tid / G;
+    const int lane = threadIdx.x & 31;
+    const int li = lane & (G - 1);      // lane within its group
+    const int g = lane / G;             // group within the warp
+    const int64_t rounds = (p.K + 31) / 32;
+    const int64_t warp0 = (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t jbeg = (int64_t) blockIdx.y * p.chunk;
     int64_t jend = jbeg + p.chunk;
     if (jend > p.rvec_total) jend = p.rvec_total;
-    const int64_t out_groups = (p.K + groups_per_block - 1) / groups_per_block;
-    for (int64_t gb = blockIdx.x; gb < out_groups; gb += gridDim.x) {
-        const int64_t ko = gb * groups_per_block + group;
-        const bool active = ko < p.K;
-        RdFetch f{p, {0}, {0}, 0, V, true};
-        S acc[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[v] = (S) p.identity_bits;
-        if (active) {
-            rd_decompose<S>((uint32_t) ko, p.nk, p.kshape, p.kdiv, f.koff_idx);
-            const int64_t RL = p.rshape[p.nr - 1];
-            for (int64_t j = jbeg + lane_in_group; j < jend; j += G) {
-                int64_t cv = j;
-                if (p.nr > 1) {
-                    const uint32_t ro = fd_div((uint32_t) j, p.vpr_div);
-                    cv = j - (int64_t) ro * p.vpr;
-                    rd_decompose<S>(ro, p.nr - 1, p.rshape, p.rdiv, f.ridx);
-                }
-                f.col = cv * V;
-                const int64_t rem = RL - f.col;
-                f.nvalid = rem < V ? (int) rem : V;
-                S x[V];
-                Eval::template run<S, V>(p.prog, f, x);
-                Acc::template cast_in<S, V>(p, x);
-                if (f.nvalid < V) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v)
-                        if (v >= f.nvalid) x[v] = (S) p.identity_bits;
-                }
-                Acc::template step<S, V>(p, acc, x);
+    for (int64_t round = warp0; round < rounds; round += (int64_t) gridDim.x * 8) {
+        const int64_t out_base = round * 32;
+        S keep = (S) p.identity_bits;
+#pragma unroll 4
+        for (int it = 0; it < G; ++it) {
+            const int64_t ko = out_base + g * G + it;
+            S r[1] = {(S) p.identity_bits};
+            if (ko < p.K) r[0] = rd_inner_partial<Eval, Acc, S, V, NL>(p, (uint32_t) ko, jbeg, jend, li, G);
+            for (int o = G >> 1; o > 0; o >>= 1) {
+                S y[1] = {shfl_xor<S>(r[0], o)};
+                Acc::template step<S, 1>(p, r, y);
             }
+            if (li == it) keep = r[0];
         }
-        // combine the V lanes of the thread, then the G lanes of the group
-        S r[1] = {acc[0]};
-#pragma unroll
-        for (int v = 1; v < V; ++v) {
-            S y[1] = {acc[v]};
-            Acc::template step<S, 1>(p, r, y);
-        }
-        const int W = G >= 32 ? 32 : G;
-        for (int o = W >> 1; o > 0; o >>= 1) {
-            S y[1];
-            if constexpr (sizeof(S) == 8) y[0] = __shfl_xor_sync(0xffffffffu, (unsigned long long) r[0], o);
-            else y[0] = __shfl_xor_sync(0xffffffffu, r[0], o);
-            Acc::template step<S, 1>(p, r, y);
-        }
-        if (G >= 256) {
-            __syncthreads();
-            if ((tid & 31) == 0) smem[tid >> 5] = r[0];
-            __syncthreads();
-            if (tid < 32) {
-                r[0] = tid < 8 ? smem[tid] : (S) p.identity_bits;
-                for (int o = 4; o > 0; o >>= 1) {
-                    S y[1];
-                    if constexpr (sizeof(S) == 8) y[0] = __shfl_xor_sync(0xffffffffu, (unsigned long long) r[0], o);
-                    else y[0] = __shfl_xor_sync(0xffffffffu, r[0], o);
-                    Acc::template step<S, 1>(p, r, y);
-                }
-            }
-        }
-        if (active && lane_in_group == 0) {
+        const int64_t ko = out_base + lane;
+        if (ko < p.K) {
             if (p.nsplit > 1) {
-                store_elem<S>(p.part_ptr + (ko * p.nsplit + blockIdx.y) * dtype_size(p.acc_rt), p.acc_rt, p.acc_rt, r[0]);
+                store_elem<S>(p.part_ptr + (ko * p.nsplit + blockIdx.y) * dtype_size(p.acc_rt), p.acc_rt, p.acc_rt, keep);
             } else {
-                int64_t off = 0;
-                for (int d = 0; d < p.nk; ++d) off += f.koff_idx[d] * p.out_kstride[d];
-                rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), r[0]);
+                const int64_t off = rd_kept_offset(p, (uint32_t) ko, p.out_kstride);
+                rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), keep);
             }
         }
     }
 }
 
-// ---- innermost dim kept ----------------------------------------------------------
+// ---- innermost dim reduced, one block (256 lanes) per output ----------------------------
+template <class Eval, class Acc, class S, int V>
+__global__ void __launch_bounds__(256) k_reduce_inner_block(const __grid_constant__ RdParams p) {
+    constexpr int NL = Eval::kLeaves;
+    __shared__ S smem[8];
+    const int tid = threadIdx.x;
+    const int64_t jbeg = (int64_t) blockIdx.y * p.chunk;
+    int64_t jend = jbeg + p.chunk;
+    if (jend > p.rvec_total) jend = p.rvec_total;
+    for (int64_t ko = blockIdx.x; ko < p.K; ko += gridDim.x) {
+        S r[1] = {rd_inner_partial<Eval, Acc, S, V, NL>(p, (uint32_t) ko, jbeg, jend, tid, 256)};
+        for (int o = 16; o > 0; o >>= 1) {
+            S y[1] = {shfl_xor<S>(r[0], o)};
+            Acc::template step<S, 1>(p, r, y);
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) smem[tid >> 5] = r[0];
+        __syncthreads();
+        if (tid < 32) {
+            r[0] = tid < 8 ? smem[tid] : (S) p.identity_bits;
+            for (int o = 4; o > 0; o >>= 1) {
+                S y[1] = {shfl_xor<S>(r[0], o)};
+                Acc::template step<S, 1>(p, r, y);
+            }
+            if (tid == 0) {
+                if (p.nsplit > 1) {
+                    store_elem<S>(p.part_ptr + (ko * p.nsplit + blockIdx.y) * dtype_size(p.acc_rt), p.acc_rt, p.acc_rt, r[0]);
+                } else {
+                    const int64_t off = rd_kept_offset(p, (uint32_t) ko, p.out_kstride);
+                    rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), r[0]);
+                }
+            }
+        }
+    }
+}
+
+// ---- innermost dim kept --------------------------------------------------------------------
 template <class Eval, class Acc, class S, int V>
 __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ RdParams p) {
+    constexpr int NL = Eval::kLeaves;
     const int64_t rbeg = (int64_t) blockIdx.y * p.chunk;
     int64_t rend = rbeg + p.chunk;
     if (rend > p.R) rend = p.R;
+    const uint32_t KL = (uint32_t) p.kshape[p.nk - 1];
     for (int64_t t = (int64_t) blockIdx.x * 256 + threadIdx.x; t < p.kvec_total; t += (int64_t) gridDim.x * 256) {
-        RdFetch f{p, {0}, {0}, 0, V, false};
         const uint32_t krow = fd_div((uint32_t) t, p.kvpr_div);
         const uint32_t cv = (uint32_t) t - krow * p.kvpr;
-        // kept coordinates: all but the innermost from krow; innermost coordinate = col
-        if (p.nk > 1) rd_decompose<S>(krow, p.nk - 1, p.kshape, p.kdiv, f.koff_idx);
-        f.koff_idx[p.nk - 1] = 0;
-        f.col = (int64_t) cv * V;
-        const int64_t rem = p.kshape[p.nk - 1] - f.col;
-        f.nvalid = rem < V ? (int) rem : V;
+        const uint32_t col = cv * V;
+        const uint32_t ko0 = krow * KL + col;      // linear kept index of the thread's first output
+        RdFetch<NL> f{p, {nullptr}, V, false};
+        const uint32_t rem = KL - col;
+        f.nvalid = rem < (uint32_t) V ? (int) rem : V;
+        const char* base[NL];
+        int64_t rstep[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            if (k < p.n_leaves) {
+                const RdLeaf& L = p.leaf[k];
+                const int sz = dtype_size(L.dtype);
+                base[k] = L.ptr + rd_kept_offset(p, ko0, L.kstride) * sz;
+                rstep[k] = L.rstride[p.nr - 1] * (int64_t) sz;
+            }
+        }
         S acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = (S) p.identity_bits;
         if (p.nr == 1) {
 #pragma unroll(Eval::kUnroll)
             for (int64_t r = rbeg; r < rend; ++r) {
-                f.ridx[0] = r;
+#pragma unroll
+                for (int k = 0; k < NL; ++k)
+                    if (k < p.n_leaves) f.cur[k] = base[k] + r * rstep[k];
                 S x[V];
                 Eval::template run<S, V>(p.prog, f, x);
                 Acc::template cast_in<S, V>(p, x);
@@ -241,7 +313,10 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
             }
         } else {
             for (int64_t r = rbeg; r < rend; ++r) {
-                rd_decompose<S>((uint32_t) r, p.nr, p.rshape, p.rdiv, f.ridx);
+#pragma unroll
+                for (int k = 0; k < NL; ++k)
+                    if (k < p.n_leaves)
+                        f.cur[k] = base[k] + rd_reduced_offset(p, (uint32_t) r, p.nr, p.leaf[k].rstride) * dtype_size(p.leaf[k].dtype);
                 S x[V];
                 Eval::template run<S, V>(p.prog, f, x);
                 Acc::template cast_in<S, V>(p, x);
@@ -249,18 +324,15 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
             }
         }
         if (p.nsplit > 1) {
-            const int asz = dtype_size(p.acc_rt);
             // partials[K][nsplit]: the merge pass reads each output's partials contiguously
-            const int64_t ko0 = (int64_t) krow * p.kshape[p.nk - 1] + f.col;
-            char* dst = p.part_ptr + (ko0 * p.nsplit + blockIdx.y) * asz;
+            const int asz = dtype_size(p.acc_rt);
+            char* dst = p.part_ptr + ((int64_t) ko0 * p.nsplit + blockIdx.y) * asz;
 #pragma unroll
             for (int v = 0; v < V; ++v)
                 if (v < f.nvalid) store_elem<S>(dst + (int64_t) v * p.nsplit * asz, p.acc_rt, p.acc_rt, acc[v]);
         } else {
-            int64_t off = f.col * p.out_kstride[p.nk - 1];
-            for (int d = 0; d < p.nk - 1; ++d) off += f.koff_idx[d] * p.out_kstride[d];
             const int osz = dtype_size(p.out_dtype);
-            char* dst = p.out_ptr + off * osz;
+            char* dst = p.out_ptr + rd_kept_offset(p, ko0, p.out_kstride) * osz;
             if (p.has_initial) {
                 S b[V];
 #pragma unroll
@@ -282,12 +354,15 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
 template <class Eval, class Acc, class S, int V>
 static int launch_reduce(const RdParams& p, DeviceCtx* ctx, bool inner, const char* evname) {
     char name[96];
-    if (inner) {
-        const int gpb = p.G >= 256 ? 1 : 256 / p.G;
-        const int64_t out_groups = (p.K + gpb - 1) / gpb;
-        dim3 grid((unsigned) std::min<int64_t>(out_groups, (int64_t) ctx->sm_count * 64), (unsigned) p.nsplit);
-        snprintf(name, sizeof(name), "k_reduce_inner<%s,S%d,V%d>[G=%d,split=%d]", evname, (int) sizeof(S) * 8, V, p.G, p.nsplit);
-        k_reduce_inner<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
+    if (inner && p.G <= 32) {
+        const int64_t rounds = (p.K + 31) / 32;
+        dim3 grid((unsigned) std::min<int64_t>((rounds + 7) / 8, (int64_t) ctx->sm_count * 64), (unsigned) p.nsplit);
+        snprintf(name, sizeof(name), "k_reduce_inner_warp<%s,S%d,V%d>[G=%d,split=%d]", evname, (int) sizeof(S) * 8, V, p.G, p.nsplit);
+        k_reduce_inner_warp<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
+    } else if (inner) {
+        dim3 grid((unsigned) std::min<int64_t>(p.K, (int64_t) ctx->sm_count * 64), (unsigned) p.nsplit);
+        snprintf(name, sizeof(name), "k_reduce_inner_block<%s,S%d,V%d>[split=%d]", evname, (int) sizeof(S) * 8, V, p.nsplit);
+        k_reduce_inner_block<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
     } else {
         const int64_t blocks = (p.kvec_total + 255) / 256;
         dim3 grid((unsigned) std::min<int64_t>(blocks, (int64_t) ctx->sm_count * 64), (unsigned) p.nsplit);
