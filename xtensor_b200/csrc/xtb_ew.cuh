@@ -37,16 +37,16 @@ struct EwParams {
     uint32_t vec_per_row;
     uint32_t out_rt;        // register type of the value to store
     int32_t idx32;          // every operand offset fits in int32: rank <= 3 kernels may run
+    int32_t fast;           // full vectors, full blocks, no gather operand (rank <= 3 kernels)
     FastDiv div_vpr;
     FastDiv div_dim[XTB_MAX_DIM];
     EwLeaf leaf[XTB_MAX_LEAVES];
     EwLeaf out;
 };
 
-// Leaf access for one thread position in the rank <= 3 kernels: 32-bit coordinates
-// and offsets (host guarantees every operand spans < 2^31 elements).
+// Position of one thread's vector in the rank <= 3 kernels: 32-bit coordinates and offsets
+// (host guarantees every operand spans < 2^31 elements).
 template <int ND> struct EwFetch {
-    const EwParams& p;
     uint32_t idx[ND > 1 ? ND - 1 : 1];  // outer coordinates
     uint32_t col;                       // first inner-dim element of this thread's vector
     uint32_t lin;                       // linear element index of that element
@@ -58,22 +58,6 @@ template <int ND> struct EwFetch {
 #pragma unroll
         for (int d = 0; d < ND - 1; ++d) off += (int32_t) idx[d] * L.s32[d];
         return off;
-    }
-    template <class S, int V> XTB_DEV void load(int k, int dt, S (&x)[V]) const {
-        const EwLeaf& L = p.leaf[k];
-        const int sz = dtype_size(dt);
-        const char* ptr = L.ptr + (int64_t) offset_of(L) * sz;
-        if ((L.mode == MODE_VEC || L.mode == MODE_LINEAR) && nvalid == V) {
-            load_vec<S, V>(ptr, dt, x);
-        } else if (L.mode == MODE_BCAST) {
-            S s = load_elem<S>(ptr, dt);
-#pragma unroll
-            for (int v = 0; v < V; ++v) x[v] = s;
-        } else {
-            const int64_t step = (int64_t) L.s32[ND - 1] * sz;
-#pragma unroll
-            for (int v = 0; v < V; ++v) x[v] = (v < nvalid) ? load_elem<S>(ptr + v * step, dt) : S(0);
-        }
     }
 };
 
@@ -111,6 +95,7 @@ struct InterpEval {
     static constexpr int kUnroll = 1;
     static constexpr int kResultType = -1;  // run-time (EwParams::out_rt)
     static constexpr int kLeaves = XTB_MAX_LEAVES;
+    static constexpr bool kPrefetch = false;
     template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
         interpret<S, V>(prog, f, r);
     }
@@ -120,6 +105,8 @@ template <class Tbl, int ID> struct StaticEval {
     static constexpr int kUnroll = 4;
     static constexpr int kResultType = sprogs::result_type(Tbl::progs[ID]);
     static constexpr int kLeaves = Tbl::progs[ID].n_leaves;
+    static constexpr bool kPrefetch = true;
+    template <int K> static constexpr int leaf_dtype() { return sprogs::leaf_dtype(Tbl::progs[ID], K); }
     template <class S, int V, class Fetch> static XTB_DEV void run(const DevProgram& prog, Fetch& f, S (&r)[V]) {
         eval_static<Tbl, ID, S, V>(prog.imms, f, r);
     }
@@ -158,43 +145,129 @@ XTB_DEV void ew_store_static(const EwParams& p, const EwFetch<ND>& f, const S (&
     }
 }
 
-// One thread evaluates ITEMS vectors of V consecutive inner-dim elements; within
-// a block consecutive threads take consecutive vectors (coalesced 128-bit access).
-template <class Eval, class S, int V, int ND, int ITEMS>
-__global__ void __launch_bounds__(256) k_ew(const __grid_constant__ EwParams p) {
+// Stage leaf K (and, recursively, the following leaves) of a compile-time program: the
+// storage dtype is a constant, so element size, address arithmetic and the load instruction
+// are all resolved at compile time; only the access mode is a (uniform) run-time branch.
+template <class Eval, class S, int V, int ND, int ITEMS, bool FAST, int K> struct EwLeafLoader {
+    template <class PF>
+    static XTB_DEV void run(const EwParams& p, const EwFetch<ND> (&f)[ITEMS], const int (&nvalid)[ITEMS], PF& pf) {
+        if constexpr (K < Eval::kLeaves) {
+            constexpr int dt = Eval::template leaf_dtype<K>();
+            constexpr int sz = dtype_size(dt);
+            const EwLeaf& L = p.leaf[K];
+            const char* addr[ITEMS];
+            if (L.mode == MODE_LINEAR) {
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it) addr[it] = L.ptr + (uint64_t) f[it].lin * (uint32_t) sz;
+            } else {
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it) {
+                    int32_t off = (int32_t) f[it].col * L.s32[ND - 1];
+#pragma unroll
+                    for (int d = 0; d < ND - 1; ++d) off += (int32_t) f[it].idx[d] * L.s32[d];
+                    addr[it] = L.ptr + (int64_t) off * sz;
+                }
+            }
+            if (L.mode == MODE_BCAST) {
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it) {
+                    const S v0 = (FAST || nvalid[it] > 0) ? load_elem<S>(addr[it], dt) : S(0);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) pf.pre[K][it][v] = v0;
+                }
+            } else if (FAST || L.mode != MODE_GATHER) {
+                bool full = true;
+                if constexpr (!FAST) {
+#pragma unroll
+                    for (int it = 0; it < ITEMS; ++it) full = full && nvalid[it] == V;
+                }
+                if (full) {
+#pragma unroll
+                    for (int it = 0; it < ITEMS; ++it) load_vec<S, V>(addr[it], dt, pf.pre[K][it]);
+                } else {
+#pragma unroll
+                    for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) pf.pre[K][it][v] = (v < nvalid[it]) ? load_elem<S>(addr[it] + v * sz, dt) : S(0);
+                }
+            } else {
+                const int64_t step = (int64_t) L.s32[ND - 1] * sz;
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+                    for (int v = 0; v < V; ++v) pf.pre[K][it][v] = (v < nvalid[it]) ? load_elem<S>(addr[it] + v * step, dt) : S(0);
+            }
+            EwLeafLoader<Eval, S, V, ND, ITEMS, FAST, K + 1>::run(p, f, nvalid, pf);
+        }
+    }
+};
+
+// One thread evaluates ITEMS vectors of V consecutive inner-dim elements; within a block
+// consecutive threads take consecutive vectors (coalesced 128-bit access).  Compile-time
+// programs only: coordinates for all items first, then the batched loads of every leaf
+// (ITEMS x leaves 128-bit loads in flight per thread), then evaluation and stores.
+// FAST: the host verified that every vector is full (inner % V == 0), every block is full and
+// no operand needs the strided-gather path, so all tail / liveness predicates vanish.
+template <class Eval, class S, int V, int ND, int ITEMS, bool FAST>
+XTB_DEV void ew_body(const EwParams& p) {
+    constexpr int NL = Eval::kLeaves > 0 ? Eval::kLeaves : 1;
     const uint32_t inner = (uint32_t) p.shape[ND - 1];
     const uint32_t total = (uint32_t) p.total_vec;
     const uint32_t base = blockIdx.x * (256u * ITEMS) + threadIdx.x;
+    EwFetch<ND> f[ITEMS] = {};
+    int nvalid[ITEMS];
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        const uint32_t vec = base + it * 256u;
-        if (vec >= total) break;
-        EwFetch<ND> f{p, {0}, 0, 0, V};
+        uint32_t vec = base + it * 256u;
+        bool live = true;
+        if constexpr (!FAST) {
+            live = vec < total;
+            if (!live) vec = 0;
+        }
         uint32_t cv = vec;
         if constexpr (ND > 1) {
             uint32_t row = fd_div(vec, p.div_vpr);
             cv = vec - row * p.vec_per_row;
-            f.lin = row * inner + cv * V;
+            f[it].lin = row * inner + cv * V;
 #pragma unroll
             for (int d = ND - 2; d >= 0; --d) {
                 if (d == 0) {
-                    f.idx[0] = row;
+                    f[it].idx[0] = row;
                 } else {
                     uint32_t q = fd_div(row, p.div_dim[d]);
-                    f.idx[d] = row - q * (uint32_t) p.shape[d];
+                    f[it].idx[d] = row - q * (uint32_t) p.shape[d];
                     row = q;
                 }
             }
         } else {
-            f.lin = vec * V;
+            f[it].lin = vec * V;
         }
-        f.col = cv * V;
-        const uint32_t rem = inner - f.col;
-        f.nvalid = rem < (uint32_t) V ? (int) rem : V;
-        S r[V];
-        Eval::template run<S, V>(p.prog, f, r);
-        ew_store_static<Eval::kResultType, S, V, ND>(p, f, r);
+        f[it].col = cv * V;
+        if constexpr (FAST) {
+            f[it].nvalid = V;
+        } else {
+            const uint32_t rem = inner - f[it].col;
+            f[it].nvalid = live ? (rem < (uint32_t) V ? (int) rem : V) : 0;
+        }
+        nvalid[it] = f[it].nvalid;
     }
+    PreFetch<NL, ITEMS, S, V> pf;
+    EwLeafLoader<Eval, S, V, ND, ITEMS, FAST, 0>::run(p, f, nvalid, pf);
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        if (FAST || nvalid[it] > 0) {
+            pf.u = it;
+            S r[V];
+            Eval::template run<S, V>(p.prog, pf, r);
+            ew_store_static<Eval::kResultType, S, V, ND>(p, f[it], r);
+        }
+    }
+}
+
+template <class Eval, class S, int V, int ND, int ITEMS>
+__global__ void __launch_bounds__(256) k_ew(const __grid_constant__ EwParams p) {
+    if (p.fast) ew_body<Eval, S, V, ND, ITEMS, true>(p);
+    else ew_body<Eval, S, V, ND, ITEMS, false>(p);
 }
 
 // Any rank, 64-bit indices (slow path: rank > 3 after collapsing, or >= 2^31 vectors).
@@ -229,11 +302,15 @@ static int launch_ew_nd(const EwParams& p, DeviceCtx* ctx, const char* evname) {
     const int64_t per_block = 256 * ITEMS;
     const unsigned grid = (unsigned) ((p.total_vec + per_block - 1) / per_block);
     char name[96];
-    snprintf(name, sizeof(name), "k_ew<%s,S%d,V%d,ND%d>", evname, (int) sizeof(S) * 8, V, nd);
+    EwParams q = p;
+    bool fast = (p.shape[nd - 1] % V == 0) && (p.total_vec % per_block == 0) && p.out.mode != MODE_GATHER && p.out.mode != MODE_BCAST;
+    for (int k = 0; k < p.n_leaves; ++k) fast = fast && p.leaf[k].mode != MODE_GATHER;
+    q.fast = fast;
+    snprintf(name, sizeof(name), "k_ew<%s,S%d,V%d,ND%d>%s", evname, (int) sizeof(S) * 8, V, nd, fast ? "[fast]" : "");
     switch (nd) {
-        case 1: k_ew<Eval, S, V, 1, ITEMS><<<grid, 256, 0, ctx->stream>>>(p); break;
-        case 2: k_ew<Eval, S, V, 2, ITEMS><<<grid, 256, 0, ctx->stream>>>(p); break;
-        default: k_ew<Eval, S, V, 3, ITEMS><<<grid, 256, 0, ctx->stream>>>(p); break;
+        case 1: k_ew<Eval, S, V, 1, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;
+        case 2: k_ew<Eval, S, V, 2, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;
+        default: k_ew<Eval, S, V, 3, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;
     }
     note_launch(name);
     return check_launch(name);

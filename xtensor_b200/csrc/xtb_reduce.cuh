@@ -157,6 +157,53 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = (S) p.identity_bits;
     const int64_t RL = p.rshape[p.nr - 1];
+    if constexpr (Eval::kPrefetch) {
+        if (p.nr == 1) {
+            // U vectors of every leaf in flight before any arithmetic
+            constexpr int U = 4;
+            PreFetch<NL, U, S, V> pf;
+            for (int64_t j = jbeg + lane; j < jend; j += (int64_t) stride * U) {
+                int nvalid[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t ju = j + (int64_t) u * stride;
+                    const int64_t rem = RL - ju * V;
+                    nvalid[u] = ju < jend ? (rem < V ? (int) rem : V) : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < NL; ++k) {
+                    const RdLeaf& L = p.leaf[k];
+                    const char* addr[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) addr[u] = base[k] + (nvalid[u] > 0 ? (j + (int64_t) u * stride) * vstep[k] : 0);
+                    preload_leaf<S, V, U>(addr, L.mode == MODE_VEC, L.mode == MODE_BCAST, L.dtype,
+                                          L.rstride[p.nr - 1] * (int64_t) dtype_size(L.dtype), nvalid, pf.pre[k]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (nvalid[u] > 0) {
+                        pf.u = u;
+                        S x[V];
+                        Eval::template run<S, V>(p.prog, pf, x);
+                        Acc::template cast_in<S, V>(p, x);
+                        if (nvalid[u] < V) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v)
+                                if (v >= nvalid[u]) x[v] = (S) p.identity_bits;
+                        }
+                        Acc::template step<S, V>(p, acc, x);
+                    }
+                }
+            }
+            S r0[1] = {acc[0]};
+#pragma unroll
+            for (int v = 1; v < V; ++v) {
+                S y[1] = {acc[v]};
+                Acc::template step<S, 1>(p, r0, y);
+            }
+            return r0[0];
+        }
+    }
     for (int64_t j = jbeg + lane; j < jend; j += stride) {
         int64_t cv = j;
         if (p.nr > 1) {
@@ -211,8 +258,67 @@ __global__ void __launch_bounds__(256) k_reduce_inner_warp(const __grid_constant
     for (int64_t round = warp0; round < rounds; round += (int64_t) gridDim.x * 8) {
         const int64_t out_base = round * 32;
         S keep = (S) p.identity_bits;
-#pragma unroll 4
-        for (int it = 0; it < G; ++it) {
+        bool done = false;
+        if constexpr (Eval::kPrefetch) {
+            if (p.nr == 1 && p.rvec_total <= G && p.nsplit == 1) {
+                // short rows: every lane owns at most one vector per output; stage the vectors of
+                // U consecutive outputs of the group before reducing them
+                constexpr int U = 4;
+                const int64_t RL = p.rshape[0];
+                const int64_t rem = RL - (int64_t) li * V;
+                const int my_valid = li < p.rvec_total ? (rem < V ? (int) rem : V) : 0;
+                PreFetch<NL, U, S, V> pf;
+                for (int it0 = 0; it0 < G; it0 += U) {
+                    int nvalid[U];
+                    int64_t kos[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        kos[u] = out_base + g * G + it0 + u;
+                        nvalid[u] = (it0 + u < G && kos[u] < p.K) ? my_valid : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) {
+                        const RdLeaf& L = p.leaf[k];
+                        const int sz = dtype_size(L.dtype);
+                        const char* addr[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            addr[u] = L.ptr + (nvalid[u] > 0 ? (rd_kept_offset(p, (uint32_t) kos[u], L.kstride) + (int64_t) li * V * L.rstride[0]) * sz : 0);
+                        preload_leaf<S, V, U>(addr, L.mode == MODE_VEC, L.mode == MODE_BCAST, L.dtype, L.rstride[0] * (int64_t) sz,
+                                              nvalid, pf.pre[k]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (it0 + u < G) {     // uniform over the warp
+                            S x[V];
+#pragma unroll
+                            for (int v = 0; v < V; ++v) x[v] = (S) p.identity_bits;
+                            if (nvalid[u] > 0) {
+                                pf.u = u;
+                                Eval::template run<S, V>(p.prog, pf, x);
+                                Acc::template cast_in<S, V>(p, x);
+#pragma unroll
+                                for (int v = 0; v < V; ++v)
+                                    if (v >= nvalid[u]) x[v] = (S) p.identity_bits;
+                            }
+                            S r[1] = {x[0]};
+#pragma unroll
+                            for (int v = 1; v < V; ++v) {
+                                S y[1] = {x[v]};
+                                Acc::template step<S, 1>(p, r, y);
+                            }
+                            for (int o = G >> 1; o > 0; o >>= 1) {
+                                S y[1] = {shfl_xor<S>(r[0], o)};
+                                Acc::template step<S, 1>(p, r, y);
+                            }
+                            if (li == it0 + u) keep = r[0];
+                        }
+                    }
+                }
+                done = true;
+            }
+        }
+        for (int it = 0; it < G && !done; ++it) {
             const int64_t ko = out_base + g * G + it;
             S r[1] = {(S) p.identity_bits};
             if (ko < p.K) r[0] = rd_inner_partial<Eval, Acc, S, V, NL>(p, (uint32_t) ko, jbeg, jend, li, G);
@@ -300,8 +406,38 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
         S acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = (S) p.identity_bits;
-        if (p.nr == 1) {
-#pragma unroll(Eval::kUnroll)
+        if (Eval::kPrefetch && p.nr == 1) {
+            if constexpr (Eval::kPrefetch) {
+                // U rows of every leaf in flight before any arithmetic; rows are then accumulated in
+                // the reference's order (row r before row r + 1)
+                constexpr int U = 8;
+                PreFetch<NL, U, S, V> pf;
+                for (int64_t r = rbeg; r < rend; r += U) {
+                    int nvalid[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) nvalid[u] = (r + u < rend) ? f.nvalid : 0;
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) {
+                        const RdLeaf& L = p.leaf[k];
+                        const char* addr[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) addr[u] = base[k] + (nvalid[u] > 0 ? (r + u) * rstep[k] : 0);
+                        preload_leaf<S, V, U>(addr, L.mode == MODE_VEC, L.mode == MODE_BCAST, L.dtype,
+                                              L.kstride[p.nk - 1] * (int64_t) dtype_size(L.dtype), nvalid, pf.pre[k]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (nvalid[u] > 0) {
+                            pf.u = u;
+                            S x[V];
+                            Eval::template run<S, V>(p.prog, pf, x);
+                            Acc::template cast_in<S, V>(p, x);
+                            Acc::template step<S, V>(p, acc, x);
+                        }
+                    }
+                }
+            }
+        } else if (p.nr == 1) {
             for (int64_t r = rbeg; r < rend; ++r) {
 #pragma unroll
                 for (int k = 0; k < NL; ++k)

@@ -61,6 +61,17 @@ constexpr int result_type(const SP& p) {
     return st[0];
 }
 
+// storage dtype of leaf k, read off the instruction that references it
+constexpr int leaf_dtype(const SP& p, int k) {
+    for (int i = 0; i < p.n; ++i) {
+        const SInsn in = p.ins[i];
+        const bool push_leaf = in.op == XTB_OP_PUSH && in.src == XTB_SRC_LEAF;
+        const bool fused_leaf = in.op >= XTB_OP_ADD && in.op < XTB_OP_WHERE && (in.src & 3) == XTB_SRC_LEAF;
+        if ((push_leaf || fused_leaf) && in.arg == k) return in.type;
+    }
+    return XTB_F32;
+}
+
 #define XTB_SP_TYPED(NAME, T)                                                                      \
     /* out = a */                                                                                   \
     inline constexpr SP copy_##NAME = make({push_leaf(0, T)}, 1, 0);                                \
