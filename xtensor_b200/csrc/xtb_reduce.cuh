@@ -138,6 +138,50 @@ template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S 
     store_elem<S>(dst, p.out_dtype, p.acc_rt, a[0]);
 }
 
+// Stage U vectors of leaf K (and recursively of the following leaves) of a compile-time
+// program.  dtype / element size are constants; the access mode is one uniform branch per leaf.
+template <class Eval, class S, int V, int U, int K> struct RdLeafLoader {
+    template <class PF, class AddrFn>
+    static XTB_DEV void run(const RdParams& p, const int (&nvalid)[U], int64_t gather_stride_elems_sel, PF& pf, AddrFn addr_of) {
+        if constexpr (K < Eval::kLeaves) {
+            constexpr int dt = Eval::template leaf_dtype<K>();
+            constexpr int sz = dtype_size(dt);
+            const RdLeaf& L = p.leaf[K];
+            const char* addr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) addr[u] = addr_of(L, sz, u);
+            if (L.mode == MODE_VEC) {
+                bool full = true;
+#pragma unroll
+                for (int u = 0; u < U; ++u) full = full && nvalid[u] == V;
+                if (full) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) load_vec<S, V>(addr[u], dt, pf.pre[K][u]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) pf.pre[K][u][v] = (v < nvalid[u]) ? load_elem<S>(addr[u] + v * sz, dt) : S(0);
+                }
+            } else if (L.mode == MODE_BCAST) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const S v0 = nvalid[u] > 0 ? load_elem<S>(addr[u], dt) : S(0);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) pf.pre[K][u][v] = v0;
+                }
+            } else {
+                const int64_t step = (gather_stride_elems_sel ? L.rstride[p.nr - 1] : L.kstride[p.nk - 1]) * sz;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int v = 0; v < V; ++v) pf.pre[K][u][v] = (v < nvalid[u]) ? load_elem<S>(addr[u] + v * step, dt) : S(0);
+            }
+            RdLeafLoader<Eval, S, V, U, K + 1>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of);
+        }
+    }
+};
+
 // one lane's share of the reduced elements of output `ko`: vectors j = jbeg + lane, += stride
 template <class Eval, class Acc, class S, int V, int NL>
 XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t jend, int lane, int stride) {
@@ -170,15 +214,11 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
                     const int64_t rem = RL - ju * V;
                     nvalid[u] = ju < jend ? (rem < V ? (int) rem : V) : 0;
                 }
-#pragma unroll
-                for (int k = 0; k < NL; ++k) {
-                    const RdLeaf& L = p.leaf[k];
-                    const char* addr[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) addr[u] = base[k] + (nvalid[u] > 0 ? (j + (int64_t) u * stride) * vstep[k] : 0);
-                    preload_leaf<S, V, U>(addr, L.mode == MODE_VEC, L.mode == MODE_BCAST, L.dtype,
-                                          L.rstride[p.nr - 1] * (int64_t) dtype_size(L.dtype), nvalid, pf.pre[k]);
-                }
+                RdLeafLoader<Eval, S, V, U, 0>::run(p, nvalid, 1, pf, [&](const RdLeaf& L, int sz, int u) -> const char* {
+                    const int64_t koff = rd_kept_offset(p, ko, L.kstride);
+                    const int64_t ju = nvalid[u] > 0 ? j + (int64_t) u * stride : 0;
+                    return L.ptr + (koff + ju * V * L.rstride[0]) * sz;
+                });
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (nvalid[u] > 0) {
@@ -276,17 +316,10 @@ __global__ void __launch_bounds__(256) k_reduce_inner_warp(const __grid_constant
                         kos[u] = out_base + g * G + it0 + u;
                         nvalid[u] = (it0 + u < G && kos[u] < p.K) ? my_valid : 0;
                     }
-#pragma unroll
-                    for (int k = 0; k < NL; ++k) {
-                        const RdLeaf& L = p.leaf[k];
-                        const int sz = dtype_size(L.dtype);
-                        const char* addr[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            addr[u] = L.ptr + (nvalid[u] > 0 ? (rd_kept_offset(p, (uint32_t) kos[u], L.kstride) + (int64_t) li * V * L.rstride[0]) * sz : 0);
-                        preload_leaf<S, V, U>(addr, L.mode == MODE_VEC, L.mode == MODE_BCAST, L.dtype, L.rstride[0] * (int64_t) sz,
-                                              nvalid, pf.pre[k]);
-                    }
+                    RdLeafLoader<Eval, S, V, U, 0>::run(p, nvalid, 1, pf, [&](const RdLeaf& L, int sz, int u) -> const char* {
+                        const int64_t koff = nvalid[u] > 0 ? rd_kept_offset(p, (uint32_t) kos[u], L.kstride) + (int64_t) li * V * L.rstride[0] : 0;
+                        return L.ptr + koff * sz;
+                    });
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (it0 + u < G) {     // uniform over the warp
@@ -416,15 +449,11 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
                     int nvalid[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) nvalid[u] = (r + u < rend) ? f.nvalid : 0;
-#pragma unroll
-                    for (int k = 0; k < NL; ++k) {
-                        const RdLeaf& L = p.leaf[k];
-                        const char* addr[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u) addr[u] = base[k] + (nvalid[u] > 0 ? (r + u) * rstep[k] : 0);
-                        preload_leaf<S, V, U>(addr, L.mode == MODE_VEC, L.mode == MODE_BCAST, L.dtype,
-                                              L.kstride[p.nk - 1] * (int64_t) dtype_size(L.dtype), nvalid, pf.pre[k]);
-                    }
+                    RdLeafLoader<Eval, S, V, U, 0>::run(p, nvalid, 0, pf, [&](const RdLeaf& L, int sz, int u) -> const char* {
+                        const int64_t koff = rd_kept_offset(p, ko0, L.kstride);
+                        const int64_t ru = nvalid[u] > 0 ? r + u : rbeg;
+                        return L.ptr + (koff + ru * L.rstride[0]) * sz;
+                    });
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (nvalid[u] > 0) {
