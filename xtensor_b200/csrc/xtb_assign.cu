@@ -13,6 +13,16 @@ template <class S, int V> static int launch_interp(const EwParams& p, DeviceCtx*
 
 static bool ew_nd_ok_rank(int nd) { return nd <= 3; }
 
+static int dispatch_tile(const xtb_program* prog, const EwParams& p, DeviceCtx* ctx, bool w64) {
+    const bool no_static = getenv("XTB_NO_STATIC") != nullptr;
+    if (!no_static) {
+        const StaticEntry* e = find_static(prog);
+        if (e && sprogs::is64(*e->prog) == w64) return e->launch_tile(p, ctx);
+    }
+    if (w64) return launch_ew_tile<InterpEval, uint64_t>(p, ctx, "interp");
+    return launch_ew_tile<InterpEval, uint32_t>(p, ctx, "interp");
+}
+
 static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ctx, bool w64, int V) {
     const bool no_static = getenv("XTB_NO_STATIC") != nullptr;  // tests toggle this per call
     if (!no_static && ew_nd_ok(p)) {
@@ -100,6 +110,49 @@ static int launch_space(const xtb_program* prog, const Space& s, const char* con
         V = 1;
         for (int k = 0; k < prog->n_leaves; ++k)
             if (p.leaf[k].mode == MODE_VEC) p.leaf[k].mode = MODE_GATHER;
+    }
+    // Transposed leaves: an operand that cannot be read along the output's fast dim but is
+    // contiguous along another one goes through the tiled kernel.
+    {
+        int ti = -1, n_tile = 0;
+        bool tile_ok = s.ndim >= 2 && s.shape[inner] >= 16 && (p.out.stride[inner] == 1 || p.out.stride[inner] == -1);
+        for (int k = 0; k < prog->n_leaves && tile_ok; ++k) {
+            EwLeaf& L = p.leaf[k];
+            if (L.mode != MODE_GATHER) continue;
+            int best = -1;
+            for (int d = 0; d < s.ndim - 1; ++d)
+                if ((L.stride[d] == 1 || L.stride[d] == -1) && s.shape[d] >= 16) best = d;
+            if (best < 0) continue;                       // plain strided gather: stays in the generic path
+            if (ti >= 0 && best != ti) { tile_ok = false; break; }
+            ti = best;
+            if (n_tile >= kMaxTileLeaves) { tile_ok = false; break; }
+            p.tile_slot[k] = n_tile++;
+        }
+        if (tile_ok && ti >= 0) {
+            for (int k = 0; k < prog->n_leaves; ++k)
+                if (p.leaf[k].mode == MODE_GATHER && (p.leaf[k].stride[ti] == 1 || p.leaf[k].stride[ti] == -1) && s.shape[ti] >= 16)
+                    p.leaf[k].mode = MODE_TILE;
+            p.tile_i = ti;
+            p.ntile_i = (uint32_t) ((s.shape[ti] + kTile - 1) / kTile);
+            p.ntile_j = (uint32_t) ((s.shape[inner] + kTile - 1) / kTile);
+            p.div_nti = make_fastdiv(p.ntile_i);
+            p.div_ntj = make_fastdiv(p.ntile_j);
+            for (int d = 0; d < s.ndim; ++d) p.div_dim[d] = make_fastdiv((uint32_t) std::min<int64_t>(s.shape[d], 0x7fffffff));
+            bool dims_ok = true;
+            for (int d = 0; d < s.ndim; ++d) dims_ok = dims_ok && s.shape[d] < 0x7fffffffLL;
+            // 32-bit offsets are fine when every operand spans < 2^31 elements
+            bool ok32 = true;
+            for (int k = 0; k <= prog->n_leaves; ++k) {
+                const EwLeaf& L = k < prog->n_leaves ? p.leaf[k] : p.out;
+                int64_t span = 0;
+                for (int d = 0; d < s.ndim; ++d) span += (L.stride[d] < 0 ? -L.stride[d] : L.stride[d]) * (s.shape[d] - 1);
+                ok32 = ok32 && span < 0x7fffffffLL;
+            }
+            p.idx32 = ok32;
+            if (dims_ok) return dispatch_tile(prog, p, ctx, w64);
+            for (int k = 0; k < prog->n_leaves; ++k)
+                if (p.leaf[k].mode == MODE_TILE) p.leaf[k].mode = MODE_GATHER;
+        }
     }
     // 32-bit offsets + linear shortcut for the rank <= 3 kernels
     {

@@ -18,7 +18,9 @@ namespace xtb {
 
 // MODE_LINEAR: MODE_VEC and additionally dense over the whole collapsed space, so the
 // element offset is just the linear index (no coordinate math).
-enum LeafMode : int32_t { MODE_VEC = 0, MODE_BCAST = 1, MODE_GATHER = 2, MODE_LINEAR = 3 };
+// MODE_TILE (k_ew_tile only): the leaf is contiguous along another dim than the output; it is
+// read in 32x32 tiles along ITS contiguous dim and transposed through shared memory.
+enum LeafMode : int32_t { MODE_VEC = 0, MODE_BCAST = 1, MODE_GATHER = 2, MODE_LINEAR = 3, MODE_TILE = 4 };
 
 struct EwLeaf {
     const char* ptr;
@@ -38,6 +40,11 @@ struct EwParams {
     uint32_t out_rt;        // register type of the value to store
     int32_t idx32;          // every operand offset fits in int32: rank <= 3 kernels may run
     int32_t fast;           // full vectors, full blocks, no gather operand (rank <= 3 kernels)
+    // k_ew_tile: tile over (dim tile_i, inner dim); batch = all other dims
+    int32_t tile_i;
+    int32_t tile_slot[XTB_MAX_LEAVES];   // shared-memory slot of each MODE_TILE leaf
+    uint32_t ntile_i, ntile_j;
+    FastDiv div_ntj, div_nti;
     FastDiv div_vpr;
     FastDiv div_dim[XTB_MAX_DIM];
     EwLeaf leaf[XTB_MAX_LEAVES];
@@ -330,6 +337,210 @@ static int launch_ew_generic(const EwParams& p, DeviceCtx* ctx, const char* evna
     return check_launch(name);
 }
 
+// ---- tiled kernel: transposed leaves -------------------------------------------------------
+// Replaces stepper_assigner::run (xassign.hpp:644-695) for the case the CPU handles worst: an
+// operand whose fast dim is not the output's (xt::transpose, column-major leaves).  A block
+// owns a 32(i) x 32(j) tile: MODE_TILE leaves are read coalesced along i into padded shared
+// memory, then every thread evaluates 4 outputs coalesced along j, reading those leaves
+// transposed from shared memory and all other leaves directly.
+constexpr int kTile = 32;
+constexpr int kMaxTileLeaves = 3;
+
+struct TileFetch {
+    const EwParams& p;
+    const void* smem;
+    int64_t idx[XTB_MAX_DIM];   // full coordinates of the current element
+    int tx, ii;
+    template <class S, int V> XTB_DEV void load(int k, int dt, S (&x)[V]) const {
+        const EwLeaf& L = p.leaf[k];
+        if (L.mode == MODE_TILE) {
+            const S(*t)[kTile][kTile + 1] = (const S(*)[kTile][kTile + 1]) smem;
+            x[0] = t[p.tile_slot[k]][tx][ii];
+        } else {
+            int64_t off = 0;
+            for (int d = 0; d < p.ndim; ++d) off += idx[d] * L.stride[d];
+            x[0] = load_elem<S>(L.ptr + off * dtype_size(dt), dt);
+        }
+    }
+};
+
+template <class Eval, class S>
+__global__ void __launch_bounds__(256) k_ew_tile(const __grid_constant__ EwParams p) {
+    __shared__ S tile[kMaxTileLeaves][kTile][kTile + 1];
+    const int nd = p.ndim, di = p.tile_i, dj = nd - 1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // block -> (batch, tile_i, tile_j)
+    uint32_t b = blockIdx.x;
+    uint32_t q = fd_div(b, p.div_ntj);
+    const uint32_t tj = b - q * p.ntile_j;
+    b = q;
+    q = fd_div(b, p.div_nti);
+    const uint32_t ti = b - q * p.ntile_i;
+    uint32_t batch = q;
+    TileFetch f{p, tile, {0}, tx, 0};
+    for (int d = nd - 2; d >= 0; --d) {
+        if (d == di) continue;
+        const uint32_t qq = fd_div(batch, p.div_dim[d]);
+        f.idx[d] = batch - qq * (uint32_t) p.shape[d];
+        batch = qq;
+    }
+    const int64_t Ni = p.shape[di], Nj = p.shape[dj];
+    const int64_t i0 = (int64_t) ti * kTile, j0 = (int64_t) tj * kTile;
+    // phase 1: transposed leaves, coalesced along i
+    for (int k = 0; k < p.n_leaves; ++k) {
+        const EwLeaf& L = p.leaf[k];
+        if (L.mode != MODE_TILE) continue;
+        const int sz = dtype_size(L.dtype);
+        int64_t boff = 0;
+        for (int d = 0; d < nd - 1; ++d)
+            if (d != di) boff += f.idx[d] * L.stride[d];
+        const int slot = p.tile_slot[k];
+#pragma unroll
+        for (int r = 0; r < kTile / 8; ++r) {
+            const int jj = ty + 8 * r;
+            const int64_t i = i0 + tx, j = j0 + jj;
+            if (i < Ni && j < Nj) tile[slot][jj][tx] = load_elem<S>(L.ptr + (boff + i * L.stride[di] + j * L.stride[dj]) * sz, L.dtype);
+        }
+    }
+    __syncthreads();
+    // phase 2: evaluate, coalesced along j
+    const EwLeaf& O = p.out;
+    const int osz = dtype_size(O.dtype);
+#pragma unroll
+    for (int r = 0; r < kTile / 8; ++r) {
+        const int ii = ty + 8 * r;
+        const int64_t i = i0 + ii, j = j0 + tx;
+        if (i < Ni && j < Nj) {
+            f.ii = ii;
+            f.idx[di] = i;
+            f.idx[dj] = j;
+            S x[1];
+            Eval::template run<S, 1>(p.prog, f, x);
+            int64_t off = 0;
+            for (int d = 0; d < nd; ++d) off += f.idx[d] * O.stride[d];
+            store_elem<S>((char*) O.ptr + off * osz, O.dtype, (int) p.out_rt, x[0]);
+        }
+    }
+}
+
+// Compile-time-program version: dtype / element size constant per leaf, 32-bit offsets, and all
+// global loads of the block (tile leaves AND the direct leaves of the 4 outputs a thread owns)
+// are issued before the barrier, so their latencies overlap.
+template <class Eval, class S, int K> struct TileLeafStage {
+    // phase 1: issue loads.  tile leaves -> shared memory, direct leaves -> registers
+    template <class PF>
+    static XTB_DEV void load(const EwParams& p, S (*tile)[kTile][kTile + 1], const int32_t (&bidx)[XTB_MAX_DIM], int32_t i0, int32_t j0,
+                             int tx, int ty, PF& pf) {
+        if constexpr (K < Eval::kLeaves) {
+            constexpr int dt = Eval::template leaf_dtype<K>();
+            constexpr int sz = dtype_size(dt);
+            const EwLeaf& L = p.leaf[K];
+            const int nd = p.ndim, di = p.tile_i, dj = nd - 1;
+            const int32_t Ni = (int32_t) p.shape[di], Nj = (int32_t) p.shape[dj];
+            int32_t boff = 0;
+            for (int d = 0; d < nd - 1; ++d)
+                if (d != di) boff += bidx[d] * (int32_t) L.stride[d];
+            const int32_t si = (int32_t) L.stride[di], sj = (int32_t) L.stride[dj];
+            if (L.mode == MODE_TILE) {
+                S tmp[kTile / 8];
+#pragma unroll
+                for (int r = 0; r < kTile / 8; ++r) {
+                    const int32_t i = i0 + tx, j = j0 + ty + 8 * r;
+                    tmp[r] = (i < Ni && j < Nj) ? load_elem<S>(L.ptr + (int64_t) (boff + i * si + j * sj) * sz, dt) : S(0);
+                }
+                const int slot = p.tile_slot[K];
+#pragma unroll
+                for (int r = 0; r < kTile / 8; ++r) tile[slot][ty + 8 * r][tx] = tmp[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < kTile / 8; ++r) {
+                    const int32_t i = i0 + ty + 8 * r, j = j0 + tx;
+                    pf.pre[K][r][0] = (i < Ni && j < Nj) ? load_elem<S>(L.ptr + (int64_t) (boff + i * si + j * sj) * sz, dt) : S(0);
+                }
+            }
+            TileLeafStage<Eval, S, K + 1>::load(p, tile, bidx, i0, j0, tx, ty, pf);
+        }
+    }
+    // phase 2: tile leaves from shared memory (transposed read)
+    template <class PF>
+    static XTB_DEV void gather(const EwParams& p, const S (*tile)[kTile][kTile + 1], int tx, int ty, PF& pf) {
+        if constexpr (K < Eval::kLeaves) {
+            if (p.leaf[K].mode == MODE_TILE) {
+                const int slot = p.tile_slot[K];
+#pragma unroll
+                for (int r = 0; r < kTile / 8; ++r) pf.pre[K][r][0] = tile[slot][tx][ty + 8 * r];
+            }
+            TileLeafStage<Eval, S, K + 1>::gather(p, tile, tx, ty, pf);
+        }
+    }
+};
+
+template <class Eval, class S>
+__global__ void __launch_bounds__(256) k_ew_tile_static(const __grid_constant__ EwParams p) {
+    constexpr int NL = Eval::kLeaves > 0 ? Eval::kLeaves : 1;
+    constexpr int RT = Eval::kResultType;
+    __shared__ S tile[kMaxTileLeaves][kTile][kTile + 1];
+    const int nd = p.ndim, di = p.tile_i, dj = nd - 1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    uint32_t b = blockIdx.x;
+    uint32_t q = fd_div(b, p.div_ntj);
+    const uint32_t tj = b - q * p.ntile_j;
+    b = q;
+    q = fd_div(b, p.div_nti);
+    const uint32_t ti = b - q * p.ntile_i;
+    uint32_t batch = q;
+    int32_t bidx[XTB_MAX_DIM] = {0};
+    for (int d = nd - 2; d >= 0; --d) {
+        if (d == di) continue;
+        const uint32_t qq = fd_div(batch, p.div_dim[d]);
+        bidx[d] = (int32_t) (batch - qq * (uint32_t) p.shape[d]);
+        batch = qq;
+    }
+    const int32_t i0 = (int32_t) (ti * kTile), j0 = (int32_t) (tj * kTile);
+    PreFetch<NL, kTile / 8, S, 1> pf;
+    TileLeafStage<Eval, S, 0>::load(p, tile, bidx, i0, j0, tx, ty, pf);
+    __syncthreads();
+    TileLeafStage<Eval, S, 0>::gather(p, tile, tx, ty, pf);
+    const EwLeaf& O = p.out;
+    constexpr int osz = dtype_size(RT);
+    const int32_t Ni = (int32_t) p.shape[di], Nj = (int32_t) p.shape[dj];
+    int32_t boff = 0;
+    for (int d = 0; d < nd - 1; ++d)
+        if (d != di) boff += bidx[d] * (int32_t) O.stride[d];
+#pragma unroll
+    for (int r = 0; r < kTile / 8; ++r) {
+        const int32_t i = i0 + ty + 8 * r, j = j0 + tx;
+        if (i < Ni && j < Nj) {
+            pf.u = r;
+            S x[1];
+            Eval::template run<S, 1>(p.prog, pf, x);
+            store_elem<S>((char*) O.ptr + (int64_t) (boff + i * (int32_t) O.stride[di] + j * (int32_t) O.stride[dj]) * osz, RT, RT, x[0]);
+        }
+    }
+}
+
+template <class Eval, class S>
+static int launch_ew_tile(const EwParams& p, DeviceCtx* ctx, const char* evname) {
+    int64_t batch = 1;
+    for (int d = 0; d < p.ndim - 1; ++d)
+        if (d != p.tile_i) batch *= p.shape[d];
+    const int64_t blocks = batch * p.ntile_i * p.ntile_j;
+    if (blocks >= 0x7fffffffLL) return set_error(XTB_ERR_UNSUPPORTED, "too many tiles");
+    char name[96];
+    if constexpr (Eval::kPrefetch) {
+        if (p.idx32 && p.out.dtype == Eval::kResultType) {
+            snprintf(name, sizeof(name), "k_ew_tile_static<%s,S%d>", evname, (int) sizeof(S) * 8);
+            k_ew_tile_static<Eval, S><<<(unsigned) blocks, 256, 0, ctx->stream>>>(p);
+            note_launch(name);
+            return check_launch(name);
+        }
+    }
+    snprintf(name, sizeof(name), "k_ew_tile<%s,S%d>", evname, (int) sizeof(S) * 8);
+    k_ew_tile<Eval, S><<<(unsigned) blocks, 256, 0, ctx->stream>>>(p);
+    note_launch(name);
+    return check_launch(name);
+}
+
 // ---- registry of compile-time programs ---------------------------------------------
 // Programs whose instruction stream equals a pre-instantiated SProg run a fully
 // unrolled kernel; anything else runs the interpreter.  Both paths share every
@@ -338,6 +549,7 @@ struct StaticEntry {
     const sprogs::SP* prog;
     const char* name;
     int (*launch_ew)(const EwParams&, DeviceCtx*);
+    int (*launch_tile)(const EwParams&, DeviceCtx*);
 };
 struct StaticTable {
     const StaticEntry* entries;

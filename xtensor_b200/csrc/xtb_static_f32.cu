@@ -21,9 +21,13 @@ template <int ID> int launch_one(const EwParams& p, DeviceCtx* ctx) {
     return launch_ew_nd<StaticEval<Tbl, ID>, Slot, kV>(p, ctx, kNames[ID]);
 }
 
+template <int ID> int launch_tile_one(const EwParams& p, DeviceCtx* ctx) {
+    return launch_ew_tile<StaticEval<Tbl, ID>, Slot>(p, ctx, kNames[ID]);
+}
+
 StaticEntry g_entries[kCount];
 template <int... I> void fill(std::integer_sequence<int, I...>) {
-    ((g_entries[I] = StaticEntry{&Tbl::progs[I], kNames[I], &launch_one<I>}), ...);
+    ((g_entries[I] = StaticEntry{&Tbl::progs[I], kNames[I], &launch_one<I>, &launch_tile_one<I>}), ...);
 }
 
 }  // namespace
