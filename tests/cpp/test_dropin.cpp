@@ -1,0 +1,154 @@
+// Drop-in test: the REAL xtensor headers + include/xtb200/xtensor_b200.hpp + libxtb200.so.
+// The same expressions are evaluated by xtensor on the CPU (host containers) and by the
+// backend (device containers); results must agree bit for bit (+ - * /, integers, integer-
+// valued reductions) or within 2 ulp propagated (transcendentals).
+// Built here (where /root/reference exists) by tests/cpp/Makefile; the binary travels to the
+// GPU box and is run by tests/test_gpu_dropin.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+
+#include <xtb200/xtensor_b200.hpp>
+#include <xtensor/generators/xbuilder.hpp>
+
+static int g_failed = 0;
+#define CHECK(cond)                                                              \
+    do {                                                                         \
+        if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); ++g_failed; } \
+    } while (0)
+
+template <class A, class B> bool same_bits(const A& a, const B& b)
+{
+    if (a.shape().size() != b.shape().size() || !std::equal(a.shape().begin(), a.shape().end(), b.shape().begin())) return false;
+    return std::memcmp(a.data(), b.data(), a.size() * sizeof(typename A::value_type)) == 0;
+}
+
+template <class A, class B> double max_abs_diff(const A& a, const B& b)
+{
+    double m = 0;
+    auto ib = b.begin();
+    for (auto ia = a.begin(); ia != a.end(); ++ia, ++ib) m = std::max(m, std::fabs(double(*ia) - double(*ib)));
+    return m;
+}
+
+template <class T, class... S> xt::xarray<T> rnd(unsigned seed, T lo, T hi, S... shape)
+{
+    std::mt19937_64 gen(seed);
+    std::uniform_real_distribution<double> dist((double) lo, (double) hi);
+    xt::xarray<T> a = xt::zeros<T>({std::size_t(shape)...});
+    for (auto& v : a) v = static_cast<T>(dist(gen));
+    return a;
+}
+
+int main()
+{
+    if (xtb_init(0) != 0) { std::printf("xtb_init failed: %s\n", xtb_last_error()); return 2; }
+
+    // cfg1: xt::noalias(c) = a + b on xtensor<double, 1>
+    {
+        xt::xtensor<double, 1> a = rnd<double>(1, -1, 1, 100003), b = rnd<double>(2, -1, 1, 100003), c;
+        xt::noalias(c) = a + b;
+        xtb::xtensor<double, 1> da = xtb::to_device(a), db = xtb::to_device(b), dc;
+        xt::noalias(dc) = da + db;
+        CHECK(same_bits(xtb::to_host(dc), c));
+        CHECK(std::strstr(xtb_last_kernel(), "add_f64") != nullptr);
+    }
+    // cfg2: c = sin(a) * b(1,N,1) + 2.0f * d, value type stays float
+    {
+        xt::xtensor<float, 3> a = rnd<float>(3, -3, 3, 16, 40, 64), b = rnd<float>(4, 0.5f, 1.5f, 1, 40, 1), d = rnd<float>(5, -3, 3, 16, 40, 64), c;
+        xt::noalias(c) = xt::sin(a) * b + 2.0f * d;
+        xtb::xtensor<float, 3> da = xtb::to_device(a), db = xtb::to_device(b), dd = xtb::to_device(d), dc;
+        auto expr = xt::sin(da) * db + 2.0f * dd;
+        static_assert(std::is_same<decltype(expr)::value_type, float>::value, "value type stays float");
+        static_assert(xtb::is_b200_expression<decltype(expr)>::value, "one device operand tags the tree");
+        xt::noalias(dc) = expr;
+        auto hc = xtb::to_host(dc);
+        CHECK(hc.shape() == c.shape());
+        CHECK(max_abs_diff(hc, c) <= 4e-7 * 4);   // 2 ulp(sin) propagated, |values| < 8
+        CHECK(std::strstr(xtb_last_kernel(), "sinmul_axpy_f32") != nullptr);
+    }
+    // cfg4: out = transpose(a) + view(b, range(0, _, 2), all())
+    {
+        xt::xtensor<double, 2> a = rnd<double>(7, -1, 1, 96, 96), b = rnd<double>(8, -1, 1, 192, 96), o;
+        xt::noalias(o) = xt::transpose(a) + xt::view(b, xt::range(0, xt::placeholders::_, 2), xt::all());
+        xtb::xtensor<double, 2> da = xtb::to_device(a), db = xtb::to_device(b), dout;
+        xt::noalias(dout) = xt::transpose(da) + xt::view(db, xt::range(0, xt::placeholders::_, 2), xt::all());
+        CHECK(same_bits(xtb::to_host(dout), o));
+    }
+    // cfg5 map, broadcasting a lower-rank operand; benchmark_assign 3.0 * x - 2.0 * y
+    {
+        xt::xtensor<float, 2> a = rnd<float>(9, -1, 1, 64, 128);
+        xt::xtensor<float, 1> m = rnd<float>(10, -0.1f, 0.1f, 128);
+        xt::xtensor<float, 2> o;
+        xt::noalias(o) = xt::exp(a - m);
+        xtb::xtensor<float, 2> da = xtb::to_device(a), dout;
+        xtb::xtensor<float, 1> dm = xtb::to_device(m);
+        xt::noalias(dout) = xt::exp(da - dm);
+        CHECK(max_abs_diff(xtb::to_host(dout), o) <= 1e-6);
+        xt::xtensor<double, 2> x = rnd<double>(11, -3, 3, 50, 70), y = rnd<double>(12, -3, 3, 50, 70), r;
+        xt::noalias(r) = 3.0 * x - 2.0 * y;
+        xtb::xtensor<double, 2> dx = xtb::to_device(x), dy = xtb::to_device(y), dr;
+        xt::noalias(dr) = 3.0 * dx - 2.0 * dy;
+        CHECK(same_bits(xtb::to_host(dr), r));
+    }
+    // operator= (alias temporary path), compound assign, xarray, integer promotion, mixed types
+    {
+        xt::xarray<int> a = xt::arange<int>(0, 60).reshape({3, 4, 5});
+        xt::xarray<int> b = xt::arange<int>(1, 21).reshape({4, 5});
+        xtb::xarray<int> da = xtb::to_device(a), db = xtb::to_device(b);
+        xtb::xarray<int> dc = da * db - da / db + (da % db);
+        xt::xarray<int> c = a * b - a / b + (a % b);
+        CHECK(same_bits(xtb::to_host(dc), c));
+        dc = dc + da;                                   // aliasing assignment: temporary, then move
+        c = c + a;
+        CHECK(same_bits(xtb::to_host(dc), c));
+        xt::noalias(dc) += db;                          // computed assign
+        c += b;
+        CHECK(same_bits(xtb::to_host(dc), c));
+        xt::xarray<float> f = rnd<float>(13, -4, 4, 3, 4, 5);
+        xtb::xarray<float> df = xtb::to_device(f);
+        auto mixed = 2.0 * df + da;                     // double * float + int -> double
+        static_assert(std::is_same<decltype(mixed)::value_type, double>::value, "C++ promotion");
+        xtb::xarray<double> dm = mixed;
+        xt::xarray<double> hm = 2.0 * f + a;
+        CHECK(same_bits(xtb::to_host(dm), hm));
+        xtb::xarray<double> dw = xt::where(df > 0.5f, xt::sqrt(xt::abs(df)), xt::square(df));
+        xt::xarray<double> hw = xt::where(f > 0.5f, xt::sqrt(xt::abs(f)), xt::square(f));
+        CHECK(max_abs_diff(xtb::to_host(dw), hw) == 0.0);
+    }
+    // reducers: lazy xreducer assigned to a device container; mean; nested in an expression
+    {
+        xt::xarray<float> a = xt::round(rnd<float>(14, -8, 8, 24, 30, 16));    // integer valued: exact in any order
+        xtb::xarray<float> da = xtb::to_device(a);
+        xtb::xarray<float> s0 = xt::sum(da, {0}), s2 = xt::sum(da, {2}), s02 = xt::sum(da, {0, 2}), mx = xt::amax(da, {1});
+        xt::xarray<float> h0 = xt::sum(a, {0}), h2 = xt::sum(a, {2}), h02 = xt::sum(a, {0, 2}), hmx = xt::amax(a, {1});
+        CHECK(same_bits(xtb::to_host(s0), h0));
+        CHECK(same_bits(xtb::to_host(s2), h2));
+        CHECK(same_bits(xtb::to_host(s02), h02));
+        CHECK(same_bits(xtb::to_host(mx), hmx));
+        auto me = xt::mean(da, {0});
+        static_assert(std::is_same<decltype(me)::value_type, double>::value, "mean of float is double");
+        xtb::xarray<double> dmean = me;
+        xt::xarray<double> hmean = xt::mean(a, {0});
+        CHECK(same_bits(xtb::to_host(dmean), hmean));
+        xtb::xarray<float> ks = xt::sum(da, {1}, xt::keep_dims);
+        xt::xarray<float> hks = xt::sum(a, {1}, xt::keep_dims);
+        CHECK(same_bits(xtb::to_host(ks), hks));
+        xtb::xarray<float> centered = da - xt::sum(da, {0}) / 24.0f;            // reducer nested in a tree
+        xt::xarray<float> hcent = a - xt::sum(a, {0}) / 24.0f;
+        CHECK(same_bits(xtb::to_host(centered), hcent));
+    }
+    // broadcast error is raised by xtensor's own shape logic before any kernel is launched
+    {
+        xtb::xtensor<float, 2> da = xtb::to_device(xt::xtensor<float, 2>(xt::ones<float>({3, 4})));
+        xtb::xtensor<float, 1> db = xtb::to_device(xt::xtensor<float, 1>(xt::ones<float>({5})));
+        bool threw = false;
+        try { xtb::xtensor<float, 2> dc = da + db; } catch (const xt::broadcast_error&) { threw = true; }
+        CHECK(threw);
+    }
+    xtb::sync();
+    std::printf("%s (%d failures, %lld kernel launches)\n", g_failed ? "FAILED" : "OK", g_failed, (long long) xtb_launch_count(0));
+    return g_failed ? 1 : 0;
+}
