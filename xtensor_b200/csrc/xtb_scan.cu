@@ -1,11 +1,383 @@
-// xtb_scan.cu -- xtb_scan: inclusive scan along an axis (cumsum / cumprod).
-// Replaces detail::accumulator_impl (include/xtensor/reducers/xaccumulator.hpp:215-341).
+// xtb_scan.cu -- xtb_scan: inclusive scan along an axis (xt::cumsum / xt::cumprod).
+//
+// Replaces detail::accumulator_impl (include/xtensor/reducers/xaccumulator.hpp:215-341):
+// the reference copies the input into a dense result (promoting the value type,
+// :224-234) and scans it in place with a serial loop along the axis (:282-294), or
+// over the flattened row-major traversal when no axis is given (:299-341).
+//
+//   k_scan_lookback : scan along a contiguous run (last axis, or the flat scan).
+//                     Single pass, decoupled look-back (Merrill & Garland): a tile of
+//                     2048 elements publishes its aggregate, then a warp looks back over
+//                     its predecessors' aggregates / inclusive prefixes.  Tile prefixes are
+//                     always accumulated in ascending tile order, so floating-point results
+//                     do not depend on timing (run-to-run deterministic).
+//   k_scan_columns  : scan along a strided axis: one thread per (outer, inner) column walks
+//                     the axis in the reference's order (bit-exact, also for floating point),
+//                     coalesced across the inner dims.
+#include <algorithm>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
+
+namespace xtb {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kLookbackBuf = 1024;
+
+struct ScanParams {
+    const char* in;
+    char* out;
+    int32_t in_dtype;
+    int32_t op;                   // XTB_RED_SUM / XTB_RED_PROD
+    int64_t n;                    // scan length
+    int64_t rows;                 // independent contiguous scans (lookback) / outer count (columns)
+    int64_t inner;                // columns kernel: product of dims after the axis
+    int64_t in_axis_stride;       // elements
+    // outer (and, for the columns kernel, inner) coordinates -> input offset
+    int32_t n_outer;
+    int64_t outer_shape[XTB_MAX_DIM];
+    int64_t outer_stride[XTB_MAX_DIM];
+    FastDiv outer_div[XTB_MAX_DIM];
+    int32_t n_inner;
+    int64_t inner_shape[XTB_MAX_DIM];
+    int64_t inner_stride[XTB_MAX_DIM];
+    FastDiv inner_div[XTB_MAX_DIM];
+    // lookback state
+    uint32_t tiles_per_row;
+    uint32_t total_tiles;
+    uint32_t* ticket;
+    uint32_t* status;             // 0 = not ready, 1 = aggregate ready, 2 = inclusive prefix ready
+    char* aggregate;
+    char* prefix;
+};
+
+template <class T> XTB_DEV T load_cast(const char* p, int dt) {
+    switch (dt) {
+        case XTB_BOOL: return (T) (*(const uint8_t*) p != 0);
+        case XTB_I8: return (T) * (const int8_t*) p;
+        case XTB_U8: return (T) * (const uint8_t*) p;
+        case XTB_I16: return (T) * (const int16_t*) p;
+        case XTB_U16: return (T) * (const uint16_t*) p;
+        case XTB_I32: return (T) * (const int32_t*) p;
+        case XTB_U32: return (T) * (const uint32_t*) p;
+        case XTB_I64: return (T) * (const long long*) p;
+        case XTB_U64: return (T) * (const unsigned long long*) p;
+        case XTB_F32: return (T) * (const float*) p;
+        default: return (T) * (const double*) p;
+    }
+}
+
+template <class T> XTB_DEV T scan_op(int op, T a, T b) { return op == XTB_RED_PROD ? (T) (a * b) : (T) (a + b); }
+template <class T> XTB_DEV T scan_identity(int op) { return op == XTB_RED_PROD ? T(1) : T(0); }
+
+XTB_DEV int64_t scan_offset(uint32_t lin, int n, const int64_t* shape, const int64_t* stride, const FastDiv* div) {
+    int64_t off = 0;
+    for (int d = n - 1; d > 0; --d) {
+        const uint32_t q = fd_div(lin, div[d]);
+        off += (int64_t) (lin - q * (uint32_t) shape[d]) * stride[d];
+        lin = q;
+    }
+    return n > 0 ? off + (int64_t) lin * stride[0] : 0;
+}
+
+template <class T> XTB_DEV T shfl_up_t(T v, int d) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long u;
+        memcpy(&u, &v, 8);
+        u = __shfl_up_sync(0xffffffffu, u, d);
+        T r;
+        memcpy(&r, &u, 8);
+        return r;
+    } else {
+        unsigned u;
+        memcpy(&u, &v, 4);
+        u = __shfl_up_sync(0xffffffffu, u, d);
+        T r;
+        memcpy(&r, &u, 4);
+        return r;
+    }
+}
+
+// ---- contiguous scan, decoupled look-back ---------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_constant__ ScanParams p) {
+    __shared__ uint32_t s_tile;
+    __shared__ T s_warp[kScanThreads / 32];
+    __shared__ T s_prefix;
+    __shared__ T s_buf[kLookbackBuf];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int op = p.op;
+    // tiles are taken in launch order, so every predecessor of a tile is already running
+    if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= p.total_tiles) return;
+    const uint32_t row = tile / p.tiles_per_row;
+    const uint32_t trow = tile - row * p.tiles_per_row;   // tile index within its row
+    const int64_t base = (int64_t) trow * kScanTile + (int64_t) tid * kScanItems;
+    const int isz = dtype_size(p.in_dtype);
+    const char* in_row = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
+    // load + thread-local inclusive scan
+    T x[kScanItems];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int64_t j = base + i;
+        x[i] = j < p.n ? load_cast<T>(in_row + j * p.in_axis_stride * isz, p.in_dtype) : scan_identity<T>(op);
+    }
+#pragma unroll
+    for (int i = 1; i < kScanItems; ++i) x[i] = scan_op<T>(op, x[i - 1], x[i]);
+    // block-wide exclusive scan of the thread totals
+    T incl = x[kScanItems - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T y = shfl_up_t<T>(incl, d);
+        if (lane >= d) incl = scan_op<T>(op, y, incl);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    T warp_off = scan_identity<T>(op);
+    for (int w = 0; w < warp; ++w) warp_off = scan_op<T>(op, warp_off, s_warp[w]);
+    const T excl_lane = shfl_up_t<T>(incl, 1);
+    T thread_off = lane == 0 ? warp_off : scan_op<T>(op, warp_off, excl_lane);
+    // tile aggregate = total of the last warp prefix
+    T tile_prefix = scan_identity<T>(op);
+    if (p.tiles_per_row > 1) {
+        T* agg = (T*) p.aggregate;
+        T* pre = (T*) p.prefix;
+        if (tid == kScanThreads - 1) {
+            const T total = scan_op<T>(op, thread_off, x[kScanItems - 1]);
+            if (trow == 0) {
+                pre[tile] = total;
+                __threadfence();
+                atomicExch(&p.status[tile], 2u);
+            } else {
+                agg[tile] = total;
+                __threadfence();
+                atomicExch(&p.status[tile], 1u);
+            }
+            s_prefix = total;  // reused below as the tile's own aggregate
+        }
+        __syncthreads();
+        if (trow > 0) {
+            if (warp == 0) {
+                // look back over the predecessors in this row, 32 at a time; collect aggregates
+                // (nearest first) until a tile with an inclusive prefix is found
+                int collected = 0;
+                T found_prefix = scan_identity<T>(op);
+                int64_t look = (int64_t) trow - 1;    // nearest predecessor still to inspect
+                bool done = false;
+                while (!done) {
+                    const int64_t mine = look - lane;
+                    uint32_t st = 2u;  // lanes before the start of the row behave like "prefix = identity"
+                    T v = scan_identity<T>(op);
+                    if (mine >= 0) {
+                        const uint32_t idx = row * p.tiles_per_row + (uint32_t) mine;
+                        do {
+                            st = *((volatile uint32_t*) &p.status[idx]);
+                        } while (st == 0u);
+                        __threadfence();
+                        v = st == 2u ? ((volatile T*) pre)[idx] : ((volatile T*) agg)[idx];
+                    }
+                    const uint32_t has_prefix = __ballot_sync(0xffffffffu, st == 2u);
+                    const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest lane with a prefix
+                    if (lane < first && collected + lane < kLookbackBuf) s_buf[collected + lane] = v;
+                    if (has_prefix) {
+                        found_prefix = __shfl_sync(0xffffffffu, v, first);
+                        collected += first;
+                        done = true;
+                    } else {
+                        collected += 32;
+                        look -= 32;
+                        if (collected + 32 > kLookbackBuf) {
+                            // buffer full: wait for the inclusive prefix of the next tile instead
+                            const uint32_t idx = row * p.tiles_per_row + (uint32_t) look;
+                            if (lane == 0) {
+                                uint32_t s2;
+                                do {
+                                    s2 = *((volatile uint32_t*) &p.status[idx]);
+                                } while (s2 != 2u);
+                                __threadfence();
+                                found_prefix = ((volatile T*) pre)[idx];
+                            }
+                            found_prefix = __shfl_sync(0xffffffffu, found_prefix, 0);
+                            done = true;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    // ascending tile order: prefix, then the collected aggregates from far to near
+                    T acc = found_prefix;
+                    for (int i = collected - 1; i >= 0; --i) acc = scan_op<T>(op, acc, s_buf[i]);
+                    const T own = s_prefix;
+                    pre[tile] = scan_op<T>(op, acc, own);
+                    __threadfence();
+                    atomicExch(&p.status[tile], 2u);
+                    s_prefix = acc;
+                }
+            }
+            __syncthreads();
+            tile_prefix = s_prefix;
+        }
+    }
+    const T off = (p.tiles_per_row > 1 && trow > 0) ? scan_op<T>(op, tile_prefix, thread_off) : thread_off;
+    T* out_row = (T*) p.out + (int64_t) row * p.n;
+    const bool has_off = !(trow == 0 && tid == 0);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int64_t j = base + i;
+        if (j < p.n) out_row[j] = has_off ? scan_op<T>(op, off, x[i]) : x[i];
+    }
+}
+
+// ---- strided axis: one thread per column ------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ ScanParams p) {
+    const int64_t cols = p.rows * p.inner;
+    const int isz = dtype_size(p.in_dtype);
+    for (int64_t c = (int64_t) blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t) gridDim.x * 256) {
+        const uint32_t o = (uint32_t) (c / p.inner);
+        const uint32_t in_i = (uint32_t) (c - (int64_t) o * p.inner);
+        const char* src = p.in + (scan_offset(o, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) +
+                                  scan_offset(in_i, p.n_inner, p.inner_shape, p.inner_stride, p.inner_div)) * isz;
+        T* dst = (T*) p.out + (int64_t) o * p.n * p.inner + in_i;
+        const int64_t sstep = p.in_axis_stride * isz;
+        T acc = load_cast<T>(src, p.in_dtype);
+        dst[0] = acc;
+        int64_t i = 1;
+        for (; i + 4 <= p.n; i += 4) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = load_cast<T>(src + (i + u) * sstep, p.in_dtype);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc = scan_op<T>(p.op, acc, v[u]);
+                dst[(i + u) * p.inner] = acc;
+            }
+        }
+        for (; i < p.n; ++i) {
+            acc = scan_op<T>(p.op, acc, load_cast<T>(src + i * sstep, p.in_dtype));
+            dst[i * p.inner] = acc;
+        }
+    }
+}
+
+template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, bool columns) {
+    if (columns) {
+        const int64_t cols = p.rows * p.inner;
+        const unsigned grid = (unsigned) std::min<int64_t>((cols + 255) / 256, (int64_t) ctx->sm_count * 32);
+        k_scan_columns<T><<<grid, 256, 0, ctx->stream>>>(p);
+        note_launch("k_scan_columns");
+        return check_launch("k_scan_columns");
+    }
+    k_scan_lookback<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(p);
+    note_launch("k_scan_lookback");
+    return check_launch("k_scan_lookback");
+}
+
+}  // namespace xtb
 
 using namespace xtb;
 
 extern "C" int xtb_scan(int op, int acc_type, const xtb_operand* in, int axis, const xtb_operand* out) {
-    (void) op; (void) acc_type; (void) in; (void) axis; (void) out;
-    XTB_FAIL(XTB_ERR_UNSUPPORTED, "xtb_scan is not implemented yet");
+    if (!in || !out) XTB_FAIL(XTB_ERR_INVALID, "null argument");
+    if (op != XTB_RED_SUM && op != XTB_RED_PROD) XTB_FAIL(XTB_ERR_INVALID, "scan supports sum and prod");
+    if (acc_type < XTB_I32 || acc_type > XTB_F64) XTB_FAIL(XTB_ERR_INVALID, "accumulator must be a register type");
+    if (in->ndim < 0 || in->ndim > XTB_MAX_DIM) XTB_FAIL(XTB_ERR_INVALID, "rank out of range");
+    if (in->dtype < 0 || in->dtype >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "bad dtype");
+    if (axis >= in->ndim) XTB_FAIL(XTB_ERR_AXIS, "Axis larger than expression dimension in accumulator.");
+    if (out->dtype != acc_type) XTB_FAIL(XTB_ERR_INVALID, "scan output must have the accumulator dtype");
+    const int nd = in->ndim;
+    int64_t total = 1;
+    for (int d = 0; d < nd; ++d) total *= in->shape[d];
+    // the result is dense row-major (the reference scans a fresh copy of the input)
+    {
+        int64_t ototal = 1, expect = 1;
+        for (int d = 0; d < out->ndim; ++d) ototal *= out->shape[d];
+        if (ototal != total) XTB_FAIL(XTB_ERR_SHAPE, "scan output has %lld elements, input %lld", (long long) ototal, (long long) total);
+        for (int d = out->ndim - 1; d >= 0; --d) {
+            if (out->shape[d] != 1 && out->stride[d] != expect) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan output must be dense row-major");
+            expect *= out->shape[d];
+        }
+        if (axis >= 0 && out->ndim != nd) XTB_FAIL(XTB_ERR_SHAPE, "scan output rank mismatch");
+    }
+    if (total == 0) return XTB_OK;
+    DeviceCtx* ctx;
+    XTB_TRY(get_ctx(&ctx));
+
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = operand_ptr(in, dtype_size(in->dtype));
+    p.out = operand_ptr(out, dtype_size(out->dtype));
+    p.in_dtype = in->dtype;
+    p.op = op;
+    int64_t st[XTB_MAX_DIM];
+    for (int d = 0; d < nd; ++d) st[d] = in->shape[d] == 1 ? 0 : in->stride[d];
+    bool columns = false;
+    if (axis < 0) {
+        // flat scan in row-major traversal order: needs a dense row-major view of the input to be one run
+        bool dense = true;
+        int64_t expect = 1;
+        for (int d = nd - 1; d >= 0; --d) {
+            if (in->shape[d] != 1 && st[d] != expect) dense = false;
+            expect *= in->shape[d];
+        }
+        if (dense) {
+            p.n = total;
+            p.rows = 1;
+            p.in_axis_stride = 1;
+            p.n_outer = 0;
+        } else {
+            XTB_FAIL(XTB_ERR_UNSUPPORTED, "flat scan of a non-contiguous view: evaluate it into a container first");
+        }
+    } else {
+        p.n = in->shape[axis];
+        p.in_axis_stride = st[axis];
+        int64_t outer = 1, inner = 1;
+        for (int d = 0; d < axis; ++d) {
+            p.outer_shape[p.n_outer] = in->shape[d];
+            p.outer_stride[p.n_outer] = st[d];
+            ++p.n_outer;
+            outer *= in->shape[d];
+        }
+        for (int d = axis + 1; d < nd; ++d) {
+            p.inner_shape[p.n_inner] = in->shape[d];
+            p.inner_stride[p.n_inner] = st[d];
+            ++p.n_inner;
+            inner *= in->shape[d];
+        }
+        p.rows = outer;
+        p.inner = inner;
+        columns = inner > 1;
+        if (outer >= 0x7fffffffLL || inner >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many independent rows");
+    }
+    for (int d = 0; d < p.n_outer; ++d) p.outer_div[d] = make_fastdiv((uint32_t) std::min<int64_t>(p.outer_shape[d], 0x7fffffff));
+    for (int d = 0; d < p.n_inner; ++d) p.inner_div[d] = make_fastdiv((uint32_t) std::min<int64_t>(p.inner_shape[d], 0x7fffffff));
+    if (!columns) {
+        const int64_t tpr = (p.n + kScanTile - 1) / kScanTile;
+        const int64_t tiles = tpr * p.rows;
+        if (tiles >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
+        p.tiles_per_row = (uint32_t) tpr;
+        p.total_tiles = (uint32_t) tiles;
+        // ticket + status + aggregate + prefix
+        const size_t asz = dtype_size(acc_type);
+        const size_t bytes = 256 + (size_t) tiles * 4 + 256 + 2 * ((size_t) tiles * asz + 256);
+        void* scratch = nullptr;
+        XTB_TRY(ensure_scratch(ctx, bytes, &scratch));
+        char* s = (char*) scratch;
+        p.ticket = (uint32_t*) s;
+        p.status = (uint32_t*) (s + 256);
+        size_t off = 256 + (((size_t) tiles * 4 + 255) / 256) * 256;
+        p.aggregate = s + off;
+        off += (((size_t) tiles * asz + 255) / 256) * 256;
+        p.prefix = s + off;
+        XTB_CUDA(cudaMemsetAsync(s, 0, 256 + (size_t) tiles * 4, ctx->stream));
+    }
+    switch (acc_type) {
+        case XTB_I32: case XTB_U32: return launch_scan<uint32_t>(p, ctx, columns);
+        case XTB_I64: case XTB_U64: return launch_scan<unsigned long long>(p, ctx, columns);
+        case XTB_F32: return launch_scan<float>(p, ctx, columns);
+        default: return launch_scan<double>(p, ctx, columns);
+    }
 }
