@@ -268,6 +268,20 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
             }
         }
     }
+    // preconditions of k_reduce_rows_exact
+    p.exact_rows = 0;
+    if (inner && p.nk == 1 && p.nr == 1 && p.G <= 32 && p.nsplit == 1 && V > 1 && p.rshape[0] % V == 0 &&
+        p.rvec_total == p.G && !p.has_initial && p.out_dtype == p.acc_rt && p.in_rt == p.acc_rt &&
+        (p.kshape[0] == 1 || p.out_kstride[0] == 1) && p.K < 0x7fffffffLL) {
+        bool ok = true;
+        for (int k = 0; k < in.n_leaves; ++k) {
+            const RdLeaf& L = p.leaf[k];
+            int64_t span = (L.kstride[0] < 0 ? -L.kstride[0] : L.kstride[0]) * (p.kshape[0] - 1) +
+                           (L.rstride[0] < 0 ? -L.rstride[0] : L.rstride[0]) * (p.rshape[0] - 1);
+            ok = ok && span < 0x7fffffffLL && L.mode != MODE_GATHER;
+        }
+        p.exact_rows = ok;
+    }
     if (p.nsplit > 1) {
         void* scratch = nullptr;
         const size_t bytes = (size_t) p.nsplit * (size_t) p.K * dtype_size(p.acc_rt);

@@ -48,6 +48,7 @@ struct RdParams {
     uint64_t identity_bits;
     uint64_t initial_bits;
     // inner kernel
+    int32_t exact_rows;     // k_reduce_rows_exact applies (host-verified preconditions)
     int32_t G;              // lanes per output: 1..32 or 256
     uint32_t vpr;           // vectors per innermost reduced row
     FastDiv vpr_div;
@@ -373,6 +374,67 @@ __global__ void __launch_bounds__(256) k_reduce_inner_warp(const __grid_constant
     }
 }
 
+// ---- innermost dim reduced, short rows, exact fit ---------------------------------------------
+// The common "reduce the last axis" shape (cfg3 axis 2: 16.7 M rows of 16 floats): one kept dim,
+// one reduced dim whose V-wide vectors exactly fill the G lanes of a group, dense output of the
+// accumulator type.  Everything the general kernel decides per element is decided once on the
+// host, so a warp round (32 outputs) is: G batched 128-bit loads per lane, G tiny shuffle trees,
+// one coalesced 128-byte store.  32-bit index math throughout.
+template <class Eval, class Acc, class S, int V>
+__global__ void __launch_bounds__(256) k_reduce_rows_exact(const __grid_constant__ RdParams p) {
+    constexpr int NL = Eval::kLeaves;
+    constexpr int U = 4;
+    const int G = p.G;
+    const int lane = threadIdx.x & 31;
+    const int li = lane & (G - 1);
+    const int g = lane / G;
+    const uint32_t K = (uint32_t) p.K;
+    const uint32_t rounds = (K + 31) >> 5;
+    const uint32_t warp0 = blockIdx.x * 8 + (threadIdx.x >> 5);
+    constexpr int RT = Eval::kResultType;
+    constexpr int osz = dtype_size(RT);
+    PreFetch<NL, U, S, V> pf;
+    for (uint32_t round = warp0; round < rounds; round += gridDim.x * 8) {
+        const uint32_t out_base = round << 5;
+        S keep = (S) p.identity_bits;
+        for (int it0 = 0; it0 < G; it0 += U) {
+            int nvalid[U];
+            uint32_t kos[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                kos[u] = out_base + g * G + it0 + u;
+                nvalid[u] = (it0 + u < G && kos[u] < K) ? V : 0;
+            }
+            RdLeafLoader<Eval, S, V, U, 0>::run(p, nvalid, 1, pf, [&](const RdLeaf& L, int sz, int u) -> const char* {
+                const uint32_t ko = nvalid[u] > 0 ? kos[u] : 0u;
+                return L.ptr + (int64_t) ((int32_t) ko * (int32_t) L.kstride[0] + (int32_t) (li * V) * (int32_t) L.rstride[0]) * sz;
+            });
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (it0 + u < G) {     // uniform over the warp
+                    pf.u = u;
+                    S x[V];
+                    Eval::template run<S, V>(p.prog, pf, x);
+                    S r[1] = {x[0]};
+#pragma unroll
+                    for (int v = 1; v < V; ++v) {
+                        S y[1] = {x[v]};
+                        Acc::template step<S, 1>(p, r, y);
+                    }
+                    if (nvalid[u] == 0) r[0] = (S) p.identity_bits;
+                    for (int o = G >> 1; o > 0; o >>= 1) {
+                        S y[1] = {shfl_xor<S>(r[0], o)};
+                        Acc::template step<S, 1>(p, r, y);
+                    }
+                    if (li == it0 + u) keep = r[0];
+                }
+            }
+        }
+        const uint32_t ko = out_base + lane;
+        if (ko < K) store_elem<S>(p.out_ptr + (int64_t) ko * osz, RT, RT, keep);
+    }
+}
+
 // ---- innermost dim reduced, one block (256 lanes) per output ----------------------------
 template <class Eval, class Acc, class S, int V>
 __global__ void __launch_bounds__(256) k_reduce_inner_block(const __grid_constant__ RdParams p) {
@@ -519,6 +581,16 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
 template <class Eval, class Acc, class S, int V>
 static int launch_reduce(const RdParams& p, DeviceCtx* ctx, bool inner, const char* evname) {
     char name[96];
+    if constexpr (Eval::kPrefetch) {
+        if (inner && p.exact_rows) {
+            const int64_t rounds = (p.K + 31) / 32;
+            const unsigned grid = (unsigned) std::min<int64_t>((rounds + 7) / 8, (int64_t) ctx->sm_count * 64);
+            snprintf(name, sizeof(name), "k_reduce_rows_exact<%s,S%d,V%d>[G=%d]", evname, (int) sizeof(S) * 8, V, p.G);
+            k_reduce_rows_exact<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
+            note_launch(name);
+            return check_launch(name);
+        }
+    }
     if (inner && p.G <= 32) {
         const int64_t rounds = (p.K + 31) / 32;
         dim3 grid((unsigned) std::min<int64_t>((rounds + 7) / 8, (int64_t) ctx->sm_count * 64), (unsigned) p.nsplit);
