@@ -143,11 +143,16 @@ template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S 
 // program.  dtype / element size are constants; the access mode is one uniform branch per leaf.
 template <class Eval, class S, int V, int U, int K> struct RdLeafLoader {
     template <class PF, class AddrFn>
-    static XTB_DEV void run(const RdParams& p, const int (&nvalid)[U], int64_t gather_stride_elems_sel, PF& pf, AddrFn addr_of) {
+    static XTB_DEV void run(const RdParams& p, const int (&nvalid)[U], int64_t gather_stride_elems_sel, PF& pf, AddrFn addr_of,
+                            bool skip_invariant = false) {
         if constexpr (K < Eval::kLeaves) {
             constexpr int dt = Eval::template leaf_dtype<K>();
             constexpr int sz = dtype_size(dt);
             const RdLeaf& L = p.leaf[K];
+            if (skip_invariant && L.rstride[0] == 0 && p.nr == 1) {
+                RdLeafLoader<Eval, S, V, U, K + 1>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
+                return;
+            }
             const char* addr[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) addr[u] = addr_of(L, sz, u);
@@ -178,7 +183,7 @@ template <class Eval, class S, int V, int U, int K> struct RdLeafLoader {
 #pragma unroll
                     for (int v = 0; v < V; ++v) pf.pre[K][u][v] = (v < nvalid[u]) ? load_elem<S>(addr[u] + v * step, dt) : S(0);
             }
-            RdLeafLoader<Eval, S, V, U, K + 1>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of);
+            RdLeafLoader<Eval, S, V, U, K + 1>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
         }
     }
 };
@@ -511,11 +516,13 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
                     int nvalid[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) nvalid[u] = (r + u < rend) ? f.nvalid : 0;
+                    // leaves that do not depend on the reduced index (e.g. the mean in square(a - mean))
+                    // keep the registers staged by the first iteration
                     RdLeafLoader<Eval, S, V, U, 0>::run(p, nvalid, 0, pf, [&](const RdLeaf& L, int sz, int u) -> const char* {
                         const int64_t koff = rd_kept_offset(p, ko0, L.kstride);
                         const int64_t ru = nvalid[u] > 0 ? r + u : rbeg;
                         return L.ptr + (koff + ru * L.rstride[0]) * sz;
-                    });
+                    }, r != rbeg);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (nvalid[u] > 0) {
