@@ -201,6 +201,13 @@ int  xtb_event_destroy(void* event);
 int  xtb_assign(const xtb_program* program, const xtb_operand* out,
                 const xtb_operand* leaves);
 
+/* Same as xtb_assign, but `out` and every leaf live in HOST memory (dense row-major; pinned
+ * memory from xtb_host_alloc makes the copies asynchronous).  The leading dimension is cut
+ * into chunks of about `chunk_bytes` (<= 0: default) and H2D / kernel / D2H of consecutive
+ * chunks are pipelined on three streams; returns when the host result is complete. */
+int  xtb_assign_host(const xtb_program* program, const xtb_operand* out,
+                     const xtb_operand* leaves, int64_t chunk_bytes);
+
 /* out = reduce_{op}( program(leaves...), axes ).
  *   ndim / shape : the iteration space = broadcast shape of the expression
  *   axes[n_axes] : sorted, unique, in range (else XTB_ERR_AXIS), n_axes may be 0

@@ -292,3 +292,24 @@ def test_compound_assign(xt, gpu):
     assert_bit_exact(d.numpy(), a + b)
     xt.noalias(d).multiplies_assign(3.0)
     assert_bit_exact(d.numpy(), (a + b) * 3.0)
+
+
+def test_assign_host_streamed(xt, gpu):
+    """xtb_assign_host: host-resident operands streamed through the device in chunks."""
+    import ctypes as C
+    from xtensor_b200 import capi
+    shape = (37, 50, 64)
+    a, d = rnd(shape, seed=3), rnd(shape, seed=5)
+    b = rnd((1, 50, 1), lo=0.5, hi=1.5, seed=4)
+    H = xt.HostArray.from_numpy
+    ha, hb, hd = H(a), H(b), H(d)
+    expr = xt.sin(ha) * hb + F32(2.0) * hd
+    lw = xt.lower(expr)
+    out = xt.HostArray.empty(shape, xt.F32)
+    prog, ops, oop = lw.program(), lw.operands(), out.operand()
+    for chunk in (0, 40000, 1 << 30):              # default, many small chunks, a single chunk
+        out.owner[:] = 0
+        capi.check(gpu.xtb_assign_host(C.byref(prog), C.byref(oop), ops, chunk))
+        dev = xt.evaluate(xt.sin(xt.DeviceArray.from_numpy(a)) * xt.DeviceArray.from_numpy(b)
+                          + F32(2.0) * xt.DeviceArray.from_numpy(d)).numpy()
+        assert_bit_exact(out.numpy(), dev)
