@@ -657,6 +657,64 @@ namespace xtb
         int emit_value(context& c, const E& e, int want);
 
         template <class E>
+        struct is_strided_view_node : std::false_type
+        {
+        };
+
+        template <class CT, class S, xt::layout_type L, class FST>
+        struct is_strided_view_node<xt::xstrided_view<CT, S, L, FST>> : std::true_type
+        {
+        };
+
+        // reshape_view(container, shape) (views/xstrided_view.hpp:850-878, used by xt::variance) is an
+        // xstrided_view over a *flat adaptor*: it has shape / strides / offset but no data().  Over a
+        // contiguous container the flat index is the storage index, so it is still an affine leaf.
+        template <class E>
+        inline xtb_operand describe_flat_view(const E& e)
+        {
+            const auto& inner = e.expression();
+            using I = std::decay_t<decltype(inner)>;
+            static_assert(xt::has_data_interface<I>::value, "xtb200: reshape_view over a non-container expression cannot be lowered");
+            if (!inner.is_contiguous())
+            {
+                XTENSOR_THROW(std::runtime_error, "xtb200: reshape_view needs a contiguous operand");
+            }
+            using value_type = typename E::value_type;
+            xtb_operand op{};
+            op.base = const_cast<void*>(static_cast<const void*>(inner.data()));
+            op.offset = static_cast<std::int64_t>(inner.data_offset() + e.data_offset());
+            op.dtype = dtype_v<value_type>;
+            op.ndim = static_cast<std::int32_t>(e.dimension());
+            std::size_t d = 0;
+            for (auto it = e.shape().begin(); it != e.shape().end(); ++it, ++d)
+            {
+                op.shape[d] = static_cast<std::int64_t>(*it);
+            }
+            d = 0;
+            for (auto it = e.strides().begin(); it != e.strides().end(); ++it, ++d)
+            {
+                op.stride[d] = static_cast<std::int64_t>(*it);
+            }
+            return op;
+        }
+
+        template <class E>
+        inline xtb_operand describe_leaf(const E& e)
+        {
+            if constexpr (xt::has_data_interface<E>::value)
+            {
+                return describe(e);
+            }
+            else
+            {
+                static_assert(is_strided_view_node<E>::value,
+                              "xtb200: this expression node has no strided data interface and cannot be "
+                              "lowered (index / filter / keep-drop views are out of scope; there is no CPU fallback)");
+                return describe_flat_view(e);
+            }
+        }
+
+        template <class E>
         struct is_leaf_node
             : std::bool_constant<!is_scalar_node<E>::value && !is_function_node<E>::value && !is_reducer_node<E>::value
                                  && !is_broadcast_node<E>::value>
@@ -673,7 +731,7 @@ namespace xtb
             }
             else if constexpr (is_leaf_node<D>::value)
             {
-                return {XTB_SRC_LEAF, c.leaf(std::addressof(e), describe(e))};
+                return {XTB_SRC_LEAF, c.leaf(std::addressof(e), describe_leaf(e))};
             }
             else
             {
@@ -823,10 +881,7 @@ namespace xtb
             }
             else
             {
-                static_assert(xt::has_data_interface<D>::value,
-                              "xtb200: this expression node has no strided data interface and cannot be "
-                              "lowered (index / filter / keep-drop views are out of scope; there is no CPU fallback)");
-                c.emit(XTB_OP_PUSH, dtype_v<typename D::value_type>, XTB_SRC_LEAF, c.leaf(std::addressof(e), describe(e)));
+                c.emit(XTB_OP_PUSH, dtype_v<typename D::value_type>, XTB_SRC_LEAF, c.leaf(std::addressof(e), describe_leaf(e)));
                 rt = regtype(dtype_v<typename D::value_type>);
             }
             if (want >= 0 && rt != want)
@@ -981,6 +1036,141 @@ namespace xt
             }
         }
     };
+}
+
+namespace xt
+{
+    // ---------------------------------------------------------------- eager reducers
+    // xt::sum(e, axes, xt::evaluation_strategy::immediate) reaches reduce_immediate through an
+    // unqualified call in detail::reduce_impl (reducers/xreducer.hpp:943-953); the generic version
+    // walks e.storage() on the host (:289-565).  This more-constrained overload is selected for
+    // device-tagged operands and runs the reduction kernel instead.
+    template <class F, class E, class X, class O>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto reduce_immediate(F&& f, E&& e, X&& axes, O&& raw_options)
+    {
+        using functors = std::decay_t<F>;
+        using reduce_functor_type = typename functors::reduce_functor_type;
+        using init_functor_type = typename functors::init_functor_type;
+        using expr_value_type = typename std::decay_t<E>::value_type;
+        using result_type = std::decay_t<decltype(std::declval<reduce_functor_type>()(
+            std::declval<init_functor_type>()(),
+            std::declval<expr_value_type>()
+        ))>;
+        using options_t = reducer_options<result_type, std::decay_t<O>>;
+        options_t options(raw_options);
+        constexpr int op = xtb::lower::reduce_op_of<reduce_functor_type>::value;
+        static_assert(op >= 0, "xtb200: only sum / prod / amax / amin reducers can be lowered");
+        (void) f;
+
+        const std::size_t nd = e.dimension();
+        std::int32_t ax[XTB_MAX_DIM] = {0};
+        int na = 0;
+        for (auto a : axes)
+        {
+            ax[na++] = static_cast<std::int32_t>(a);
+        }
+        // same checks and messages as reducers/xreducer.hpp:336-350 (raised by the library)
+        constexpr bool keep = typename options_t::keep_dims();
+        std::vector<std::size_t> out_shape;
+        for (std::size_t d = 0; d < nd; ++d)
+        {
+            bool reduced = false;
+            for (int i = 0; i < na; ++i)
+            {
+                reduced = reduced || (static_cast<std::size_t>(ax[i]) == d);
+            }
+            if (!reduced)
+            {
+                out_shape.push_back(e.shape()[d]);
+            }
+            else if (keep)
+            {
+                out_shape.push_back(1);
+            }
+        }
+        xtb::xarray<result_type> result;
+        result.resize(out_shape);
+        xtb::lower::context c;
+        xtb::lower::emit_value(c, e, -1);
+        std::int64_t shape[XTB_MAX_DIM] = {0};
+        for (std::size_t d = 0; d < nd; ++d)
+        {
+            shape[d] = static_cast<std::int64_t>(e.shape()[d]);
+        }
+        const void* initial = nullptr;
+        result_type init_v{};
+        if constexpr (options_t::has_initial_value)
+        {
+            init_v = static_cast<result_type>(options.initial_value);
+            initial = &init_v;
+        }
+        xtb_operand oop = xtb::lower::describe(result);
+        const int st = xtb_reduce(op, xtb::regtype(xtb::dtype_v<result_type>), &c.prog, c.leaves, static_cast<int>(nd), shape, na, ax,
+                                  keep ? 1 : 0, initial, &oop, 0);
+        if (st == XTB_ERR_AXIS)
+        {
+            XTENSOR_THROW(std::runtime_error, xtb_last_error());
+        }
+        xtb::check(st);
+        return result;
+    }
+
+    // ---------------------------------------------------------------- accumulators
+    // xt::cumsum / xt::cumprod call accumulate() unqualified (core/xmath.hpp:2247-2297); the generic
+    // accumulator_impl scans res.storage() on the host (reducers/xaccumulator.hpp:215-341).
+    namespace detail
+    {
+        template <class F, class E>
+        inline auto b200_accumulate(F&&, E&& e, int axis)
+        {
+            using functor = std::decay_t<F>;
+            using accumulate_functor_type = typename functor::accumulate_functor_type;
+            using init_type = typename functor::init_value_type;
+            using expr_value_type = typename std::decay_t<E>::value_type;
+            using return_type = std::decay_t<decltype(std::declval<accumulate_functor_type>()(
+                std::declval<init_type>(),
+                std::declval<expr_value_type>()
+            ))>;
+            constexpr int op = xtb::lower::reduce_op_of<accumulate_functor_type>::value;
+            static_assert(op == XTB_RED_SUM || op == XTB_RED_PROD, "xtb200: only cumsum / cumprod can be lowered");
+            auto&& src = xt::eval(e);          // containers pass through, expressions become device temporaries
+            if (axis >= static_cast<int>(src.dimension()))
+            {
+                XTENSOR_THROW(std::runtime_error, "Axis larger than expression dimension in accumulator.");
+            }
+            xtb::xarray<return_type> result;
+            std::vector<std::size_t> shp;
+            if (axis < 0)
+            {
+                shp.push_back(src.size());
+            }
+            else
+            {
+                shp.assign(src.shape().begin(), src.shape().end());
+            }
+            result.resize(shp);
+            xtb_operand in = xtb::lower::describe(src);
+            xtb_operand out = xtb::lower::describe(result);
+            xtb::check(xtb_scan(op, xtb::regtype(xtb::dtype_v<return_type>), &in, axis, &out));
+            return result;
+        }
+    }
+
+    template <class F, class E, class EVS = DEFAULT_STRATEGY_ACCUMULATORS, XTL_REQUIRES(is_evaluation_strategy<EVS>)>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto accumulate(F&& f, E&& e, EVS = EVS())
+    {
+        return detail::b200_accumulate(std::forward<F>(f), std::forward<E>(e), -1);
+    }
+
+    template <class F, class E, class EVS = DEFAULT_STRATEGY_ACCUMULATORS>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto accumulate(F&& f, E&& e, std::ptrdiff_t axis, EVS = EVS())
+    {
+        const std::size_t ax = normalize_axis(e.dimension(), axis);
+        return detail::b200_accumulate(std::forward<F>(f), std::forward<E>(e), static_cast<int>(ax));
+    }
 }
 
 namespace xtb

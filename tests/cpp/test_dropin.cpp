@@ -140,6 +140,34 @@ int main()
         xt::xarray<float> hcent = a - xt::sum(a, {0}) / 24.0f;
         CHECK(same_bits(xtb::to_host(centered), hcent));
     }
+    // immediate evaluation strategy and accumulators (overloads selected by the expression tag)
+    {
+        xt::xarray<double> a = xt::round(rnd<double>(15, -8, 8, 12, 20, 9));
+        xtb::xarray<double> da = xtb::to_device(a);
+        auto si = xt::sum(da, {0, 1}, xt::evaluation_strategy::immediate);
+        xt::xarray<double> hsi = xt::sum(a, {0, 1}, xt::evaluation_strategy::immediate);
+        CHECK(same_bits(xtb::to_host(si), hsi));
+        auto mi = xt::amin(da, {2}, xt::keep_dims | xt::evaluation_strategy::immediate);
+        xt::xarray<double> hmi = xt::amin(a, {2}, xt::keep_dims | xt::evaluation_strategy::immediate);
+        CHECK(same_bits(xtb::to_host(mi), hmi));
+        xt::xarray<double> hvar = xt::variance(a, {0});                 // two-pass, uses eval(mean(immediate))
+        xtb::xarray<double> dvar = xt::variance(da, {0});
+        CHECK(max_abs_diff(xtb::to_host(dvar), hvar) <= 1e-12 * 64);
+        auto c1 = xt::cumsum(da, 1);
+        xt::xarray<double> hc1 = xt::cumsum(a, 1);
+        CHECK(same_bits(xtb::to_host(c1), hc1));
+        auto cf = xt::cumsum(da);
+        xt::xarray<double> hcf = xt::cumsum(a);
+        CHECK(same_bits(xtb::to_host(cf), hcf));
+        xt::xarray<short> sh = {short(1), short(2), short(3), short(4)};  // test_xaccumulator.cpp:22-34
+        auto cs = xt::cumsum(xtb::xarray<short>(xtb::to_device(sh)));
+        static_assert(std::is_same<decltype(cs)::value_type, int>::value, "short -> int promotion");
+        xt::xarray<int> expect = {1, 3, 6, 10};
+        CHECK(same_bits(xtb::to_host(cs), expect));
+        auto cp = xt::cumprod(da * 0.5 + 1.0, 2);                           // accumulator over an expression
+        xt::xarray<double> hcp = xt::cumprod(a * 0.5 + 1.0, 2);
+        CHECK(max_abs_diff(xtb::to_host(cp), hcp) <= 1e-9 * std::fabs(hcp(0, 0, 8)) + 1e-6);
+    }
     // broadcast error is raised by xtensor's own shape logic before any kernel is launched
     {
         xtb::xtensor<float, 2> da = xtb::to_device(xt::xtensor<float, 2>(xt::ones<float>({3, 4})));
