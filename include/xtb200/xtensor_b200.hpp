@@ -1173,6 +1173,54 @@ namespace xt
     }
 }
 
+namespace xt
+{
+    // ---------------------------------------------------------------- a op= scalar
+    // The generic scalar_computed_assign (core/xassign.hpp:525-537) loops over d.storage() on the
+    // host.  For the device tag that member template is specialised: `a += 3.1` becomes the
+    // in-place kernel  a = static_cast<T>(a + 3.1)  with the same C++ promotion.
+    namespace detail
+    {
+        template <class F>
+        struct b200_scalar_op
+        {
+            static constexpr int value = -1;
+        };
+#define XTB_SCALAR_OP(F, OP)                  \
+    template <>                               \
+    struct b200_scalar_op<F>                  \
+    {                                         \
+        static constexpr int value = OP;      \
+    };
+        XTB_SCALAR_OP(std::plus<>, XTB_OP_ADD)
+        XTB_SCALAR_OP(std::minus<>, XTB_OP_SUB)
+        XTB_SCALAR_OP(std::multiplies<>, XTB_OP_MUL)
+        XTB_SCALAR_OP(std::divides<>, XTB_OP_DIV)
+        XTB_SCALAR_OP(std::modulus<>, XTB_OP_MOD)
+        XTB_SCALAR_OP(std::bit_and<>, XTB_OP_BAND)
+        XTB_SCALAR_OP(std::bit_or<>, XTB_OP_BOR)
+        XTB_SCALAR_OP(std::bit_xor<>, XTB_OP_BXOR)
+#undef XTB_SCALAR_OP
+    }
+
+    template <>
+    template <class E1, class E2, class F>
+    inline void xexpression_assigner<xtb::b200_expression_tag>::scalar_computed_assign(xexpression<E1>& e1, const E2& e2, F&&)
+    {
+        E1& d = e1.derived_cast();
+        using T = typename E1::value_type;
+        constexpr int op = detail::b200_scalar_op<std::decay_t<F>>::value;
+        static_assert(op >= 0, "xtb200: unsupported scalar computed assignment");
+        using common_t = decltype(std::declval<T>() + std::declval<E2>());
+        const int t = xtb::regtype(xtb::dtype_v<common_t>);
+        xtb::lower::context c;
+        xtb::lower::emit_value(c, d, t);
+        c.emit(op, t, XTB_SRC_IMM, c.imm(e2, t));
+        xtb_operand out = xtb::lower::describe_leaf(d);
+        xtb::check(xtb_assign(&c.prog, &out, c.leaves));
+    }
+}
+
 namespace xtb
 {
     // ---------------------------------------------------------------- host <-> device

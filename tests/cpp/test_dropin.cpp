@@ -107,6 +107,18 @@ int main()
         xt::noalias(dc) += db;                          // computed assign
         c += b;
         CHECK(same_bits(xtb::to_host(dc), c));
+        dc *= 3;                                        // scalar computed assign (core/xassign.hpp:525-537)
+        c *= 3;
+        dc -= 7;
+        c -= 7;
+        CHECK(same_bits(xtb::to_host(dc), c));
+        xt::xarray<double> q = rnd<double>(21, -4, 4, 3, 4, 5);
+        xtb::xarray<double> dq = xtb::to_device(q);
+        xt::noalias(dq) += 3.123;                       // benchmark_assign.cpp assign_x_scalar_computed
+        q += 3.123;
+        dq /= 1.5;
+        q /= 1.5;
+        CHECK(same_bits(xtb::to_host(dq), q));
         xt::xarray<float> f = rnd<float>(13, -4, 4, 3, 4, 5);
         xtb::xarray<float> df = xtb::to_device(f);
         auto mixed = 2.0 * df + da;                     // double * float + int -> double

@@ -32,6 +32,14 @@ static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ct
             if (k64 == w64 && V == (k64 ? 2 : 4) && p.out.dtype == sprogs::result_type(*e->prog)) return e->launch_ew(p, ctx);
         }
     }
+    if (p.idx32 && p.total_vec < (int64_t) 0x7fffffff && getenv("XTB_NO_STAGED") == nullptr) {
+        // run-time program with 32-bit offsets: staged interpreter (cp.async operand staging)
+        EwParams q = p;
+        for (int k = 0; k < q.n_leaves; ++k) if (q.leaf[k].mode == MODE_LINEAR) q.leaf[k].mode = MODE_VEC;
+        if (q.out.mode == MODE_LINEAR) q.out.mode = MODE_VEC;
+        if (w64) return V == 2 ? launch_ew_staged<uint64_t, 2>(q, ctx) : launch_ew_staged<uint64_t, 1>(q, ctx);
+        return V == 4 ? launch_ew_staged<uint32_t, 4>(q, ctx) : launch_ew_staged<uint32_t, 1>(q, ctx);
+    }
     EwParams q = p;  // the generic kernel does not know MODE_LINEAR
     for (int k = 0; k < q.n_leaves; ++k) if (q.leaf[k].mode == MODE_LINEAR) q.leaf[k].mode = MODE_VEC;
     if (q.out.mode == MODE_LINEAR) q.out.mode = MODE_VEC;
@@ -156,7 +164,7 @@ static int launch_space(const xtb_program* prog, const Space& s, const char* con
     }
     // 32-bit offsets + linear shortcut for the rank <= 3 kernels
     {
-        bool ok32 = s.ndim <= 3;
+        bool ok32 = true;
         auto fill32 = [&](EwLeaf& L, bool is_out) {
             int64_t span = 0, dense = 1;
             bool linear = (L.mode == MODE_VEC);
@@ -171,10 +179,9 @@ static int launch_space(const xtb_program* prog, const Space& s, const char* con
             if (linear && s.total < 0x7fffffffLL) L.mode = MODE_LINEAR;
             (void) is_out;
         };
-        if (s.ndim <= 3) {
-            for (int k = 0; k < prog->n_leaves; ++k) fill32(p.leaf[k], false);
-            fill32(p.out, true);
-        }
+        for (int k = 0; k < prog->n_leaves; ++k) fill32(p.leaf[k], false);
+        fill32(p.out, true);
+        for (int d = 0; d < s.ndim; ++d) ok32 = ok32 && s.shape[d] < 0x7fffffffLL;
         p.idx32 = ok32;
         if (!ok32 || !ew_nd_ok_rank(s.ndim)) {
             // the generic kernel does not know MODE_LINEAR

@@ -541,6 +541,153 @@ static int launch_ew_tile(const EwParams& p, DeviceCtx* ctx, const char* evname)
     return check_launch(name);
 }
 
+// ---- staged interpreter kernel -----------------------------------------------------------------
+// Run-time programs cannot rely on the compiler to hoist loads out of the interpreter loop, so
+// memory-level parallelism is built explicitly: every thread first issues cp.async copies of all
+// the vectors it will need (leaves x ITEMS, 16 bytes each) into its private shared-memory slots,
+// waits once, and only then interprets.  PUSH then reads shared memory (dynamic leaf index is
+// free there), and the opcode switch runs once per V-wide vector (vec_unary / vec_binary).
+constexpr int kStageItems = 2;
+
+XTB_DEV void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+XTB_DEV void cp_async_8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+XTB_DEV void cp_async_4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+XTB_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// thread-private staging slot of (leaf k, item it): 16 bytes holding V elements in storage dtype
+struct StagedFetch {
+    const EwParams& p;
+    const uint4* stage;   // [n_leaves][kStageItems][256]
+    int it;
+    template <class S, int V> XTB_DEV void load(int k, int dt, S (&x)[V]) const {
+        const char* s = (const char*) &stage[(k * kStageItems + it) * 256 + threadIdx.x];
+        const int sz = dtype_size(dt);
+        if (p.leaf[k].mode == MODE_BCAST) {
+            const S e = load_elem<S>(s, dt);
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = e;
+        } else if (sz == 4 && V == 4) {
+            const uint4 r = *(const uint4*) s;
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = (S) w[v & 3];
+        } else if (sz == 8 && V == 2 && sizeof(S) == 8) {
+            const uint4 r = *(const uint4*) s;
+            x[0] = (S) (((uint64_t) r.y << 32) | r.x);
+            if (V > 1) x[V > 1 ? 1 : 0] = (S) (((uint64_t) r.w << 32) | r.z);
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = load_elem<S>(s + v * sz, dt);
+        }
+    }
+};
+
+template <class S, int V>
+__global__ void __launch_bounds__(256) k_ew_staged(const __grid_constant__ EwParams p) {
+    extern __shared__ uint4 stage[];
+    const int nd = p.ndim;
+    const uint32_t inner = (uint32_t) p.shape[nd - 1];
+    const uint32_t total = (uint32_t) p.total_vec;
+    const uint32_t base = blockIdx.x * (256u * kStageItems) + threadIdx.x;
+    int32_t idx[kStageItems][XTB_MAX_DIM];
+    uint32_t col[kStageItems];
+    int nvalid[kStageItems];
+#pragma unroll
+    for (int it = 0; it < kStageItems; ++it) {
+        uint32_t vec = base + it * 256u;
+        const bool live = vec < total;
+        if (!live) vec = 0;
+        uint32_t row = fd_div(vec, p.div_vpr);
+        col[it] = (vec - row * p.vec_per_row) * V;
+        for (int d = nd - 2; d >= 0; --d) {
+            const uint32_t q = d == 0 ? 0u : fd_div(row, p.div_dim[d]);
+            idx[it][d] = (int32_t) (d == 0 ? row : row - q * (uint32_t) p.shape[d]);
+            row = q;
+        }
+        const uint32_t rem = inner - col[it];
+        nvalid[it] = live ? (rem < (uint32_t) V ? (int) rem : V) : 0;
+    }
+    // phase 1: asynchronous copies of every operand vector into this thread's slots
+    for (int k = 0; k < p.n_leaves; ++k) {
+        const EwLeaf& L = p.leaf[k];
+        const int sz = dtype_size(L.dtype);
+#pragma unroll
+        for (int it = 0; it < kStageItems; ++it) {
+            if (nvalid[it] == 0) continue;
+            int32_t off = (int32_t) col[it] * (int32_t) L.stride[nd - 1];
+            for (int d = 0; d < nd - 1; ++d) off += idx[it][d] * (int32_t) L.stride[d];
+            const char* g = L.ptr + (int64_t) off * sz;
+            char* sdst = (char*) &stage[(k * kStageItems + it) * 256 + threadIdx.x];
+            const int bytes = V * sz;
+            if (L.mode == MODE_VEC && nvalid[it] == V && bytes >= 4) {
+                if (bytes == 16) cp_async_16(sdst, g);
+                else if (bytes == 8) cp_async_8(sdst, g);
+                else if (bytes == 4) cp_async_4(sdst, g);
+                else { cp_async_16(sdst, g); cp_async_16(sdst + 16, g + 16); }
+            } else if (L.mode == MODE_BCAST) {
+                if (sz == 4) cp_async_4(sdst, g);
+                else if (sz == 8) cp_async_8(sdst, g);
+                else if (sz == 2) *(uint16_t*) sdst = *(const uint16_t*) g;
+                else *(uint8_t*) sdst = *(const uint8_t*) g;
+            } else {
+                // tails, misaligned rows, strided gathers: element by element
+                const int64_t step = (L.mode == MODE_VEC ? 1 : L.stride[nd - 1]) * sz;
+                for (int v = 0; v < nvalid[it]; ++v) {
+                    const char* ge = g + v * step;
+                    char* se = sdst + v * sz;
+                    if (sz == 4) cp_async_4(se, ge);
+                    else if (sz == 8) cp_async_8(se, ge);
+                    else if (sz == 2) *(uint16_t*) se = *(const uint16_t*) ge;
+                    else *(uint8_t*) se = *(const uint8_t*) ge;
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+    // phase 2: interpret
+#pragma unroll
+    for (int it = 0; it < kStageItems; ++it) {
+        if (nvalid[it] == 0) continue;
+        StagedFetch f{p, stage, it};
+        S r[V];
+        interpret<S, V>(p.prog, f, r);
+        const EwLeaf& O = p.out;
+        const int osz = dtype_size(O.dtype);
+        int32_t off = (int32_t) col[it] * (int32_t) O.stride[nd - 1];
+        for (int d = 0; d < nd - 1; ++d) off += idx[it][d] * (int32_t) O.stride[d];
+        char* ptr = (char*) O.ptr + (int64_t) off * osz;
+        if (O.mode == MODE_VEC && nvalid[it] == V) {
+            store_vec<S, V>(ptr, O.dtype, (int) p.out_rt, r);
+        } else {
+            const int64_t step = O.stride[nd - 1] * osz;
+            for (int v = 0; v < nvalid[it]; ++v) store_elem<S>(ptr + v * step, O.dtype, (int) p.out_rt, r[v]);
+        }
+    }
+}
+
+template <class S, int V>
+static int launch_ew_staged(const EwParams& p, DeviceCtx* ctx) {
+    const int64_t per_block = 256 * kStageItems;
+    const unsigned grid = (unsigned) ((p.total_vec + per_block - 1) / per_block);
+    const size_t smem = (size_t) std::max(p.n_leaves, 1) * kStageItems * 256 * sizeof(uint4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_ew_staged<S, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, XTB_MAX_LEAVES * kStageItems * 256 * (int) sizeof(uint4));
+        attr_set = true;
+    }
+    char name[96];
+    snprintf(name, sizeof(name), "k_ew_staged<interp,S%d,V%d>", (int) sizeof(S) * 8, V);
+    k_ew_staged<S, V><<<grid, 256, smem, ctx->stream>>>(p);
+    note_launch(name);
+    return check_launch(name);
+}
+
 // ---- registry of compile-time programs ---------------------------------------------
 // Programs whose instruction stream equals a pre-instantiated SProg run a fully
 // unrolled kernel; anything else runs the interpreter.  Both paths share every
