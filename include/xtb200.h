@@ -35,8 +35,10 @@
 #ifndef XTB200_H
 #define XTB200_H
 
+#ifndef __CUDACC_RTC__ /* NVRTC (run-time kernel specialisation) brings its own fixed-width types */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {

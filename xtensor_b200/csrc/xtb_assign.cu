@@ -4,6 +4,7 @@
 // selection.  Kernels: xtb_ew.cuh.
 #include <cstdlib>
 #include "xtb_ew.cuh"
+#include "xtb_jit.hpp"
 
 namespace xtb {
 
@@ -19,6 +20,25 @@ static int dispatch_tile(const xtb_program* prog, const EwParams& p, DeviceCtx* 
         const StaticEntry* e = find_static(prog);
         if (e && sprogs::is64(*e->prog) == w64) return e->launch_tile(p, ctx);
     }
+    int64_t tile_elems = 1;
+    for (int d = 0; d < p.ndim; ++d) tile_elems *= p.shape[d];
+    if (!no_static && p.idx32 && jit_program_ok(prog) && p.out.dtype == (int) p.out_rt && jit_worthwhile(tile_elems)) {
+        JitSpec spec;
+        spec.kind = JIT_TILE;
+        spec.w64 = w64;
+        void* fn = nullptr;
+        if (jit_get(ctx, prog, spec, &fn) == XTB_OK) {
+            int64_t batch = 1;
+            for (int d = 0; d < p.ndim - 1; ++d)
+                if (d != p.tile_i) batch *= p.shape[d];
+            const int64_t blocks = batch * p.ntile_i * p.ntile_j;
+            if (blocks < 0x7fffffffLL) {
+                XTB_TRY(jit_launch(fn, (unsigned) blocks, 1, 256, 0, ctx->stream, &p));
+                note_launch(w64 ? "k_ew_tile_static<jit,S64>" : "k_ew_tile_static<jit,S32>");
+                return XTB_OK;
+            }
+        }
+    }
     if (w64) return launch_ew_tile<InterpEval, uint64_t>(p, ctx, "interp");
     return launch_ew_tile<InterpEval, uint32_t>(p, ctx, "interp");
 }
@@ -30,6 +50,28 @@ static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ct
         if (e) {
             const bool k64 = sprogs::is64(*e->prog);
             if (k64 == w64 && V == (k64 ? 2 : 4) && p.out.dtype == sprogs::result_type(*e->prog)) return e->launch_ew(p, ctx);
+        }
+    }
+    // no ahead-of-time instantiation: specialise the same kernel template for this program at run time
+    if (!no_static && ew_nd_ok(p) && V == (w64 ? 2 : 4) && jit_program_ok(prog) && p.out.dtype == (int) p.out_rt &&
+        jit_worthwhile(p.total_vec * V)) {
+        JitSpec spec;
+        spec.kind = JIT_EW;
+        spec.w64 = w64;
+        spec.V = V;
+        spec.nd = p.ndim;
+        void* fn = nullptr;
+        if (jit_get(ctx, prog, spec, &fn) == XTB_OK) {
+            const int64_t per_block = 256 * 2;
+            EwParams q = p;
+            bool fast = (p.shape[p.ndim - 1] % V == 0) && (p.total_vec % per_block == 0) && p.out.mode != MODE_GATHER && p.out.mode != MODE_BCAST;
+            for (int k = 0; k < p.n_leaves; ++k) fast = fast && p.leaf[k].mode != MODE_GATHER;
+            q.fast = fast;
+            char name[96];
+            snprintf(name, sizeof(name), "k_ew<jit,S%d,V%d,ND%d>%s", w64 ? 64 : 32, V, p.ndim, fast ? "[fast]" : "");
+            XTB_TRY(jit_launch(fn, (unsigned) ((p.total_vec + per_block - 1) / per_block), 1, 256, 0, ctx->stream, &q));
+            note_launch(name);
+            return XTB_OK;
         }
     }
     if (p.idx32 && p.total_vec < (int64_t) 0x7fffffff && getenv("XTB_NO_STAGED") == nullptr) {

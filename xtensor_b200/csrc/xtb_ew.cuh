@@ -9,9 +9,11 @@
 // The stepper odometer of xiterator.hpp:589-631 becomes closed-form index math:
 //   addr_k(i) = base_k + sum_d i_d * stride_k[d],  stride 0 on broadcast dims.
 #pragma once
+#include "xtb_ops.cuh"
+#ifndef XTB_RTC
 #include <algorithm>
 #include "xtb_common.hpp"
-#include "xtb_ops.cuh"
+#endif
 #include "xtb_static_programs.cuh"
 
 namespace xtb {
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(256) k_ew_generic(const __grid_constant__ EwPa
 }
 
 
+#ifndef XTB_RTC
 // ---- launch ---------------------------------------------------------------------
 // Rank-specialised kernels (compile-time programs): 32-bit index math, ND <= 3.
 template <class Eval, class S, int V>
@@ -337,6 +340,7 @@ static int launch_ew_generic(const EwParams& p, DeviceCtx* ctx, const char* evna
     return check_launch(name);
 }
 
+#endif  // XTB_RTC
 // ---- tiled kernel: transposed leaves -------------------------------------------------------
 // Replaces stepper_assigner::run (xassign.hpp:644-695) for the case the CPU handles worst: an
 // operand whose fast dim is not the output's (xt::transpose, column-major leaves).  A block
@@ -519,6 +523,7 @@ __global__ void __launch_bounds__(256) k_ew_tile_static(const __grid_constant__ 
     }
 }
 
+#ifndef XTB_RTC
 template <class Eval, class S>
 static int launch_ew_tile(const EwParams& p, DeviceCtx* ctx, const char* evname) {
     int64_t batch = 1;
@@ -541,6 +546,7 @@ static int launch_ew_tile(const EwParams& p, DeviceCtx* ctx, const char* evname)
     return check_launch(name);
 }
 
+#endif  // XTB_RTC
 // ---- staged interpreter kernel -----------------------------------------------------------------
 // Run-time programs cannot rely on the compiler to hoist loads out of the interpreter loop, so
 // memory-level parallelism is built explicitly: every thread first issues cp.async copies of all
@@ -671,6 +677,7 @@ __global__ void __launch_bounds__(256) k_ew_staged(const __grid_constant__ EwPar
     }
 }
 
+#ifndef XTB_RTC
 template <class S, int V>
 static int launch_ew_staged(const EwParams& p, DeviceCtx* ctx) {
     const int64_t per_block = 256 * kStageItems;
@@ -688,6 +695,8 @@ static int launch_ew_staged(const EwParams& p, DeviceCtx* ctx) {
     return check_launch(name);
 }
 
+#endif  // XTB_RTC
+#ifndef XTB_RTC
 // ---- registry of compile-time programs ---------------------------------------------
 // Programs whose instruction stream equals a pre-instantiated SProg run a fully
 // unrolled kernel; anything else runs the interpreter.  Both paths share every
@@ -722,5 +731,7 @@ inline const StaticEntry* find_static(const xtb_program* prog) {
             if (sprog_matches(*t.entries[i].prog, prog)) return &t.entries[i];
     return nullptr;
 }
+
+#endif  // XTB_RTC
 
 }  // namespace xtb

@@ -8,6 +8,7 @@
 #include <climits>
 #include <cstdlib>
 #include "xtb_reduce.cuh"
+#include "xtb_jit.hpp"
 
 namespace xtb {
 
@@ -66,6 +67,25 @@ static int run_reduce_kernel(const xtb_program* prog, const RdParams& p, DeviceC
             const StaticReduceEntry& e = t.entries[i];
             if (e.binop == p.binop && e.acc_rt == p.acc_rt && sprogs::is64(*e.prog) == w64 && sprog_matches(*e.prog, prog))
                 return e.launch(p, ctx, inner);
+        }
+    }
+    if (!no_static && p.in_rt == p.acc_rt && V == (w64 ? 2 : 4) && p.K < 0x7fffffff && jit_program_ok(prog) &&
+        jit_worthwhile(p.K * std::max<int64_t>(p.R, 1))) {
+        // run-time specialisation of the reduction kernel for this (program, reducer, accumulator)
+        const RdLaunch g = reduce_geometry(p, ctx, inner, p.out_dtype == p.acc_rt);
+        static const int kinds[4] = {JIT_RED_ROWS_EXACT, JIT_RED_INNER_WARP, JIT_RED_INNER_BLOCK, JIT_RED_OUTER};
+        static const char* names[4] = {"k_reduce_rows_exact<jit>", "k_reduce_inner_warp<jit>", "k_reduce_inner_block<jit>", "k_reduce_outer<jit>"};
+        JitSpec spec;
+        spec.kind = kinds[g.kind];
+        spec.w64 = w64;
+        spec.V = V;
+        spec.binop = p.binop;
+        spec.acc_rt = p.acc_rt;
+        void* fn = nullptr;
+        if (jit_get(ctx, prog, spec, &fn) == XTB_OK) {
+            XTB_TRY(jit_launch(fn, g.gx, g.gy, 256, 0, ctx->stream, &p));
+            note_launch(names[g.kind]);
+            return XTB_OK;
         }
     }
     if (w64) {

@@ -585,6 +585,34 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
     }
 }
 
+#ifndef XTB_RTC
+// launch geometry shared by the ahead-of-time and the run-time specialised kernels
+struct RdLaunch {
+    int kind;          // 0 rows_exact, 1 inner_warp, 2 inner_block, 3 outer
+    unsigned gx, gy;
+};
+static inline RdLaunch reduce_geometry(const RdParams& p, const DeviceCtx* ctx, bool inner, bool allow_exact) {
+    RdLaunch g{3, 1, (unsigned) p.nsplit};
+    if (inner && p.exact_rows && allow_exact) {
+        const int64_t rounds = (p.K + 31) / 32;
+        g.kind = 0;
+        g.gx = (unsigned) std::min<int64_t>((rounds + 7) / 8, (int64_t) ctx->sm_count * 64);
+        g.gy = 1;
+    } else if (inner && p.G <= 32) {
+        const int64_t rounds = (p.K + 31) / 32;
+        g.kind = 1;
+        g.gx = (unsigned) std::min<int64_t>((rounds + 7) / 8, (int64_t) ctx->sm_count * 64);
+    } else if (inner) {
+        g.kind = 2;
+        g.gx = (unsigned) std::min<int64_t>(p.K, (int64_t) ctx->sm_count * 64);
+    } else {
+        const int64_t blocks = (p.kvec_total + 255) / 256;
+        g.kind = 3;
+        g.gx = (unsigned) std::min<int64_t>(blocks, (int64_t) ctx->sm_count * 64);
+    }
+    return g;
+}
+
 template <class Eval, class Acc, class S, int V>
 static int launch_reduce(const RdParams& p, DeviceCtx* ctx, bool inner, const char* evname) {
     char name[96];
@@ -630,5 +658,7 @@ struct StaticReduceTable {
     int n;
 };
 StaticReduceTable static_reduce_table();
+
+#endif  // XTB_RTC
 
 }  // namespace xtb

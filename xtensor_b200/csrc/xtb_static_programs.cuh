@@ -8,7 +8,7 @@
 namespace xtb {
 namespace sprogs {
 
-constexpr int kCap = 12;
+constexpr int kCap = XTB_MAX_INSNS;
 using SP = SProg<kCap>;
 
 constexpr SInsn push_leaf(int k, int dt) { return {XTB_OP_PUSH, dt, XTB_SRC_LEAF, k}; }
