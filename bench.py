@@ -337,6 +337,22 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
             e = xt.transpose(a) + xt.view(b, slice(0, None, 2), slice(None))
             out["cfg4_transpose_view_f64"] = timed(lambda: xt.assign(o, e), 3 * 8192 * 8192 * 8, iters=5)
             del a, b, o, e
+        if world == 1:
+            # cumsum (north_star: xaccumulator as a decoupled look-back scan); 2 x element size per element
+            x = xt.DeviceArray.from_numpy(np.random.default_rng(2).uniform(-1, 1, 1 << 26).astype(np.float32))
+            out["cumsum_flat_f32_2^26"] = timed(lambda: xt.cumsum(x), 2 * (1 << 26) * 4)
+            x2 = x.reshape_view((8192, 8192))
+            out["cumsum_axis1_f32_8192x8192"] = timed(lambda: xt.cumsum(x2, 1), 2 * (1 << 26) * 4)
+            out["cumsum_axis0_f32_8192x8192"] = timed(lambda: xt.cumsum(x2, 0), 2 * (1 << 26) * 4)
+            del x, x2
+            # an expression with no ahead-of-time instantiation: run-time specialised kernel
+            n = 1 << 26
+            a3 = [xt.DeviceArray.from_numpy(np.random.default_rng(3 + i).uniform(0.5, 2, n).astype(np.float32)) for i in range(3)]
+            o3 = xt.DeviceArray.empty((n,), xt.F32)
+            e3 = xt.sqrt(a3[0] * a3[0] + a3[1] * a3[1]) / (a3[2] + np.float32(1.0))
+            xt.assign(o3, e3)
+            out["jit_hypot_div_f32_2^26"] = timed(lambda: xt.assign(o3, e3), 16 * n)
+            del a3, o3, e3
         # cfg5: sharded (262144, 8192) fp32: mean / variance over axis 0 (allreduce) + exp(a - mean)
         rows = 262144 // world
         cols = 8192

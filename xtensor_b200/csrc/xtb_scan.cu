@@ -21,7 +21,7 @@
 namespace xtb {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kLookbackBuf = 1024;
 
@@ -50,6 +50,11 @@ struct ScanParams {
     uint32_t* status;             // 0 = not ready, 1 = aggregate ready, 2 = inclusive prefix ready
     char* aggregate;
     char* prefix;
+    unsigned long long* packed;   // 4-byte accumulators: {status, value} in one 64-bit word per tile
+    int32_t vec_io;               // input is the accumulator dtype, unit stride, 16-byte aligned rows
+    // chunked column scan
+    int64_t chunk;                // rows per chunk (0: whole axis)
+    const char* carry;            // [nchunks][rows * inner] inclusive chunk totals scan (acc dtype)
 };
 
 template <class T> XTB_DEV T load_cast(const char* p, int dt) {
@@ -120,10 +125,21 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
     const char* in_row = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
     // load + thread-local inclusive scan
     T x[kScanItems];
+    const bool full_tile = base + kScanItems <= p.n;
+    if (p.vec_io && full_tile) {
+        constexpr int PER = 16 / sizeof(T);
+        const uint4* src = (const uint4*) (in_row + base * sizeof(T));
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        const int64_t j = base + i;
-        x[i] = j < p.n ? load_cast<T>(in_row + j * p.in_axis_stride * isz, p.in_dtype) : scan_identity<T>(op);
+        for (int q = 0; q < kScanItems / PER; ++q) {
+            const uint4 r = ldg_stream_16(src + q);
+            memcpy(&x[q * PER], &r, 16);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            const int64_t j = base + i;
+            x[i] = j < p.n ? load_cast<T>(in_row + j * p.in_axis_stride * isz, p.in_dtype) : scan_identity<T>(op);
+        }
     }
 #pragma unroll
     for (int i = 1; i < kScanItems; ++i) x[i] = scan_op<T>(op, x[i - 1], x[i]);
@@ -147,7 +163,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
         T* pre = (T*) p.prefix;
         if (tid == kScanThreads - 1) {
             const T total = scan_op<T>(op, thread_off, x[kScanItems - 1]);
-            if (trow == 0) {
+            if constexpr (sizeof(T) == 4) {
+                uint32_t bits;
+                memcpy(&bits, &total, 4);
+                const unsigned long long w = ((unsigned long long) (trow == 0 ? 2u : 1u) << 32) | bits;
+                *((volatile unsigned long long*) &p.packed[tile]) = w;     // one 64-bit store: status + value
+            } else if (trow == 0) {
                 pre[tile] = total;
                 __threadfence();
                 atomicExch(&p.status[tile], 2u);
@@ -173,11 +194,21 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
                     T v = scan_identity<T>(op);
                     if (mine >= 0) {
                         const uint32_t idx = row * p.tiles_per_row + (uint32_t) mine;
-                        do {
-                            st = *((volatile uint32_t*) &p.status[idx]);
-                        } while (st == 0u);
-                        __threadfence();
-                        v = st == 2u ? ((volatile T*) pre)[idx] : ((volatile T*) agg)[idx];
+                        if constexpr (sizeof(T) == 4) {
+                            unsigned long long w;
+                            do {
+                                w = *((volatile unsigned long long*) &p.packed[idx]);
+                            } while ((w >> 32) == 0ull);
+                            st = (uint32_t) (w >> 32);
+                            const uint32_t bits = (uint32_t) w;
+                            memcpy(&v, &bits, 4);
+                        } else {
+                            do {
+                                st = *((volatile uint32_t*) &p.status[idx]);
+                            } while (st == 0u);
+                            __threadfence();
+                            v = st == 2u ? ((volatile T*) pre)[idx] : ((volatile T*) agg)[idx];
+                        }
                     }
                     const uint32_t has_prefix = __ballot_sync(0xffffffffu, st == 2u);
                     const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest lane with a prefix
@@ -193,12 +224,21 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
                             // buffer full: wait for the inclusive prefix of the next tile instead
                             const uint32_t idx = row * p.tiles_per_row + (uint32_t) look;
                             if (lane == 0) {
-                                uint32_t s2;
-                                do {
-                                    s2 = *((volatile uint32_t*) &p.status[idx]);
-                                } while (s2 != 2u);
-                                __threadfence();
-                                found_prefix = ((volatile T*) pre)[idx];
+                                if constexpr (sizeof(T) == 4) {
+                                    unsigned long long w;
+                                    do {
+                                        w = *((volatile unsigned long long*) &p.packed[idx]);
+                                    } while ((w >> 32) != 2ull);
+                                    const uint32_t bits = (uint32_t) w;
+                                    memcpy(&found_prefix, &bits, 4);
+                                } else {
+                                    uint32_t s2;
+                                    do {
+                                        s2 = *((volatile uint32_t*) &p.status[idx]);
+                                    } while (s2 != 2u);
+                                    __threadfence();
+                                    found_prefix = ((volatile T*) pre)[idx];
+                                }
                             }
                             found_prefix = __shfl_sync(0xffffffffu, found_prefix, 0);
                             done = true;
@@ -211,9 +251,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
                     T acc = found_prefix;
                     for (int i = collected - 1; i >= 0; --i) acc = scan_op<T>(op, acc, s_buf[i]);
                     const T own = s_prefix;
-                    pre[tile] = scan_op<T>(op, acc, own);
-                    __threadfence();
-                    atomicExch(&p.status[tile], 2u);
+                    const T incl_prefix = scan_op<T>(op, acc, own);
+                    if constexpr (sizeof(T) == 4) {
+                        uint32_t bits;
+                        memcpy(&bits, &incl_prefix, 4);
+                        *((volatile unsigned long long*) &p.packed[tile]) = (2ull << 32) | bits;
+                    } else {
+                        pre[tile] = incl_prefix;
+                        __threadfence();
+                        atomicExch(&p.status[tile], 2u);
+                    }
                     s_prefix = acc;
                 }
             }
@@ -224,10 +271,25 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
     const T off = (p.tiles_per_row > 1 && trow > 0) ? scan_op<T>(op, tile_prefix, thread_off) : thread_off;
     T* out_row = (T*) p.out + (int64_t) row * p.n;
     const bool has_off = !(trow == 0 && tid == 0);
+    if (has_off) {
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        const int64_t j = base + i;
-        if (j < p.n) out_row[j] = has_off ? scan_op<T>(op, off, x[i]) : x[i];
+        for (int i = 0; i < kScanItems; ++i) x[i] = scan_op<T>(op, off, x[i]);
+    }
+    if (p.vec_io && full_tile && ((p.n * sizeof(T)) % 16 == 0 || p.rows == 1)) {
+        constexpr int PER = 16 / sizeof(T);
+        uint4* dst = (uint4*) (out_row + base);
+#pragma unroll
+        for (int q = 0; q < kScanItems / PER; ++q) {
+            uint4 r;
+            memcpy(&r, &x[q * PER], 16);
+            stg_stream_16(dst + q, r);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            const int64_t j = base + i;
+            if (j < p.n) out_row[j] = x[i];
+        }
     }
 }
 
@@ -236,6 +298,45 @@ template <class T>
 __global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ ScanParams p) {
     const int64_t cols = p.rows * p.inner;
     const int isz = dtype_size(p.in_dtype);
+    if (p.chunk > 0) {
+        // chunked: blockIdx.y owns rows [i0, i1) of every column and starts from the carry of the
+        // previous chunks (inclusive scan of the per-chunk totals, computed by two earlier launches)
+        const int64_t i0 = (int64_t) blockIdx.y * p.chunk;
+        const int64_t i1 = i0 + p.chunk < p.n ? i0 + p.chunk : p.n;
+        for (int64_t c = (int64_t) blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t) gridDim.x * 256) {
+            const uint32_t o = (uint32_t) (c / p.inner);
+            const uint32_t in_i = (uint32_t) (c - (int64_t) o * p.inner);
+            const char* src = p.in + (scan_offset(o, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) +
+                                      scan_offset(in_i, p.n_inner, p.inner_shape, p.inner_stride, p.inner_div)) * isz;
+            T* dst = (T*) p.out + (int64_t) o * p.n * p.inner + in_i;
+            const int64_t sstep = p.in_axis_stride * isz;
+            T acc = scan_identity<T>(p.op);
+            bool have = false;
+            if (blockIdx.y > 0) {
+                acc = ((const T*) p.carry)[((int64_t) o * gridDim.y + (blockIdx.y - 1)) * p.inner + in_i];
+                have = true;
+            }
+            int64_t i = i0;
+            for (; i + 4 <= i1; i += 4) {
+                T v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = load_cast<T>(src + (i + u) * sstep, p.in_dtype);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc = have ? scan_op<T>(p.op, acc, v[u]) : v[u];
+                    have = true;
+                    dst[(i + u) * p.inner] = acc;
+                }
+            }
+            for (; i < i1; ++i) {
+                const T v = load_cast<T>(src + i * sstep, p.in_dtype);
+                acc = have ? scan_op<T>(p.op, acc, v) : v;
+                have = true;
+                dst[i * p.inner] = acc;
+            }
+        }
+        return;
+    }
     for (int64_t c = (int64_t) blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t) gridDim.x * 256) {
         const uint32_t o = (uint32_t) (c / p.inner);
         const uint32_t in_i = (uint32_t) (c - (int64_t) o * p.inner);
@@ -263,12 +364,89 @@ __global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ Sc
     }
 }
 
+// per-chunk column totals: totals[(o * nch + c) * inner + i] = op over rows [c*chunk, (c+1)*chunk)
+template <class T>
+__global__ void __launch_bounds__(256) k_scan_chunk_totals(const __grid_constant__ ScanParams p, T* totals) {
+    const int64_t cols = p.rows * p.inner;
+    const int isz = dtype_size(p.in_dtype);
+    const int64_t i0 = (int64_t) blockIdx.y * p.chunk;
+    const int64_t i1 = i0 + p.chunk < p.n ? i0 + p.chunk : p.n;
+    for (int64_t c = (int64_t) blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t) gridDim.x * 256) {
+        const uint32_t o = (uint32_t) (c / p.inner);
+        const uint32_t in_i = (uint32_t) (c - (int64_t) o * p.inner);
+        const char* src = p.in + (scan_offset(o, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) +
+                                  scan_offset(in_i, p.n_inner, p.inner_shape, p.inner_stride, p.inner_div)) * isz;
+        const int64_t sstep = p.in_axis_stride * isz;
+        T acc = load_cast<T>(src + i0 * sstep, p.in_dtype);
+        int64_t i = i0 + 1;
+        for (; i + 8 <= i1; i += 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = load_cast<T>(src + (i + u) * sstep, p.in_dtype);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = scan_op<T>(p.op, acc, v[u]);
+        }
+        for (; i < i1; ++i) acc = scan_op<T>(p.op, acc, load_cast<T>(src + i * sstep, p.in_dtype));
+        totals[((int64_t) o * gridDim.y + blockIdx.y) * p.inner + in_i] = acc;
+    }
+}
+
+template <class T> static int scan_chunked_t(ScanParams p, int64_t chunk, int64_t nch, DeviceCtx* ctx) {
+    const int64_t cols = p.rows * p.inner;
+    void* scratch = nullptr;
+    const size_t each = ((size_t) cols * nch * sizeof(T) + 255) / 256 * 256;
+    XTB_TRY(ensure_scratch(ctx, 2 * each, &scratch));
+    T* totals = (T*) scratch;
+    T* carry = (T*) ((char*) scratch + each);
+    p.chunk = chunk;
+    const unsigned gx = (unsigned) std::min<int64_t>((cols + 255) / 256, (int64_t) ctx->sm_count * 32);
+    k_scan_chunk_totals<T><<<dim3(gx, (unsigned) nch), 256, 0, ctx->stream>>>(p, totals);
+    note_launch("k_scan_chunk_totals");
+    XTB_TRY(check_launch("k_scan_chunk_totals"));
+    // inclusive scan of the chunk totals along the chunk index (small): totals[o][c][i] -> carry[o][c][i]
+    ScanParams q;
+    memset(&q, 0, sizeof(q));
+    q.in = (const char*) totals;
+    q.out = (char*) carry;
+    q.in_dtype = sizeof(T) == 4 ? (std::is_same<T, float>::value ? XTB_F32 : XTB_U32) : (std::is_same<T, double>::value ? XTB_F64 : XTB_U64);
+    q.op = p.op;
+    q.n = nch;
+    q.rows = p.rows;
+    q.inner = p.inner;
+    q.in_axis_stride = p.inner;
+    q.n_outer = 1;
+    q.outer_shape[0] = p.rows;
+    q.outer_stride[0] = nch * p.inner;
+    q.outer_div[0] = make_fastdiv((uint32_t) std::min<int64_t>(p.rows, 0x7fffffff));
+    q.n_inner = 1;
+    q.inner_shape[0] = p.inner;
+    q.inner_stride[0] = 1;
+    q.inner_div[0] = make_fastdiv((uint32_t) std::min<int64_t>(p.inner, 0x7fffffff));
+    k_scan_columns<T><<<gx, 256, 0, ctx->stream>>>(q);
+    note_launch("k_scan_columns[carry]");
+    XTB_TRY(check_launch("k_scan_columns"));
+    p.carry = (const char*) carry;
+    k_scan_columns<T><<<dim3(gx, (unsigned) nch), 256, 0, ctx->stream>>>(p);
+    note_launch("k_scan_columns[chunked]");
+    return check_launch("k_scan_columns");
+}
+
+static int scan_chunked(int acc_type, const ScanParams& p, int64_t chunk, int64_t nch, DeviceCtx* ctx) {
+    switch (acc_type) {
+        case XTB_I32: case XTB_U32: return scan_chunked_t<uint32_t>(p, chunk, nch, ctx);
+        case XTB_I64: case XTB_U64: return scan_chunked_t<unsigned long long>(p, chunk, nch, ctx);
+        case XTB_F32: return scan_chunked_t<float>(p, chunk, nch, ctx);
+        default: return scan_chunked_t<double>(p, chunk, nch, ctx);
+    }
+}
+
 template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, bool columns) {
     if (columns) {
         const int64_t cols = p.rows * p.inner;
-        const unsigned grid = (unsigned) std::min<int64_t>((cols + 255) / 256, (int64_t) ctx->sm_count * 32);
-        k_scan_columns<T><<<grid, 256, 0, ctx->stream>>>(p);
-        note_launch("k_scan_columns");
+        const unsigned gx = (unsigned) std::min<int64_t>((cols + 255) / 256, (int64_t) ctx->sm_count * 32);
+        const unsigned gy = p.chunk > 0 ? (unsigned) ((p.n + p.chunk - 1) / p.chunk) : 1u;
+        k_scan_columns<T><<<dim3(gx, gy), 256, 0, ctx->stream>>>(p);
+        note_launch(p.chunk > 0 ? "k_scan_columns[chunked]" : "k_scan_columns");
         return check_launch("k_scan_columns");
     }
     k_scan_lookback<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(p);
@@ -372,7 +550,26 @@ extern "C" int xtb_scan(int op, int acc_type, const xtb_operand* in, int axis, c
         p.aggregate = s + off;
         off += (((size_t) tiles * asz + 255) / 256) * 256;
         p.prefix = s + off;
-        XTB_CUDA(cudaMemsetAsync(s, 0, 256 + (size_t) tiles * 4, ctx->stream));
+        p.packed = (unsigned long long*) p.aggregate;   // 4-byte accumulators: 8 bytes per tile fit in aggregate+prefix
+        XTB_CUDA(cudaMemsetAsync(s, 0, asz == 4 ? off + (((size_t) tiles * asz + 255) / 256) * 256 : 256 + (size_t) tiles * 4, ctx->stream));
+        p.vec_io = in->dtype == acc_type && p.in_axis_stride == 1 && ((uintptr_t) p.in % 16 == 0) && ((uintptr_t) p.out % 16 == 0) &&
+                   (p.rows == 1 || (p.n * asz) % 16 == 0);
+        if (p.vec_io && p.rows > 1)
+            for (int d = 0; d < p.n_outer; ++d) p.vec_io = p.vec_io && (p.outer_stride[d] * asz) % 16 == 0;
+    } else {
+        // few columns and a long axis: chunk the axis.  The per-chunk totals come from the reduction
+        // kernel (one extra read of the input), their scan from this kernel on a small array.
+        const int64_t cols = p.rows * p.inner;
+        const int64_t target = (int64_t) ctx->sm_count * 2048;
+        if (cols * 4 < target && p.n >= 256) {
+            int64_t nch = std::min<int64_t>(std::max<int64_t>(target / std::max<int64_t>(cols, 1), 1), p.n / 64);
+            nch = std::min<int64_t>(nch, 1024);
+            if (nch > 1) {
+                const int64_t chunk = (p.n + nch - 1) / nch;
+                nch = (p.n + chunk - 1) / chunk;
+                return scan_chunked(acc_type, p, chunk, nch, ctx);
+            }
+        }
     }
     switch (acc_type) {
         case XTB_I32: case XTB_U32: return launch_scan<uint32_t>(p, ctx, columns);
