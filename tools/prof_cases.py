@@ -43,6 +43,10 @@ for c in cases:
             f = lambda: xt.evaluate(xt.sum(a, [0]))
         else:
             f = lambda: xt.evaluate(xt.sum(xt.square(a - m), [0]))
+    elif c in ("cumsum_flat", "cumsum_ax1", "cumsum_ax0"):
+        x = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, 1 << 26).astype(np.float32))
+        x2 = x.reshape_view((8192, 8192))
+        f = {"cumsum_flat": lambda: xt.cumsum(x), "cumsum_ax1": lambda: xt.cumsum(x2, 1), "cumsum_ax0": lambda: xt.cumsum(x2, 0)}[c]
     else:
         raise SystemExit(f"unknown case {c}")
     for _ in range(REPS):

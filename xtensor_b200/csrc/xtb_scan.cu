@@ -20,7 +20,7 @@
 
 namespace xtb {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 512;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kLookbackBuf = 1024;
@@ -52,6 +52,8 @@ struct ScanParams {
     char* prefix;
     unsigned long long* packed;   // 4-byte accumulators: {status, value} in one 64-bit word per tile
     int32_t vec_io;               // input is the accumulator dtype, unit stride, 16-byte aligned rows
+    const char* tile_incl;        // != nullptr: inclusive scan of the tile totals [rows][tiles_per_row] is precomputed
+                                  // (long rows: reduce-then-scan, no look-back chain)
     // chunked column scan
     int64_t chunk;                // rows per chunk (0: whole axis)
     const char* carry;            // [nchunks][rows * inner] inclusive chunk totals scan (acc dtype)
@@ -106,7 +108,7 @@ template <class T> XTB_DEV T shfl_up_t(T v, int d) {
 
 // ---- contiguous scan, decoupled look-back ---------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan_lookback(const __grid_constant__ ScanParams p) {
     __shared__ uint32_t s_tile;
     __shared__ T s_warp[kScanThreads / 32];
     __shared__ T s_prefix;
@@ -158,7 +160,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
     T thread_off = lane == 0 ? warp_off : scan_op<T>(op, warp_off, excl_lane);
     // tile aggregate = total of the last warp prefix
     T tile_prefix = scan_identity<T>(op);
-    if (p.tiles_per_row > 1) {
+    if (p.tile_incl != nullptr) {
+        if (trow > 0) tile_prefix = ((const T*) p.tile_incl)[tile - 1];
+    } else if (p.tiles_per_row > 1) {
         T* agg = (T*) p.aggregate;
         T* pre = (T*) p.prefix;
         if (tid == kScanThreads - 1) {
@@ -290,6 +294,50 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_lookback(const __grid_con
             const int64_t j = base + i;
             if (j < p.n) out_row[j] = x[i];
         }
+    }
+}
+
+// per-tile totals for long rows (phase 1 of reduce-then-scan)
+template <class T>
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan_tile_sums(const __grid_constant__ ScanParams p, T* sums) {
+    __shared__ T s_warp[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t row = tile / p.tiles_per_row;
+    const uint32_t trow = tile - row * p.tiles_per_row;
+    const int64_t base = (int64_t) trow * kScanTile + (int64_t) tid * kScanItems;
+    const int isz = dtype_size(p.in_dtype);
+    const char* in_row = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
+    T x[kScanItems];
+    if (p.vec_io && base + kScanItems <= p.n) {
+        constexpr int PER = 16 / sizeof(T);
+        const uint4* src = (const uint4*) (in_row + base * sizeof(T));
+#pragma unroll
+        for (int q = 0; q < kScanItems / PER; ++q) {
+            const uint4 r = ldg_stream_16(src + q);
+            memcpy(&x[q * PER], &r, 16);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            const int64_t j = base + i;
+            x[i] = j < p.n ? load_cast<T>(in_row + j * p.in_axis_stride * isz, p.in_dtype) : scan_identity<T>(p.op);
+        }
+    }
+    T acc = x[0];
+#pragma unroll
+    for (int i = 1; i < kScanItems; ++i) acc = scan_op<T>(p.op, acc, x[i]);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T y = shfl_up_t<T>(acc, d);
+        if (lane >= d) acc = scan_op<T>(p.op, y, acc);
+    }
+    if (lane == 31) s_warp[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        T t = s_warp[0];
+        for (int w = 1; w < kScanThreads / 32; ++w) t = scan_op<T>(p.op, t, s_warp[w]);
+        sums[tile] = t;
     }
 }
 
@@ -448,6 +496,57 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         k_scan_columns<T><<<dim3(gx, gy), 256, 0, ctx->stream>>>(p);
         note_launch(p.chunk > 0 ? "k_scan_columns[chunked]" : "k_scan_columns");
         return check_launch("k_scan_columns");
+    }
+    if (p.tiles_per_row > 32 && p.tile_incl == nullptr) {
+        // long rows: the look-back chain (32 tiles per poll round) would bound throughput; do
+        // reduce-then-scan instead: tile totals -> their inclusive scan (recursively, a short row) ->
+        // final pass with the tile prefixes read from memory.  Deterministic, 3 passes over memory.
+        T* sums = nullptr;
+        T* incl = nullptr;
+        const size_t bytes = (size_t) p.total_tiles * sizeof(T);
+        XTB_CUDA(cudaMallocAsync((void**) &sums, bytes, ctx->stream));
+        XTB_CUDA(cudaMallocAsync((void**) &incl, bytes, ctx->stream));
+        k_scan_tile_sums<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(p, sums);
+        note_launch("k_scan_tile_sums");
+        XTB_TRY(check_launch("k_scan_tile_sums"));
+        ScanParams q;
+        memset(&q, 0, sizeof(q));
+        q.in = (const char*) sums;
+        q.out = (char*) incl;
+        q.in_dtype = sizeof(T) == 4 ? (std::is_same<T, float>::value ? XTB_F32 : XTB_U32) : (std::is_same<T, double>::value ? XTB_F64 : XTB_U64);
+        q.op = p.op;
+        q.n = p.tiles_per_row;
+        q.rows = p.rows;
+        q.in_axis_stride = 1;
+        q.n_outer = 1;
+        q.outer_shape[0] = p.rows;
+        q.outer_stride[0] = p.tiles_per_row;
+        q.outer_div[0] = make_fastdiv((uint32_t) std::min<int64_t>(p.rows, 0x7fffffff));
+        const int64_t tpr2 = (q.n + kScanTile - 1) / kScanTile;
+        q.tiles_per_row = (uint32_t) tpr2;
+        q.total_tiles = (uint32_t) (tpr2 * p.rows);
+        // look-back state of the inner scan lives in the context scratch after the outer scan's state
+        void* scratch = nullptr;
+        const size_t state = 256 + ((size_t) q.total_tiles * 4 + 255) / 256 * 256 + 2 * (((size_t) q.total_tiles * sizeof(T) + 255) / 256 * 256);
+        XTB_CUDA(cudaMallocAsync(&scratch, state, ctx->stream));
+        char* s = (char*) scratch;
+        q.ticket = (uint32_t*) s;
+        q.status = (uint32_t*) (s + 256);
+        size_t off = 256 + ((size_t) q.total_tiles * 4 + 255) / 256 * 256;
+        q.aggregate = s + off;
+        q.prefix = s + off + ((size_t) q.total_tiles * sizeof(T) + 255) / 256 * 256;
+        q.packed = (unsigned long long*) q.aggregate;
+        XTB_CUDA(cudaMemsetAsync(s, 0, state, ctx->stream));
+        XTB_TRY((launch_scan<T>(q, ctx, false)));
+        ScanParams r = p;
+        r.tile_incl = (const char*) incl;
+        k_scan_lookback<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(r);
+        note_launch("k_scan_lookback[tile prefixes precomputed]");
+        XTB_TRY(check_launch("k_scan_lookback"));
+        XTB_CUDA(cudaFreeAsync(scratch, ctx->stream));
+        XTB_CUDA(cudaFreeAsync(sums, ctx->stream));
+        XTB_CUDA(cudaFreeAsync(incl, ctx->stream));
+        return XTB_OK;
     }
     k_scan_lookback<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(p);
     note_launch("k_scan_lookback");
