@@ -197,6 +197,15 @@ int  xtb_event_record(void* event);
 int  xtb_event_elapsed_ms(void* start, void* stop, float* ms);  /* syncs on `stop` */
 int  xtb_event_destroy(void* event);
 
+/* CUDA-graph capture of a sequence of calls (kernels, xtb_allreduce) on the library stream:
+ * launch-bound pipelines (many short kernels, e.g. the sharded mean / variance / map step on
+ * 8 GPUs) replay without host launch gaps.  Between begin and end the calls are recorded, not
+ * executed; allocate outputs (and run the sequence once, to size internal scratch) beforehand. */
+int  xtb_graph_begin(void);
+int  xtb_graph_end(void** graph_exec);
+int  xtb_graph_launch(void* graph_exec);
+int  xtb_graph_destroy(void* graph_exec);
+
 /* ---- the hot path ---------------------------------------------------------- */
 /* out(i...) = static_cast<out.dtype>( program(leaves...)(i...) ) over out's shape.
  * Every leaf must be broadcastable to out's shape (else XTB_ERR_SHAPE). */

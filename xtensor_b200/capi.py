@@ -59,6 +59,7 @@ SYMBOLS = [
     "xtb_abi_version", "xtb_init", "xtb_device_count", "xtb_sync", "xtb_last_error", "xtb_set_stream",
     "xtb_get_stream", "xtb_malloc", "xtb_free", "xtb_memcpy", "xtb_memset", "xtb_host_alloc", "xtb_host_free",
     "xtb_event_create", "xtb_event_record", "xtb_event_elapsed_ms", "xtb_event_destroy",
+    "xtb_graph_begin", "xtb_graph_end", "xtb_graph_launch", "xtb_graph_destroy",
     "xtb_assign", "xtb_assign_host", "xtb_reduce", "xtb_scan", "xtb_comm_unique_id", "xtb_comm_init", "xtb_comm_destroy",
     "xtb_comm_info", "xtb_allreduce", "xtb_launch_count", "xtb_last_kernel", "xtb_program_result_type",
 ]
@@ -99,6 +100,10 @@ def lib():
         "xtb_event_record": (i32, [vp]),
         "xtb_event_elapsed_ms": (i32, [vp, vp, C.POINTER(C.c_float)]),
         "xtb_event_destroy": (i32, [vp]),
+        "xtb_graph_begin": (i32, []),
+        "xtb_graph_end": (i32, [C.POINTER(vp)]),
+        "xtb_graph_launch": (i32, [vp]),
+        "xtb_graph_destroy": (i32, [vp]),
         "xtb_assign": (i32, [C.POINTER(Program), C.POINTER(Operand), C.POINTER(Operand)]),
         "xtb_assign_host": (i32, [C.POINTER(Program), C.POINTER(Operand), C.POINTER(Operand), i64]),
         "xtb_reduce": (i32, [i32, i32, C.POINTER(Program), C.POINTER(Operand), i32, C.POINTER(i64), i32,

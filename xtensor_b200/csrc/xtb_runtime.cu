@@ -411,6 +411,40 @@ int xtb_event_destroy(void* event) {
     return XTB_OK;
 }
 
+int xtb_graph_begin(void) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    XTB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    return XTB_OK;
+}
+
+int xtb_graph_end(void** graph_exec) {
+    if (!graph_exec) XTB_FAIL(XTB_ERR_INVALID, "null graph");
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    cudaGraph_t graph = nullptr;
+    XTB_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) XTB_FAIL(XTB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    *graph_exec = (void*) exec;
+    return XTB_OK;
+}
+
+int xtb_graph_launch(void* graph_exec) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    XTB_CUDA(cudaGraphLaunch((cudaGraphExec_t) graph_exec, c->stream));
+    note_launch("cudaGraphLaunch");
+    return XTB_OK;
+}
+
+int xtb_graph_destroy(void* graph_exec) {
+    if (graph_exec) XTB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t) graph_exec));
+    return XTB_OK;
+}
+
 int64_t xtb_launch_count(int reset) {
     int64_t v = g_launches.load();
     if (reset) g_launches.store(0);

@@ -651,11 +651,13 @@ def evaluate(e, dtype: Optional[int] = None) -> Array:
     return assign(out, e)
 
 
-def _run_reducer(r: Reducer, kind, out_dtype: Optional[int] = None, allreduce: bool = False, mode: int = 0) -> Array:
+def _run_reducer(r: Reducer, kind, out_dtype: Optional[int] = None, allreduce: bool = False, mode: int = 0,
+                 out: Optional[Array] = None) -> Array:
     inner = _materialise(r.e)
     lw = Lowered()
     _emit_value(lw, inner, None)
-    out = _alloc_like(kind, r.shape, r.dtype if out_dtype is None else out_dtype)
+    if out is None:
+        out = _alloc_like(kind, r.shape, r.dtype if out_dtype is None else out_dtype)
     prog, ops, oop = lw.program(), lw.operands(), out.operand()
     nd = len(r.e.shape)
     shape = (C.c_int64 * max(nd, 1))(*r.e.shape)
