@@ -180,6 +180,29 @@ int main()
         xt::xarray<double> hcp = xt::cumprod(a * 0.5 + 1.0, 2);
         CHECK(max_abs_diff(xtb::to_host(cp), hcp) <= 1e-9 * std::fabs(hcp(0, 0, 8)) + 1e-6);
     }
+    // view on the left-hand side (xview_semantic, core/xsemantic.hpp:726-796): strided store and
+    // broadcasting into a view (test_strided_assign.cpp:178-196, test_extended_broadcast_view.cpp:811-1033)
+    {
+        xt::xarray<int> buf = xt::ones<int>({4, 6}) * -1;
+        xt::xarray<int> src = xt::arange<int>(1, 9).reshape({2, 4});
+        xtb::xarray<int> dbuf = xtb::to_device(buf), dsrc = xtb::to_device(src);
+        xt::noalias(xt::view(dbuf, xt::range(1, 3), xt::range(2, 6))) = dsrc;
+        xt::noalias(xt::view(buf, xt::range(1, 3), xt::range(2, 6))) = src;
+        CHECK(same_bits(xtb::to_host(dbuf), buf));
+        xt::xarray<int> row = xt::arange<int>(10, 16);
+        xtb::xarray<int> drow = xtb::to_device(row);
+        xt::noalias(xt::view(dbuf, xt::range(0, 4, 2), xt::all())) = drow * 2;   // broadcast a row into every other row
+        xt::view(buf, xt::range(0, 4, 2), xt::all()) = row * 2;
+        CHECK(same_bits(xtb::to_host(dbuf), buf));
+        xt::noalias(xt::view(dbuf, 3, xt::all())) += drow;                   // computed assign on a view
+        xt::noalias(xt::view(buf, 3, xt::all())) += row;
+        CHECK(same_bits(xtb::to_host(dbuf), buf));
+        xt::xarray<double> a = rnd<double>(31, -1, 1, 6, 5), out = xt::zeros<double>({5, 6});
+        xtb::xarray<double> da = xtb::to_device(a), dout = xtb::to_device(out);
+        xt::noalias(xt::transpose(dout)) = da * 2.0;                         // strided (transposed) destination
+        xt::noalias(xt::transpose(out)) = a * 2.0;
+        CHECK(same_bits(xtb::to_host(dout), out));
+    }
     // broadcast error is raised by xtensor's own shape logic before any kernel is launched
     {
         xtb::xtensor<float, 2> da = xtb::to_device(xt::xtensor<float, 2>(xt::ones<float>({3, 4})));
