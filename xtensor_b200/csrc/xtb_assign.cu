@@ -62,7 +62,7 @@ static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ct
         spec.nd = p.ndim;
         void* fn = nullptr;
         if (jit_get(ctx, prog, spec, &fn) == XTB_OK) {
-            const int64_t per_block = 256 * 2;
+            const int64_t per_block = 256 * kEwItems;
             EwParams q = p;
             bool fast = (p.shape[p.ndim - 1] % V == 0) && (p.total_vec % per_block == 0) && p.out.mode != MODE_GATHER && p.out.mode != MODE_BCAST;
             for (int k = 0; k < p.n_leaves; ++k) fast = fast && p.leaf[k].mode != MODE_GATHER;

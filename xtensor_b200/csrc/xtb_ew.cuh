@@ -211,6 +211,12 @@ template <class Eval, class S, int V, int ND, int ITEMS, bool FAST, int K> struc
     }
 };
 
+// vectors per thread of the rank <= 3 kernels (ahead-of-time and run-time specialised alike)
+#ifndef XTB_EW_ITEMS
+#define XTB_EW_ITEMS 2
+#endif
+constexpr int kEwItems = XTB_EW_ITEMS;
+
 // One thread evaluates ITEMS vectors of V consecutive inner-dim elements; within a block
 // consecutive threads take consecutive vectors (coalesced 128-bit access).  Compile-time
 // programs only: coordinates for all items first, then the batched loads of every leaf
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(256) k_ew_generic(const __grid_constant__ EwPa
 template <class Eval, class S, int V>
 static int launch_ew_nd(const EwParams& p, DeviceCtx* ctx, const char* evname) {
     const int nd = p.ndim;
-    constexpr int ITEMS = 2;
+    constexpr int ITEMS = kEwItems;
     const int64_t per_block = 256 * ITEMS;
     const unsigned grid = (unsigned) ((p.total_vec + per_block - 1) / per_block);
     char name[96];

@@ -150,7 +150,7 @@ int jit_get(const DeviceCtx* ctx, const xtb_program* prog, const JitSpec& spec, 
     std::ostringstream acc;
     acc << "xtb::StaticAcc<" << spec.binop << ", " << spec.acc_rt << ">";
     switch (spec.kind) {
-        case JIT_EW: name << "xtb::k_ew<" << eval << ", " << S << ", " << spec.V << ", " << spec.nd << ", 2>"; break;
+        case JIT_EW: name << "xtb::k_ew<" << eval << ", " << S << ", " << spec.V << ", " << spec.nd << ", xtb::kEwItems>"; break;
         case JIT_TILE: name << "xtb::k_ew_tile_static<" << eval << ", " << S << ">"; break;
         case JIT_RED_OUTER: name << "xtb::k_reduce_outer<" << eval << ", " << acc.str() << ", " << S << ", " << spec.V << ">"; break;
         case JIT_RED_INNER_WARP: name << "xtb::k_reduce_inner_warp<" << eval << ", " << acc.str() << ", " << S << ", " << spec.V << ">"; break;
