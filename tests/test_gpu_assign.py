@@ -313,3 +313,28 @@ def test_assign_host_streamed(xt, gpu):
         dev = xt.evaluate(xt.sin(xt.DeviceArray.from_numpy(a)) * xt.DeviceArray.from_numpy(b)
                           + F32(2.0) * xt.DeviceArray.from_numpy(d)).numpy()
         assert_bit_exact(out.numpy(), dev)
+
+
+def test_sin_cos_f32_own_reduction(xt, gpu):
+    """fp32 sin / cos use the backend's own Cody-Waite fast path (one range check per vector) and the
+    library routine beyond |x| > 105615: <= 2 ulp of glibc everywhere, specials preserved, and the three
+    evaluators (ahead-of-time, interpreter, generic strided) agree bit for bit."""
+    rng = np.random.default_rng(21)
+    k = np.arange(-4000, 4000, dtype=np.float64)
+    near = np.concatenate([(k * np.pi / 2).astype(np.float32), np.nextafter((k * np.pi / 2).astype(np.float32), np.float32(np.inf)),
+                           (k * np.pi / 4).astype(np.float32)])
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 105615.0, -105615.0, 105615.01, 1e-30, -1e-30, 1e-45, 3e38, -3e38,
+                        1e6, 1e9, 7e4, -9.9e4], np.float32)
+    x = np.concatenate([rng.uniform(-np.pi, np.pi, 1 << 18), rng.uniform(-100, 100, 1 << 18), rng.uniform(-105615, 105615, 1 << 18),
+                        rng.uniform(-1e7, 1e7, 1 << 16), near, special]).astype(np.float32)
+    x = np.resize(x, (x.size + 3) // 4 * 4)          # mixed small / huge / non-finite values inside one 4-vector
+    for fn in (xt.sin, xt.cos):
+        with np.errstate(invalid="ignore"):
+            got, want = run_both(xt, lambda A: fn(A), x)
+        assert ulp_distance(got, want) <= 2, fn.__name__
+        assert np.array_equal(np.signbit(got[want == 0]), np.signbit(want[want == 0]))
+        with interpreter_only():
+            interp = xt.evaluate(fn(xt.DeviceArray.from_numpy(x))).numpy()
+        assert_bit_exact(interp, got)
+        strided = xt.evaluate(fn(xt.DeviceArray.from_numpy(np.repeat(x, 2))[::2])).numpy()      # gather path, scalar evaluation
+        assert_bit_exact(strided, got)

@@ -85,3 +85,55 @@ def test_cumprod_views_and_errors(xt, gpu):
         xt.cumsum(xt.DeviceArray.from_numpy(a), 2)
     e = xt.cumsum(xt.DeviceArray.from_numpy(np.zeros((0, 3), np.float32)), 0).numpy()
     assert e.shape == (0, 3)
+
+
+# ---- the tiled kernels: staged super-tiles (long rows), packed short rows, column tiles -------------
+BIG = [
+    # contiguous axis: several super-tiles per row -> two-level look-back (block totals from 256 tiles on)
+    ((16384 * 5 + 4,), None), ((16384 * 300 + 8,), None), ((16384 * 300 + 5,), None), ((3, 16384 * 40), 1), ((5, 100003), 1),
+    # rows of one super-tile, ragged rows, short rows packed per warp / one warp per row
+    ((300, 8192), 1), ((300, 5000), 1), ((4096, 64), 1), ((4096, 4), 1), ((1000, 24), 1), ((513, 512), 1), ((77, 300), 1),
+    # strided axis: column tiles (wide, narrow with row groups, ragged, tree of 2 and 3 levels, outer dims)
+    ((3000, 512), 0), ((3000, 300), 0), ((20000, 64), 0), ((20000, 3), 0), ((70000, 8), 0), ((2, 700, 260), 1),
+    ((5, 130, 7, 9), 1), ((128, 1000), 0),
+]
+
+
+@pytest.mark.parametrize("shape,axis", BIG)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64, np.int16])
+def test_tiled_kernels_integer_valued(xt, gpu, shape, axis, dtype):
+    a = np.random.default_rng(11).integers(-3, 4, shape).astype(dtype)
+    got = xt.cumsum(xt.DeviceArray.from_numpy(a), axis).numpy()
+    want = np.cumsum(a, axis=axis, dtype=got.dtype).reshape(got.shape)
+    assert_bit_exact(got, want)
+
+
+def test_tiled_kernels_views_and_conversions(xt, gpu):
+    """Inputs the bulk-copy path cannot take (strided, unaligned, other dtype) go through registers."""
+    rng = np.random.default_rng(12)
+    a = rng.integers(-3, 4, (600, 1030)).astype(np.float32)
+    d = xt.DeviceArray.from_numpy(a)
+    assert_bit_exact(xt.cumsum(d[:, 1:1027], 0).numpy(), np.cumsum(a[:, 1:1027], axis=0))       # unaligned columns
+    assert_bit_exact(xt.cumsum(d[::2, :], 0).numpy(), np.cumsum(a[::2, :], axis=0))              # strided rows
+    assert_bit_exact(xt.cumsum(xt.transpose(d), 1).numpy(), np.cumsum(a.T, axis=1))              # scan axis strided
+    assert_bit_exact(xt.cumsum(xt.transpose(d), 0).numpy(), np.cumsum(a.T, axis=0))
+    assert_bit_exact(xt.cumsum(d, 0, dtype=xt.F64).numpy(), np.cumsum(a, axis=0, dtype=np.float64))
+    b = rng.integers(-3, 4, (3, 70001)).astype(np.int16)
+    assert_bit_exact(xt.cumsum(xt.DeviceArray.from_numpy(b), 1).numpy(), np.cumsum(b, axis=1, dtype=np.int32))
+    assert_bit_exact(xt.cumsum(xt.DeviceArray.from_numpy(b)[:, 3:], 1).numpy(), np.cumsum(b[:, 3:], axis=1, dtype=np.int32))
+    c = rng.integers(1, 3, (40, 300)).astype(np.float64) * 0.5 + 0.5                              # {1, 1.5}: cumprod exact for a while
+    c[:, 20:] = 1.0
+    assert_bit_exact(xt.cumprod(xt.DeviceArray.from_numpy(c), 0).numpy(), np.cumprod(c, axis=0))
+
+
+def test_tiled_kernels_fp_tolerance_and_determinism(xt, gpu):
+    rng = np.random.default_rng(13)
+    for shape, axis in [((1 << 22,), None), ((4096, 1024), 0), ((64, 65536), 1)]:
+        a = rng.uniform(-1, 1, shape).astype(np.float32)
+        d = xt.DeviceArray.from_numpy(a)
+        g1 = xt.cumsum(d, axis).numpy()
+        g2 = xt.cumsum(d, axis).numpy()
+        assert_bit_exact(g1, g2)                                   # fixed look-back tree: no timing dependence
+        ref = np.cumsum(a.astype(np.float64), axis=axis).reshape(g1.shape)
+        scale = np.cumsum(np.abs(a).astype(np.float64), axis=axis).reshape(g1.shape)
+        assert np.all(np.abs(g1 - ref) <= 1e-6 * np.maximum(scale, 1.0))

@@ -15,15 +15,13 @@
 //                     the axis in the reference's order (bit-exact, also for floating point),
 //                     coalesced across the inner dims.
 #include <algorithm>
+#include <cstdlib>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
 
 namespace xtb {
 
-constexpr int kScanThreads = 512;
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kScanThreads * kScanItems;
-constexpr int kLookbackBuf = 1024;
+constexpr int kScanThreads = 256;
 
 struct ScanParams {
     const char* in;
@@ -47,16 +45,12 @@ struct ScanParams {
     uint32_t tiles_per_row;
     uint32_t total_tiles;
     uint32_t* ticket;
-    uint32_t* status;             // 0 = not ready, 1 = aggregate ready, 2 = inclusive prefix ready
-    char* aggregate;
-    char* prefix;
-    unsigned long long* packed;   // 4-byte accumulators: {status, value} in one 64-bit word per tile
-    int32_t vec_io;               // input is the accumulator dtype, unit stride, 16-byte aligned rows
-    const char* tile_incl;        // != nullptr: inclusive scan of the tile totals [rows][tiles_per_row] is precomputed
-                                  // (long rows: reduce-then-scan, no look-back chain)
-    // chunked column scan
-    int64_t chunk;                // rows per chunk (0: whole axis)
-    const char* carry;            // [nchunks][rows * inner] inclusive chunk totals scan (acc dtype)
+    char* aggregate;              // {flag, value} slot per tile
+    char* prefix;                 // {flag, value} slot per block of kScanWindow tiles: the block total
+    int32_t vec_io;               // input is the accumulator dtype, unit stride, 16-byte aligned rows (in and out)
+    int32_t packed;               // short dense rows: a warp's window holds 128 / seg_vecs whole rows
+    int32_t seg_vecs;             // 16-byte vectors per row (power of two <= 128) when packed
+    int32_t st_elems;             // k_scan_stile: elements per super-tile
 };
 
 template <class T> XTB_DEV T load_cast(const char* p, int dt) {
@@ -106,239 +100,821 @@ template <class T> XTB_DEV T shfl_up_t(T v, int d) {
     }
 }
 
-// ---- contiguous scan, decoupled look-back ---------------------------------------------------
+// ---- contiguous scan: single pass, two-level decoupled look-back ------------------------------
+// Tile = 512 threads x 64 bytes.  Inside a tile the data stays in the *striped* arrangement it is
+// loaded in (warp w owns 32*ITEMS consecutive elements; its q-th 128-bit access covers vectors
+// q*32 + lane), so every global access is a fully coalesced 512-byte warp transaction; the scan is
+// done on that arrangement with shuffles (vector-local scan, one warp scan per q, carry over q).
+//
+// Across tiles: tiles of a row are grouped in blocks of kScanWindow.  A tile publishes its aggregate
+// as soon as it is known; the last tile of a block publishes the block total.  The exclusive prefix of
+// tile t in block k is
+//        tree(block totals 0..k-1)  (+)  tree(aggregates of the tiles of block k before t)
+// where tree() is a fixed-shape reduction (per-lane ascending partial sums, then a butterfly), so a
+// floating-point result depends only on the tile's position, never on timing: run-to-run
+// deterministic, no serial chain (dependency depth 2), and one read + one write of the data.
+// Tiles take a ticket in launch order, so everything a tile waits for is already running.
+constexpr int kScanWindow = 256;   // tiles per block = 32 lanes x 8
+constexpr int kScanWarpsPerTile = kScanThreads / 32;
+
+template <class T> struct ScanTile {
+    static constexpr int VEC = 16 / (int) sizeof(T);
+    static constexpr int NV = 4;
+    static constexpr int ITEMS = VEC * NV;
+    static constexpr int WARP_ELEMS = 32 * ITEMS;
+    static constexpr int TILE = kScanThreads * ITEMS;
+    static constexpr int SLOT = 2 * (int) sizeof(T);   // {flag, value}: 8 or 16 bytes, one memory transaction
+};
+
+// {flag, value} slots: written and read with ONE 64- / 128-bit access, so a reader that sees the flag
+// sees the value (no fence); 0 = empty (the state is zeroed before the launch)
+template <class T> XTB_DEV void slot_publish(char* slots, uint32_t i, T v) {
+    if constexpr (sizeof(T) == 4) {
+        uint32_t bits;
+        memcpy(&bits, &v, 4);
+        const unsigned long long w = (1ull << 32) | bits;
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slots + (size_t) i * 8), "l"(w) : "memory");
+    } else {
+        unsigned long long bits;
+        memcpy(&bits, &v, 8);
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(slots + (size_t) i * 16), "l"(1ull), "l"(bits) : "memory");
+    }
+}
+template <class T> XTB_DEV bool slot_try(const char* slots, uint32_t i, T& v) {
+    if constexpr (sizeof(T) == 4) {
+        unsigned long long w;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slots + (size_t) i * 8) : "memory");
+        const uint32_t bits = (uint32_t) w;
+        memcpy(&v, &bits, 4);
+        return (w >> 32) != 0ull;
+    } else {
+        unsigned long long f, bits;
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(f), "=l"(bits) : "l"(slots + (size_t) i * 16) : "memory");
+        memcpy(&v, &bits, 8);
+        return f != 0ull;
+    }
+}
+
+template <class T> XTB_DEV T shfl_idx_t(T v, int src) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long u;
+        memcpy(&u, &v, 8);
+        u = __shfl_sync(0xffffffffu, u, src);
+        T r;
+        memcpy(&r, &u, 8);
+        return r;
+    } else {
+        unsigned u;
+        memcpy(&u, &v, 4);
+        u = __shfl_sync(0xffffffffu, u, src);
+        T r;
+        memcpy(&r, &u, 4);
+        return r;
+    }
+}
+template <class T> XTB_DEV T shfl_xor_t(T v, int m) {
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long u;
+        memcpy(&u, &v, 8);
+        u = __shfl_xor_sync(0xffffffffu, u, m);
+        T r;
+        memcpy(&r, &u, 8);
+        return r;
+    } else {
+        unsigned u;
+        memcpy(&u, &v, 4);
+        u = __shfl_xor_sync(0xffffffffu, u, m);
+        T r;
+        memcpy(&r, &u, 4);
+        return r;
+    }
+}
+// butterfly total (the operators are commutative, so every lane ends with the same bits)
+template <class T> XTB_DEV T warp_total(int op, T v) {
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) v = scan_op<T>(op, v, shfl_xor_t<T>(v, m));
+    return v;
+}
+
+// Executed by one whole warp of a tile: gathers what precedes the tile in its row.  Returns (in every
+// lane) the exclusive prefix of the tile; *block_part = the part contributed by the tile's own block
+// (what the last tile of a block adds its aggregate to when it publishes the block total).
+// The tile's own aggregate is not needed here, so this can run while the tile's data is still in flight.
 template <class T>
-__global__ void __launch_bounds__(kScanThreads, 2) k_scan_lookback(const __grid_constant__ ScanParams p) {
-    __shared__ uint32_t s_tile;
-    __shared__ T s_warp[kScanThreads / 32];
-    __shared__ T s_prefix;
-    __shared__ T s_buf[kLookbackBuf];
+XTB_DEV T tile_lookback(const ScanParams& p, int op, uint32_t row, uint32_t trow, int lane, T* block_part) {
+    const T ident = scan_identity<T>(op);
+    const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
+    const uint32_t kb = trow / kScanWindow;            // complete blocks before mine
+    const uint32_t cnt = trow - kb * kScanWindow;      // tiles of my block before me
+    const uint32_t first = row * p.tiles_per_row + kb * kScanWindow;
+    // aggregates of my block: lane l owns tiles l, l+32, .. (ascending); all loads (and the first block
+    // total) are issued before the first one is inspected
+    T v[8];
+    bool ok[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t idx = (uint32_t) j * 32 + lane;
+        v[j] = ident;
+        ok[j] = idx >= cnt || slot_try<T>(p.aggregate, first + idx, v[j]);
+    }
+    T bv = ident;
+    bool bok = (uint32_t) lane >= kb || slot_try<T>(p.prefix, row * blocks_per_row + lane, bv);
+    T a = ident;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t idx = (uint32_t) j * 32 + lane;
+        while (!ok[j]) {
+            __nanosleep(40);
+            ok[j] = slot_try<T>(p.aggregate, first + idx, v[j]);
+        }
+        if (idx < cnt) a = scan_op<T>(op, a, v[j]);
+    }
+    a = warp_total<T>(op, a);
+    *block_part = a;
+    T e = a;
+    if (kb > 0) {
+        T b = ident;
+        for (uint32_t m = lane; m < kb; m += 32) {
+            if (m >= 32) bok = slot_try<T>(p.prefix, row * blocks_per_row + m, bv);
+            while (!bok) {
+                __nanosleep(40);
+                bok = slot_try<T>(p.prefix, row * blocks_per_row + m, bv);
+            }
+            b = scan_op<T>(op, b, bv);
+        }
+        b = warp_total<T>(op, b);
+        e = cnt > 0 ? scan_op<T>(op, b, a) : b;
+    }
+    return e;
+}
+
+// WARP_ROWS: rows of at most 32*ITEMS elements, one warp per row (no block or tile combine)
+template <class T, bool WARP_ROWS>
+__global__ void __launch_bounds__(kScanThreads, 4) k_scan_tiles(const __grid_constant__ ScanParams p) {
+    using C = ScanTile<T>;
+    constexpr int VEC = C::VEC, NV = C::NV;
+    __shared__ T s_warp[kScanWarpsPerTile];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int op = p.op;
-    // tiles are taken in launch order, so every predecessor of a tile is already running
-    if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= p.total_tiles) return;
-    const uint32_t row = tile / p.tiles_per_row;
-    const uint32_t trow = tile - row * p.tiles_per_row;   // tile index within its row
-    const int64_t base = (int64_t) trow * kScanTile + (int64_t) tid * kScanItems;
+    const T ident = scan_identity<T>(op);
+    const uint32_t tile = blockIdx.x;
+    uint32_t row, trow;
+    int64_t wbase;                       // first element (within the row) of this warp's chunk
+    int64_t limit = p.n;                 // elements addressable from in_row / out_row
+    int seg = 128;                       // vectors per scan segment inside the warp's window
     const int isz = dtype_size(p.in_dtype);
-    const char* in_row = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
-    // load + thread-local inclusive scan
-    T x[kScanItems];
-    const bool full_tile = base + kScanItems <= p.n;
-    if (p.vec_io && full_tile) {
-        constexpr int PER = 16 / sizeof(T);
-        const uint4* src = (const uint4*) (in_row + base * sizeof(T));
+    const char* in_row;
+    T* out_row;
+    if constexpr (WARP_ROWS) {
+        const int64_t r = (int64_t) tile * kScanWarpsPerTile + warp;
+        trow = 0;
+        if (p.packed) {
+            // the array is one dense run of short rows: windows of 128 vectors over the flat data
+            wbase = r * C::WARP_ELEMS;
+            limit = p.rows * p.n;
+            if (wbase >= limit) return;
+            seg = p.seg_vecs;
+            row = 0;
+            in_row = p.in;
+            out_row = (T*) p.out;
+        } else {
+            if (r >= p.rows) return;
+            row = (uint32_t) r;
+            wbase = 0;
+            in_row = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
+            out_row = (T*) p.out + (int64_t) row * p.n;
+        }
+    } else {
+        row = tile / p.tiles_per_row;
+        trow = tile - row * p.tiles_per_row;
+        wbase = (int64_t) trow * C::TILE + (int64_t) warp * C::WARP_ELEMS;
+        in_row = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
+        out_row = (T*) p.out + (int64_t) row * p.n;
+    }
+
+    // ---- load (striped) ----
+    T x[NV][VEC];
+    if (p.vec_io) {
+        // rows are 16-byte aligned; a vector is loaded whole when it lies inside the row
+        const char* src = in_row + wbase * (int64_t) sizeof(T);
 #pragma unroll
-        for (int q = 0; q < kScanItems / PER; ++q) {
-            const uint4 r = ldg_stream_16(src + q);
-            memcpy(&x[q * PER], &r, 16);
+        for (int q = 0; q < NV; ++q) {
+            const int vi = q * 32 + lane;
+            const int64_t j0 = wbase + (int64_t) vi * VEC;
+            if (j0 + VEC <= limit) {
+                const uint4 r = ldg_stream_16(src + (size_t) vi * 16);
+                memcpy(&x[q][0], &r, 16);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) x[q][i] = j0 + i < limit ? ((const T*) in_row)[j0 + i] : ident;
+            }
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            const int64_t j = base + i;
-            x[i] = j < p.n ? load_cast<T>(in_row + j * p.in_axis_stride * isz, p.in_dtype) : scan_identity<T>(op);
+        for (int q = 0; q < NV; ++q) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const int64_t j = wbase + (int64_t) (q * 32 + lane) * VEC + i;
+                x[q][i] = j < limit ? load_cast<T>(in_row + j * p.in_axis_stride * isz, p.in_dtype) : ident;
+            }
         }
     }
+    // ---- warp-level scan on the striped arrangement ----
+    T inc[NV];
 #pragma unroll
-    for (int i = 1; i < kScanItems; ++i) x[i] = scan_op<T>(op, x[i - 1], x[i]);
-    // block-wide exclusive scan of the thread totals
-    T incl = x[kScanItems - 1];
+    for (int q = 0; q < NV; ++q) {
+#pragma unroll
+        for (int i = 1; i < VEC; ++i) x[q][i] = scan_op<T>(op, x[q][i - 1], x[q][i]);
+        inc[q] = x[q][VEC - 1];
+    }
+    const int segl = seg < 32 ? seg : 32;            // lanes per segment within one q-row
+    const int lis = lane & (segl - 1);               // lane position inside its segment
+    const int qper = seg >= 32 ? seg >> 5 : 1;       // q-rows per segment
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const T y = shfl_up_t<T>(incl, d);
-        if (lane >= d) incl = scan_op<T>(op, y, incl);
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    T warp_off = scan_identity<T>(op);
-    for (int w = 0; w < warp; ++w) warp_off = scan_op<T>(op, warp_off, s_warp[w]);
-    const T excl_lane = shfl_up_t<T>(incl, 1);
-    T thread_off = lane == 0 ? warp_off : scan_op<T>(op, warp_off, excl_lane);
-    // tile aggregate = total of the last warp prefix
-    T tile_prefix = scan_identity<T>(op);
-    if (p.tile_incl != nullptr) {
-        if (trow > 0) tile_prefix = ((const T*) p.tile_incl)[tile - 1];
-    } else if (p.tiles_per_row > 1) {
-        T* agg = (T*) p.aggregate;
-        T* pre = (T*) p.prefix;
-        if (tid == kScanThreads - 1) {
-            const T total = scan_op<T>(op, thread_off, x[kScanItems - 1]);
-            if constexpr (sizeof(T) == 4) {
-                uint32_t bits;
-                memcpy(&bits, &total, 4);
-                const unsigned long long w = ((unsigned long long) (trow == 0 ? 2u : 1u) << 32) | bits;
-                *((volatile unsigned long long*) &p.packed[tile]) = w;     // one 64-bit store: status + value
-            } else if (trow == 0) {
-                pre[tile] = total;
-                __threadfence();
-                atomicExch(&p.status[tile], 2u);
-            } else {
-                agg[tile] = total;
-                __threadfence();
-                atomicExch(&p.status[tile], 1u);
-            }
-            s_prefix = total;  // reused below as the tile's own aggregate
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const T y = shfl_up_t<T>(inc[q], d);
+            if (lis >= d) inc[q] = scan_op<T>(op, y, inc[q]);
         }
+    }
+    T off[NV];                           // exclusive offset of vector (q, lane) within its segment
+    T carry = ident;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const T ex = shfl_up_t<T>(inc[q], 1);
+        const T rowtot = shfl_idx_t<T>(inc[q], 31);
+        const bool seg_start = (q & (qper - 1)) == 0;
+        const T c = seg_start ? ident : carry;
+        off[q] = lis == 0 ? c : scan_op<T>(op, c, ex);
+        carry = seg_start ? rowtot : scan_op<T>(op, carry, rowtot);
+    }
+    T base_off = ident;                  // everything before this warp's chunk
+    if constexpr (!WARP_ROWS) {
+        // ---- block-level: offsets of the warps, tile aggregate ----
+        if (lane == 0) s_warp[warp] = carry;
         __syncthreads();
-        if (trow > 0) {
-            if (warp == 0) {
-                // look back over the predecessors in this row, 32 at a time; collect aggregates
-                // (nearest first) until a tile with an inclusive prefix is found
-                int collected = 0;
-                T found_prefix = scan_identity<T>(op);
-                int64_t look = (int64_t) trow - 1;    // nearest predecessor still to inspect
-                bool done = false;
-                while (!done) {
-                    const int64_t mine = look - lane;
-                    uint32_t st = 2u;  // lanes before the start of the row behave like "prefix = identity"
-                    T v = scan_identity<T>(op);
-                    if (mine >= 0) {
-                        const uint32_t idx = row * p.tiles_per_row + (uint32_t) mine;
-                        if constexpr (sizeof(T) == 4) {
-                            unsigned long long w;
-                            do {
-                                w = *((volatile unsigned long long*) &p.packed[idx]);
-                            } while ((w >> 32) == 0ull);
-                            st = (uint32_t) (w >> 32);
-                            const uint32_t bits = (uint32_t) w;
-                            memcpy(&v, &bits, 4);
-                        } else {
-                            do {
-                                st = *((volatile uint32_t*) &p.status[idx]);
-                            } while (st == 0u);
-                            __threadfence();
-                            v = st == 2u ? ((volatile T*) pre)[idx] : ((volatile T*) agg)[idx];
-                        }
-                    }
-                    const uint32_t has_prefix = __ballot_sync(0xffffffffu, st == 2u);
-                    const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest lane with a prefix
-                    if (lane < first && collected + lane < kLookbackBuf) s_buf[collected + lane] = v;
-                    if (has_prefix) {
-                        found_prefix = __shfl_sync(0xffffffffu, v, first);
-                        collected += first;
-                        done = true;
-                    } else {
-                        collected += 32;
-                        look -= 32;
-                        if (collected + 32 > kLookbackBuf) {
-                            // buffer full: wait for the inclusive prefix of the next tile instead
-                            const uint32_t idx = row * p.tiles_per_row + (uint32_t) look;
-                            if (lane == 0) {
-                                if constexpr (sizeof(T) == 4) {
-                                    unsigned long long w;
-                                    do {
-                                        w = *((volatile unsigned long long*) &p.packed[idx]);
-                                    } while ((w >> 32) != 2ull);
-                                    const uint32_t bits = (uint32_t) w;
-                                    memcpy(&found_prefix, &bits, 4);
-                                } else {
-                                    uint32_t s2;
-                                    do {
-                                        s2 = *((volatile uint32_t*) &p.status[idx]);
-                                    } while (s2 != 2u);
-                                    __threadfence();
-                                    found_prefix = ((volatile T*) pre)[idx];
-                                }
-                            }
-                            found_prefix = __shfl_sync(0xffffffffu, found_prefix, 0);
-                            done = true;
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    // ascending tile order: prefix, then the collected aggregates from far to near
-                    T acc = found_prefix;
-                    for (int i = collected - 1; i >= 0; --i) acc = scan_op<T>(op, acc, s_buf[i]);
-                    const T own = s_prefix;
-                    const T incl_prefix = scan_op<T>(op, acc, own);
-                    if constexpr (sizeof(T) == 4) {
-                        uint32_t bits;
-                        memcpy(&bits, &incl_prefix, 4);
-                        *((volatile unsigned long long*) &p.packed[tile]) = (2ull << 32) | bits;
-                    } else {
-                        pre[tile] = incl_prefix;
-                        __threadfence();
-                        atomicExch(&p.status[tile], 2u);
-                    }
-                    s_prefix = acc;
-                }
-            }
-            __syncthreads();
-            tile_prefix = s_prefix;
+        T wv = lane < kScanWarpsPerTile ? s_warp[lane] : ident;
+#pragma unroll
+        for (int d = 1; d < kScanWarpsPerTile; d <<= 1) {
+            const T y = shfl_up_t<T>(wv, d);
+            if (lane >= d) wv = scan_op<T>(op, y, wv);
+        }
+        const T tile_total = shfl_idx_t<T>(wv, kScanWarpsPerTile - 1);
+        const T warp_off = shfl_idx_t<T>(wv, warp > 0 ? warp - 1 : 0);
+        base_off = warp > 0 ? warp_off : ident;
+    }
+    // ---- apply offsets, store (striped) ----
+    const bool first_warp_of_row = (WARP_ROWS && !p.packed) || (!WARP_ROWS && trow == 0 && warp == 0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const T o = first_warp_of_row ? off[q] : scan_op<T>(op, base_off, off[q]);
+        if (!(first_warp_of_row && q == 0 && lane == 0)) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x[q][i] = scan_op<T>(op, o, x[q][i]);
         }
     }
-    const T off = (p.tiles_per_row > 1 && trow > 0) ? scan_op<T>(op, tile_prefix, thread_off) : thread_off;
-    T* out_row = (T*) p.out + (int64_t) row * p.n;
-    const bool has_off = !(trow == 0 && tid == 0);
-    if (has_off) {
+    if (p.vec_io) {
+        char* dst = (char*) (out_row + wbase);
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) x[i] = scan_op<T>(op, off, x[i]);
-    }
-    if (p.vec_io && full_tile && ((p.n * sizeof(T)) % 16 == 0 || p.rows == 1)) {
-        constexpr int PER = 16 / sizeof(T);
-        uint4* dst = (uint4*) (out_row + base);
+        for (int q = 0; q < NV; ++q) {
+            const int vi = q * 32 + lane;
+            const int64_t j0 = wbase + (int64_t) vi * VEC;
+            if (j0 + VEC <= limit) {
+                uint4 r;
+                memcpy(&r, &x[q][0], 16);
+                stg_stream_16(dst + (size_t) vi * 16, r);
+            } else {
 #pragma unroll
-        for (int q = 0; q < kScanItems / PER; ++q) {
-            uint4 r;
-            memcpy(&r, &x[q * PER], 16);
-            stg_stream_16(dst + q, r);
+                for (int i = 0; i < VEC; ++i)
+                    if (j0 + i < limit) out_row[j0 + i] = x[q][i];
+            }
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            const int64_t j = base + i;
-            if (j < p.n) out_row[j] = x[i];
+        for (int q = 0; q < NV; ++q) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const int64_t j = wbase + (int64_t) (q * 32 + lane) * VEC + i;
+                if (j < limit) out_row[j] = x[q][i];
+            }
         }
     }
 }
 
-// per-tile totals for long rows (phase 1 of reduce-then-scan)
-template <class T>
-__global__ void __launch_bounds__(kScanThreads, 2) k_scan_tile_sums(const __grid_constant__ ScanParams p, T* sums) {
-    __shared__ T s_warp[kScanThreads / 32];
+// ---- contiguous scan, long rows: shared-memory staged super-tiles -------------------------------
+// At HBM3e latencies the bytes a register-resident tile keeps in flight (64 B per thread) cannot cover
+// the look-back wait.  Here a CTA owns a super-tile of up to 64 KB: each warp fetches its slice with one
+// bulk asynchronous copy (cp.async.bulk -> mbarrier; no registers held while the data is in flight, 3
+// CTAs = 192 KB in flight per SM), scans it in place in shared memory as soon as it lands, and the CTA
+// then does ONE look-back for the whole super-tile before streaming the result out.  Inputs that cannot
+// be bulk-copied (other dtype, strided, unaligned) are read through registers into the same pipeline.
+constexpr int kStMaxBytesLimit = 64 * 1024;
+
+XTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+template <class T, int kStThreads, int kStCtas, bool CHAINED>
+__global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_scan_stile(const __grid_constant__ ScanParams p) {
+    constexpr int kStWarps = kStThreads / 32;               // scan warps; a chained tile has one more warp: the look-back warp
+    constexpr int VEC = 16 / (int) sizeof(T), NV = 4, SUB = 128 * VEC;     // elements per warp sub-chunk
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    T* sm = (T*) st_smem;
+    __shared__ __align__(8) unsigned long long s_bar[kStWarps];
+    __shared__ uint32_t s_tile;
+    __shared__ T s_warp[kStWarps];
+    __shared__ T s_prefix;
+    __shared__ T s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
+    const int op = p.op;
+    const T ident = scan_identity<T>(op);
+    constexpr bool chained = CHAINED;
+    uint32_t tile = blockIdx.x;
+    if (lane == 0 && warp < kStWarps) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[warp])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (chained) {
+        if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    __syncwarp();
     const uint32_t row = tile / p.tiles_per_row;
     const uint32_t trow = tile - row * p.tiles_per_row;
-    const int64_t base = (int64_t) trow * kScanTile + (int64_t) tid * kScanItems;
+    if (chained && warp == kStWarps) {
+        // ---- the look-back warp: gathers the predecessors while the tile's data is still in flight ----
+        T part;
+        const T e = tile_lookback<T>(p, op, row, trow, lane, &part);
+        asm volatile("bar.sync 2, 64;" ::: "memory");          // scan warp 0 has stored the tile aggregate
+        if (lane == 0) {
+            const uint32_t kb = trow / kScanWindow;
+            if (trow - kb * kScanWindow == kScanWindow - 1 && trow + 1 < p.tiles_per_row) {
+                const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
+                slot_publish<T>(p.prefix, row * blocks_per_row + kb, scan_op<T>(op, part, *(volatile T*) &s_total));
+            }
+            s_prefix = e;
+        }
+        __syncthreads();
+        return;
+    }
+    const int tile_elems = p.st_elems;
+    const int chunk = tile_elems / kStWarps;                 // elements per warp, multiple of SUB
+    const int64_t tbase = (int64_t) trow * tile_elems;
     const int isz = dtype_size(p.in_dtype);
     const char* in_row = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
-    T x[kScanItems];
-    if (p.vec_io && base + kScanItems <= p.n) {
-        constexpr int PER = 16 / sizeof(T);
-        const uint4* src = (const uint4*) (in_row + base * sizeof(T));
-#pragma unroll
-        for (int q = 0; q < kScanItems / PER; ++q) {
-            const uint4 r = ldg_stream_16(src + q);
-            memcpy(&x[q * PER], &r, 16);
+    T* out_row = (T*) p.out + (int64_t) row * p.n;
+    const int64_t left = p.n - tbase - (int64_t) warp * chunk;          // valid elements from my chunk on
+    const int cvalid = left <= 0 ? 0 : (left < chunk ? (int) left : chunk);
+    T* my = sm + warp * chunk;
+    const bool bulk = p.vec_io && ((size_t) cvalid * sizeof(T)) % 16 == 0;   // warp-uniform
+    if (bulk && cvalid > 0) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t) cvalid * (uint32_t) sizeof(T);
+            const uint32_t bar = smem_u32(&s_bar[warp]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(my)), "l"(in_row + (tbase + (int64_t) warp * chunk) * (int64_t) sizeof(T)), "r"(bytes), "r"(bar)
+                         : "memory");
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            const int64_t j = base + i;
-            x[i] = j < p.n ? load_cast<T>(in_row + j * p.in_axis_stride * isz, p.in_dtype) : scan_identity<T>(p.op);
+        // wait for my slice (phase 0 of my barrier)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&s_bar[warp])) : "memory");
         }
     }
-    T acc = x[0];
+    // ---- phase A: scan my slice in place (sub-chunks of 128 vectors, striped over the lanes) ----
+    T carry = ident;
+    const int nsub = chunk / SUB;
+    for (int sc = 0; sc < nsub; ++sc) {
+        const int sbase = sc * SUB;                           // within my chunk
+        if (sbase >= cvalid) break;                           // warp-uniform
+        T x[NV][VEC];
 #pragma unroll
-    for (int i = 1; i < kScanItems; ++i) acc = scan_op<T>(p.op, acc, x[i]);
+        for (int q = 0; q < NV; ++q) {
+            const int e0 = sbase + (q * 32 + lane) * VEC;
+            if (bulk) {
+                if (e0 + VEC <= cvalid) {
+                    const uint4 r = *(const uint4*) (my + e0);
+                    memcpy(&x[q][0], &r, 16);
+                } else {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const T y = shfl_up_t<T>(acc, d);
-        if (lane >= d) acc = scan_op<T>(p.op, y, acc);
+                    for (int i = 0; i < VEC; ++i) x[q][i] = ident;   // cvalid is a multiple of VEC here
+                }
+            } else {
+                const int64_t g0 = tbase + (int64_t) warp * chunk + e0;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    x[q][i] = e0 + i < cvalid ? load_cast<T>(in_row + (g0 + i) * p.in_axis_stride * isz, p.in_dtype) : ident;
+            }
+        }
+        T inc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+#pragma unroll
+            for (int i = 1; i < VEC; ++i) x[q][i] = scan_op<T>(op, x[q][i - 1], x[q][i]);
+            inc[q] = x[q][VEC - 1];
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const T y = shfl_up_t<T>(inc[q], d);
+                if (lane >= d) inc[q] = scan_op<T>(op, y, inc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const T ex = shfl_up_t<T>(inc[q], 1);
+            const T rowtot = shfl_idx_t<T>(inc[q], 31);
+            const T o = lane == 0 ? carry : scan_op<T>(op, carry, ex);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x[q][i] = scan_op<T>(op, o, x[q][i]);
+            carry = scan_op<T>(op, carry, rowtot);
+            uint4 r;
+            memcpy(&r, &x[q][0], 16);
+            *(uint4*) (my + sbase + (q * 32 + lane) * VEC) = r;
+        }
     }
-    if (lane == 31) s_warp[warp] = acc;
-    __syncthreads();
+    // ---- offsets of the warps, tile aggregate, look-back ----
+    if (lane == 0) s_warp[warp] = carry;
+    asm volatile("bar.sync 1, %0;" ::"n"(kStThreads) : "memory");      // the scan warps
+    T wv = lane < kStWarps ? s_warp[lane] : ident;
+#pragma unroll
+    for (int d = 1; d < kStWarps; d <<= 1) {
+        const T y = shfl_up_t<T>(wv, d);
+        if (lane >= d) wv = scan_op<T>(op, y, wv);
+    }
+    const T tile_total = shfl_idx_t<T>(wv, kStWarps - 1);
+    const T warp_off = shfl_idx_t<T>(wv, warp > 0 ? warp - 1 : 0);
+    T base_off = warp > 0 ? warp_off : ident;
+    bool have_off = warp > 0;
+    if (chained) {
+        if (warp == 0) {
+            // publish the aggregate at once; successors never wait for this tile's own look-back
+            if (lane == 0) {
+                if (trow + 1 < p.tiles_per_row) slot_publish<T>(p.aggregate, tile, tile_total);
+                s_total = tile_total;
+            }
+            __syncwarp();
+            asm volatile("bar.arrive 2, 64;" ::: "memory");
+        }
+        __syncthreads();                                       // the look-back warp has stored s_prefix
+        if (trow > 0) {
+            base_off = warp > 0 ? scan_op<T>(op, s_prefix, warp_off) : s_prefix;
+            have_off = true;
+        }
+    }
+    // ---- phase B: add the offset, stream out ----
+    T* dst = out_row + tbase + (int64_t) warp * chunk;
+    for (int sc = 0; sc < nsub; ++sc) {
+        const int sbase = sc * SUB;
+        if (sbase >= cvalid) break;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int e0 = sbase + (q * 32 + lane) * VEC;
+            if (e0 >= cvalid) continue;
+            T v[VEC];
+            const uint4 r = *(const uint4*) (my + e0);
+            memcpy(&v[0], &r, 16);
+            if (have_off) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) v[i] = scan_op<T>(op, base_off, v[i]);
+            }
+            if (p.vec_io && e0 + VEC <= cvalid) {
+                uint4 w;
+                memcpy(&w, &v[0], 16);
+                stg_stream_16(dst + e0, w);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    if (e0 + i < cvalid) dst[e0 + i] = v[i];
+            }
+        }
+    }
+}
+
+// ---- strided axis, long axis: single-pass column tiles -------------------------------------------
+// A CTA owns R rows x W <= 256 columns (<= 64 KB) of one (outer, column-strip): warp 0 fetches the rows
+// with bulk asynchronous copies, every scan thread walks one column of the tile downwards in shared
+// memory (row groups when the strip is narrow), and a dedicated look-back warp gathers -- while the tile
+// is still in flight -- the column totals of the tiles above it through a fixed fan-16 tree
+// (tile -> group of 16 -> group of 256 ...), so one read + one write of the data and a result that does
+// not depend on timing.  One tile along the axis and >= 256 columns: exactly the reference's order.
+constexpr int kCtThreads = 256;
+constexpr int kCtFan = 16;
+constexpr int kCtMaxLevels = 8;
+constexpr int kCtTileBytes = 64 * 1024;
+
+struct ColTileParams {
+    int32_t W, R, G;                   // columns / rows per tile, row groups per tile (= 256 / W)
+    int32_t strips, chunks, levels;    // tiles across the columns / along the axis, tree levels
+    int32_t bulk;                      // tile rows can be fetched with cp.async.bulk
+    int64_t units[kCtMaxLevels];       // units along the axis at each tree level: ceil(chunks / 16^l)
+    int64_t level_off[kCtMaxLevels];   // first slot of each level
+    char* vals;                        // [slot][256] column totals, each a {flag, value} word (zeroed before the launch)
+};
+
+template <class T, bool BULK>
+__global__ void __launch_bounds__(kCtThreads + 32, 3) k_scan_coltile(const __grid_constant__ ScanParams p, const __grid_constant__ ColTileParams c) {
+    constexpr int CV = BULK ? 16 / (int) sizeof(T) : 1;   // adjacent columns per scan thread (one 128-bit access)
+    extern __shared__ __align__(128) unsigned char ct_smem[];
+    T* sm = (T*) ct_smem;                                  // [R][W]
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_tile;
+    __shared__ __align__(16) T s_gt[kCtThreads * CV];      // totals of the row groups [G][W]
+    __shared__ T s_tot[kCtThreads];                        // column totals of the tile
+    __shared__ T s_off[kCtThreads];                        // exclusive prefix of the tile per column
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int op = p.op;
+    const T ident = scan_identity<T>(op);
+    const bool chained = c.chunks > 1;
     if (tid == 0) {
-        T t = s_warp[0];
-        for (int w = 1; w < kScanThreads / 32; ++w) t = scan_op<T>(p.op, t, s_warp[w]);
-        sums[tile] = t;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (chained) s_tile = atomicAdd(p.ticket, 1u);
     }
+    __syncthreads();
+    const uint32_t tile = chained ? s_tile : blockIdx.x;
+    // tickets run strip-fastest, then along the axis, then over the outer index: what a tile waits for
+    // was started at least `strips` tickets earlier
+    const uint32_t per_o = (uint32_t) c.chunks * (uint32_t) c.strips;
+    const uint32_t o = tile / per_o;
+    const uint32_t rem = tile - o * per_o;
+    const uint32_t chunk = rem / (uint32_t) c.strips;
+    const uint32_t strip = rem - chunk * (uint32_t) c.strips;
+    const int W = c.W, R = c.R;
+    const int64_t col0 = (int64_t) strip * 256;
+    const int wv = (int) (p.inner - col0 < W ? p.inner - col0 : W);        // valid columns
+    const int64_t r0 = (int64_t) chunk * R;
+    const int rvalid = (int) (p.n - r0 < R ? p.n - r0 : R);
+
+    if (warp == kCtThreads / 32) {
+        // ---- look-back warp (present only when chained) ----
+        // Every published column total is a {flag, value} slot of its own (one 64-/128-bit access), so
+        // neither side needs a fence.  Columns are handled CH at a time per lane to bound registers.
+        constexpr int CH = sizeof(T) == 4 ? 4 : 2;
+        const int64_t lane_base = (int64_t) o * c.strips + strip;
+        bool synced = false;
+        for (int h = 0; h < 8 / CH; ++h) {
+            T low[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) low[i] = ident;
+            uint32_t u = chunk;                            // index of my ancestor unit at level l
+            uint32_t span = 1;                             // chunks per unit at level l
+            for (int l = 0; l < c.levels; ++l) {
+                const uint32_t cnt = u % kCtFan;           // preceding siblings
+                const int64_t first = c.level_off[l] + lane_base * c.units[l] + (u - cnt);
+                T part[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) part[i] = ident;
+                // JU siblings at a time: all their slots are requested before the first is inspected
+                constexpr int JU = 4;
+                for (uint32_t j0 = 0; j0 < cnt; j0 += JU) {
+                    T v[JU][CH];
+                    bool ok[JU][CH];
+#pragma unroll
+                    for (int jj = 0; jj < JU; ++jj) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            const int cx = lane + 32 * (h * CH + i);
+                            v[jj][i] = ident;
+                            ok[jj][i] = j0 + jj >= cnt || cx >= wv || slot_try<T>(c.vals, (uint32_t) ((first + j0 + jj) * 256 + cx), v[jj][i]);
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < JU; ++jj) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            const int cx = lane + 32 * (h * CH + i);
+                            while (!ok[jj][i]) {
+                                __nanosleep(40);
+                                ok[jj][i] = slot_try<T>(c.vals, (uint32_t) ((first + j0 + jj) * 256 + cx), v[jj][i]);
+                            }
+                            part[i] = scan_op<T>(op, part[i], v[jj][i]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CH; ++i) low[i] = scan_op<T>(op, part[i], low[i]);
+                // last chunk of a level-(l+1) unit that something follows: publish that unit's total
+                span *= kCtFan;
+                if (l + 1 < c.levels && (chunk + 1) % span == 0 && chunk + 1 < (uint32_t) c.chunks) {
+                    if (!synced) {
+                        asm volatile("bar.sync 2, 64;" ::: "memory");      // the tile's own totals are in s_tot
+                        synced = true;
+                    }
+                    const int64_t slot = c.level_off[l + 1] + lane_base * c.units[l + 1] + u / kCtFan;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const int cx = lane + 32 * (h * CH + i);
+                        if (cx < wv) slot_publish<T>(c.vals, (uint32_t) (slot * 256 + cx), scan_op<T>(op, low[i], s_tot[cx]));
+                    }
+                }
+                u /= kCtFan;
+            }
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int cx = lane + 32 * (h * CH + i);
+                if (cx < wv) s_off[cx] = low[i];
+            }
+        }
+        if (!synced) asm volatile("bar.sync 2, 64;" ::: "memory");
+        __syncthreads();
+        return;
+    }
+
+    // ---- scan threads ----
+    const int isz = dtype_size(p.in_dtype);
+    const char* in_o = p.in + scan_offset(o, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
+    if constexpr (BULK) {
+        if (warp == 0) {
+            const uint32_t row_bytes = (uint32_t) wv * (uint32_t) sizeof(T);
+            const uint32_t bar = smem_u32(&s_bar);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t) rvalid) : "memory");
+            __syncwarp();
+            for (int r = lane; r < rvalid; r += 32) {
+                const char* src = in_o + ((r0 + r) * p.in_axis_stride + col0) * (int64_t) sizeof(T);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(sm + (size_t) r * W)), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+            }
+        }
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
+        }
+    }
+    // phase A: thread (g, cv) walks rows [ra, rb) of its CV adjacent columns downwards, in place
+    const int wt = W / CV;                                 // threads across a tile row
+    const int g = tid / wt, col = (tid - g * wt) * CV;
+    const bool active = g < c.G && col < wv;               // wv is a multiple of CV
+    const int rg = (R + c.G - 1) / c.G;
+    const int ra = g * rg;
+    const int rb = ra + rg < rvalid ? ra + rg : rvalid;
+    T acc[CV];
+#pragma unroll
+    for (int k = 0; k < CV; ++k) acc[k] = ident;
+    if (active && ra < rb) {
+        T* q = sm + col;
+        if constexpr (BULK) {
+            uint4 v0 = *(const uint4*) (q + (size_t) ra * W);
+            memcpy(&acc[0], &v0, 16);
+#pragma unroll 4
+            for (int r = ra + 1; r < rb; ++r) {
+                T x[CV];
+                uint4 v = *(const uint4*) (q + (size_t) r * W);
+                memcpy(&x[0], &v, 16);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[k] = scan_op<T>(op, acc[k], x[k]);
+                memcpy(&v, &acc[0], 16);
+                *(uint4*) (q + (size_t) r * W) = v;
+            }
+        } else {
+            const char* src = in_o + scan_offset((uint32_t) (col0 + col), p.n_inner, p.inner_shape, p.inner_stride, p.inner_div) * isz;
+            const int64_t step = p.in_axis_stride * isz;
+            bool have = false;
+            for (int r = ra; r < rb; r += 8) {
+                T x[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = r + k < rb ? load_cast<T>(src + (r0 + r + k) * step, p.in_dtype) : ident;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (r + k < rb) {
+                        acc[0] = have ? scan_op<T>(op, acc[0], x[k]) : x[k];
+                        have = true;
+                        q[(size_t) (r + k) * W] = acc[0];
+                    }
+                }
+            }
+        }
+    }
+    if (tid < c.G * wt) {
+#pragma unroll
+        for (int k = 0; k < CV; ++k) s_gt[g * W + col + k] = acc[k];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kCtThreads) : "memory");
+    // offset of my row group inside the tile; column totals
+    T go[CV];
+#pragma unroll
+    for (int k = 0; k < CV; ++k) go[k] = ident;
+    if (active) {
+        for (int gg = 0; gg < g; ++gg) {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) go[k] = gg == 0 ? s_gt[col + k] : scan_op<T>(op, go[k], s_gt[gg * W + col + k]);
+        }
+    }
+    if (chained) {
+        if (active && g == 0) {
+            const bool pub = chunk + 1 < (uint32_t) c.chunks;
+            const int64_t slot = c.level_off[0] + ((int64_t) o * c.strips + strip) * c.units[0] + chunk;
+#pragma unroll
+            for (int k = 0; k < CV; ++k) {
+                T tot = s_gt[col + k];
+                for (int gg = 1; gg < c.G; ++gg) tot = scan_op<T>(op, tot, s_gt[gg * W + col + k]);
+                s_tot[col + k] = tot;
+                if (pub) slot_publish<T>(c.vals, (uint32_t) (slot * 256 + col + k), tot);
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kCtThreads) : "memory");
+        if (warp == 0) asm volatile("bar.arrive 2, 64;" ::: "memory");
+        __syncthreads();                                   // the look-back warp has stored s_off
+    }
+    // phase B: add what lies above (other tiles, earlier row groups), stream out
+    if (active && ra < rb) {
+        const bool from_tiles = chained && chunk > 0;
+        const bool have_off = from_tiles || g > 0;
+        T off[CV];
+#pragma unroll
+        for (int k = 0; k < CV; ++k) {
+            off[k] = go[k];
+            if (from_tiles) off[k] = g > 0 ? scan_op<T>(op, s_off[col + k], go[k]) : s_off[col + k];
+        }
+        T* dst = (T*) p.out + ((int64_t) o * p.n + r0) * p.inner + col0 + col;
+        const T* q = sm + col;
+#pragma unroll 4
+        for (int r = ra; r < rb; ++r) {
+            if constexpr (BULK) {
+                T x[CV];
+                uint4 v = *(const uint4*) (q + (size_t) r * W);
+                memcpy(&x[0], &v, 16);
+                if (have_off) {
+#pragma unroll
+                    for (int k = 0; k < CV; ++k) x[k] = scan_op<T>(op, off[k], x[k]);
+                }
+                memcpy(&v, &x[0], 16);
+                stg_stream_16(dst + (int64_t) r * p.inner, v);
+            } else {
+                T v = q[(size_t) r * W];
+                if (have_off) v = scan_op<T>(op, off[0], v);
+                dst[(int64_t) r * p.inner] = v;
+            }
+        }
+    }
+}
+
+template <class T> static int scan_coltile(ScanParams p, DeviceCtx* ctx) {
+    ColTileParams c;
+    memset(&c, 0, sizeof(c));
+    c.W = (int32_t) std::min<int64_t>(p.inner, 256);
+    c.strips = (int32_t) ((p.inner + 255) / 256);
+    int64_t R = kCtTileBytes / ((int64_t) c.W * (int64_t) sizeof(T));
+    if (R > p.n) R = p.n;
+    c.R = (int32_t) R;
+    c.chunks = (int32_t) ((p.n + R - 1) / R);
+    const int64_t tiles = (int64_t) c.chunks * c.strips * p.rows;
+    if (tiles >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
+    // bulk copies need the tile rows to be dense, 16-byte aligned runs of the accumulator dtype
+    const int64_t asz = sizeof(T);
+    bool bulk = std::is_same<T, float>::value ? p.in_dtype == XTB_F32
+              : std::is_same<T, double>::value ? p.in_dtype == XTB_F64
+              : sizeof(T) == 4 ? (p.in_dtype == XTB_I32 || p.in_dtype == XTB_U32)      // same bits modulo 2^32
+                               : (p.in_dtype == XTB_I64 || p.in_dtype == XTB_U64);
+    bulk = bulk && (uintptr_t) p.in % 16 == 0 && (p.inner * asz) % 16 == 0 && (p.in_axis_stride * asz) % 16 == 0;
+    int64_t expect = 1;
+    for (int d = p.n_inner - 1; d >= 0 && bulk; --d) {
+        if (p.inner_shape[d] != 1 && p.inner_stride[d] != expect) bulk = false;
+        expect *= p.inner_shape[d];
+    }
+    for (int d = 0; d < p.n_outer && bulk; ++d) bulk = (p.outer_stride[d] * asz) % 16 == 0;
+    c.bulk = bulk ? 1 : 0;
+    // the output is dense, but its rows are 16-byte aligned only if the inner extent is (bulk implies it)
+    bulk = bulk && (uintptr_t) p.out % 16 == 0;
+    c.bulk = bulk ? 1 : 0;
+    c.G = std::max(1, kCtThreads / (c.W / (bulk ? 16 / (int) sizeof(T) : 1)));
+    if (c.G > c.R) c.G = c.R;
+    if (c.chunks > 1) {
+        int64_t slots = 0, units = c.chunks, span = 1;
+        while (span < c.chunks) {
+            if (c.levels >= kCtMaxLevels) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: axis too long");
+            c.units[c.levels] = units;
+            c.level_off[c.levels] = slots;
+            slots += units * c.strips * p.rows;
+            units = (units + kCtFan - 1) / kCtFan;
+            span *= kCtFan;
+            ++c.levels;
+        }
+        if (slots * 256 >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
+        const size_t val_bytes = (size_t) slots * 256 * 2 * sizeof(T);
+        void* scratch = nullptr;
+        XTB_TRY(ensure_scratch(ctx, 256 + val_bytes, &scratch));
+        char* s = (char*) scratch;
+        p.ticket = (uint32_t*) s;
+        c.vals = s + 256;
+        XTB_CUDA(cudaMemsetAsync(s, 0, 256 + val_bytes, ctx->stream));
+    }
+    const size_t smem = (size_t) c.R * c.W * sizeof(T);
+    const unsigned threads = kCtThreads + (c.chunks > 1 ? 32 : 0);
+    if (bulk) {
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_coltile<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtTileBytes));
+        k_scan_coltile<T, true><<<(unsigned) tiles, threads, smem, ctx->stream>>>(p, c);
+    } else {
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_coltile<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtTileBytes));
+        k_scan_coltile<T, false><<<(unsigned) tiles, threads, smem, ctx->stream>>>(p, c);
+    }
+    note_launch(c.chunks > 1 ? "k_scan_coltile[look-back]" : "k_scan_coltile");
+    return check_launch("k_scan_coltile");
 }
 
 // ---- strided axis: one thread per column ------------------------------------------------------
@@ -346,45 +922,6 @@ template <class T>
 __global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ ScanParams p) {
     const int64_t cols = p.rows * p.inner;
     const int isz = dtype_size(p.in_dtype);
-    if (p.chunk > 0) {
-        // chunked: blockIdx.y owns rows [i0, i1) of every column and starts from the carry of the
-        // previous chunks (inclusive scan of the per-chunk totals, computed by two earlier launches)
-        const int64_t i0 = (int64_t) blockIdx.y * p.chunk;
-        const int64_t i1 = i0 + p.chunk < p.n ? i0 + p.chunk : p.n;
-        for (int64_t c = (int64_t) blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t) gridDim.x * 256) {
-            const uint32_t o = (uint32_t) (c / p.inner);
-            const uint32_t in_i = (uint32_t) (c - (int64_t) o * p.inner);
-            const char* src = p.in + (scan_offset(o, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) +
-                                      scan_offset(in_i, p.n_inner, p.inner_shape, p.inner_stride, p.inner_div)) * isz;
-            T* dst = (T*) p.out + (int64_t) o * p.n * p.inner + in_i;
-            const int64_t sstep = p.in_axis_stride * isz;
-            T acc = scan_identity<T>(p.op);
-            bool have = false;
-            if (blockIdx.y > 0) {
-                acc = ((const T*) p.carry)[((int64_t) o * gridDim.y + (blockIdx.y - 1)) * p.inner + in_i];
-                have = true;
-            }
-            int64_t i = i0;
-            for (; i + 4 <= i1; i += 4) {
-                T v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = load_cast<T>(src + (i + u) * sstep, p.in_dtype);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    acc = have ? scan_op<T>(p.op, acc, v[u]) : v[u];
-                    have = true;
-                    dst[(i + u) * p.inner] = acc;
-                }
-            }
-            for (; i < i1; ++i) {
-                const T v = load_cast<T>(src + i * sstep, p.in_dtype);
-                acc = have ? scan_op<T>(p.op, acc, v) : v;
-                have = true;
-                dst[i * p.inner] = acc;
-            }
-        }
-        return;
-    }
     for (int64_t c = (int64_t) blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t) gridDim.x * 256) {
         const uint32_t o = (uint32_t) (c / p.inner);
         const uint32_t in_i = (uint32_t) (c - (int64_t) o * p.inner);
@@ -412,145 +949,87 @@ __global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ Sc
     }
 }
 
-// per-chunk column totals: totals[(o * nch + c) * inner + i] = op over rows [c*chunk, (c+1)*chunk)
-template <class T>
-__global__ void __launch_bounds__(256) k_scan_chunk_totals(const __grid_constant__ ScanParams p, T* totals) {
-    const int64_t cols = p.rows * p.inner;
-    const int isz = dtype_size(p.in_dtype);
-    const int64_t i0 = (int64_t) blockIdx.y * p.chunk;
-    const int64_t i1 = i0 + p.chunk < p.n ? i0 + p.chunk : p.n;
-    for (int64_t c = (int64_t) blockIdx.x * 256 + threadIdx.x; c < cols; c += (int64_t) gridDim.x * 256) {
-        const uint32_t o = (uint32_t) (c / p.inner);
-        const uint32_t in_i = (uint32_t) (c - (int64_t) o * p.inner);
-        const char* src = p.in + (scan_offset(o, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) +
-                                  scan_offset(in_i, p.n_inner, p.inner_shape, p.inner_stride, p.inner_div)) * isz;
-        const int64_t sstep = p.in_axis_stride * isz;
-        T acc = load_cast<T>(src + i0 * sstep, p.in_dtype);
-        int64_t i = i0 + 1;
-        for (; i + 8 <= i1; i += 8) {
-            T v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = load_cast<T>(src + (i + u) * sstep, p.in_dtype);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc = scan_op<T>(p.op, acc, v[u]);
-        }
-        for (; i < i1; ++i) acc = scan_op<T>(p.op, acc, load_cast<T>(src + i * sstep, p.in_dtype));
-        totals[((int64_t) o * gridDim.y + blockIdx.y) * p.inner + in_i] = acc;
-    }
-}
-
-template <class T> static int scan_chunked_t(ScanParams p, int64_t chunk, int64_t nch, DeviceCtx* ctx) {
-    const int64_t cols = p.rows * p.inner;
-    void* scratch = nullptr;
-    const size_t each = ((size_t) cols * nch * sizeof(T) + 255) / 256 * 256;
-    XTB_TRY(ensure_scratch(ctx, 2 * each, &scratch));
-    T* totals = (T*) scratch;
-    T* carry = (T*) ((char*) scratch + each);
-    p.chunk = chunk;
-    const unsigned gx = (unsigned) std::min<int64_t>((cols + 255) / 256, (int64_t) ctx->sm_count * 32);
-    k_scan_chunk_totals<T><<<dim3(gx, (unsigned) nch), 256, 0, ctx->stream>>>(p, totals);
-    note_launch("k_scan_chunk_totals");
-    XTB_TRY(check_launch("k_scan_chunk_totals"));
-    // inclusive scan of the chunk totals along the chunk index (small): totals[o][c][i] -> carry[o][c][i]
-    ScanParams q;
-    memset(&q, 0, sizeof(q));
-    q.in = (const char*) totals;
-    q.out = (char*) carry;
-    q.in_dtype = sizeof(T) == 4 ? (std::is_same<T, float>::value ? XTB_F32 : XTB_U32) : (std::is_same<T, double>::value ? XTB_F64 : XTB_U64);
-    q.op = p.op;
-    q.n = nch;
-    q.rows = p.rows;
-    q.inner = p.inner;
-    q.in_axis_stride = p.inner;
-    q.n_outer = 1;
-    q.outer_shape[0] = p.rows;
-    q.outer_stride[0] = nch * p.inner;
-    q.outer_div[0] = make_fastdiv((uint32_t) std::min<int64_t>(p.rows, 0x7fffffff));
-    q.n_inner = 1;
-    q.inner_shape[0] = p.inner;
-    q.inner_stride[0] = 1;
-    q.inner_div[0] = make_fastdiv((uint32_t) std::min<int64_t>(p.inner, 0x7fffffff));
-    k_scan_columns<T><<<gx, 256, 0, ctx->stream>>>(q);
-    note_launch("k_scan_columns[carry]");
-    XTB_TRY(check_launch("k_scan_columns"));
-    p.carry = (const char*) carry;
-    k_scan_columns<T><<<dim3(gx, (unsigned) nch), 256, 0, ctx->stream>>>(p);
-    note_launch("k_scan_columns[chunked]");
-    return check_launch("k_scan_columns");
-}
-
-static int scan_chunked(int acc_type, const ScanParams& p, int64_t chunk, int64_t nch, DeviceCtx* ctx) {
-    switch (acc_type) {
-        case XTB_I32: case XTB_U32: return scan_chunked_t<uint32_t>(p, chunk, nch, ctx);
-        case XTB_I64: case XTB_U64: return scan_chunked_t<unsigned long long>(p, chunk, nch, ctx);
-        case XTB_F32: return scan_chunked_t<float>(p, chunk, nch, ctx);
-        default: return scan_chunked_t<double>(p, chunk, nch, ctx);
-    }
-}
-
 template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, bool columns) {
     if (columns) {
         const int64_t cols = p.rows * p.inner;
         const unsigned gx = (unsigned) std::min<int64_t>((cols + 255) / 256, (int64_t) ctx->sm_count * 32);
-        const unsigned gy = p.chunk > 0 ? (unsigned) ((p.n + p.chunk - 1) / p.chunk) : 1u;
-        k_scan_columns<T><<<dim3(gx, gy), 256, 0, ctx->stream>>>(p);
-        note_launch(p.chunk > 0 ? "k_scan_columns[chunked]" : "k_scan_columns");
+        k_scan_columns<T><<<gx, 256, 0, ctx->stream>>>(p);
+        note_launch("k_scan_columns");
         return check_launch("k_scan_columns");
     }
-    if (p.tiles_per_row > 32 && p.tile_incl == nullptr) {
-        // long rows: the look-back chain (32 tiles per poll round) would bound throughput; do
-        // reduce-then-scan instead: tile totals -> their inclusive scan (recursively, a short row) ->
-        // final pass with the tile prefixes read from memory.  Deterministic, 3 passes over memory.
-        T* sums = nullptr;
-        T* incl = nullptr;
-        const size_t bytes = (size_t) p.total_tiles * sizeof(T);
-        XTB_CUDA(cudaMallocAsync((void**) &sums, bytes, ctx->stream));
-        XTB_CUDA(cudaMallocAsync((void**) &incl, bytes, ctx->stream));
-        k_scan_tile_sums<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(p, sums);
-        note_launch("k_scan_tile_sums");
-        XTB_TRY(check_launch("k_scan_tile_sums"));
-        ScanParams q;
-        memset(&q, 0, sizeof(q));
-        q.in = (const char*) sums;
-        q.out = (char*) incl;
-        q.in_dtype = sizeof(T) == 4 ? (std::is_same<T, float>::value ? XTB_F32 : XTB_U32) : (std::is_same<T, double>::value ? XTB_F64 : XTB_U64);
-        q.op = p.op;
-        q.n = p.tiles_per_row;
-        q.rows = p.rows;
-        q.in_axis_stride = 1;
-        q.n_outer = 1;
-        q.outer_shape[0] = p.rows;
-        q.outer_stride[0] = p.tiles_per_row;
-        q.outer_div[0] = make_fastdiv((uint32_t) std::min<int64_t>(p.rows, 0x7fffffff));
-        const int64_t tpr2 = (q.n + kScanTile - 1) / kScanTile;
-        q.tiles_per_row = (uint32_t) tpr2;
-        q.total_tiles = (uint32_t) (tpr2 * p.rows);
-        // look-back state of the inner scan lives in the context scratch after the outer scan's state
+    // contiguous: state = ticket | one slot per tile | one slot per block of kScanWindow tiles
+    ScanParams q = p;
+    using C = ScanTile<T>;
+    if (q.rows > 1 && q.n <= C::WARP_ELEMS) {
+        // short rows: a warp per row, or -- dense input, power-of-two row bytes -- several rows per warp
+        const int64_t row_bytes = q.n * (int64_t) sizeof(T);
+        bool dense = q.vec_io != 0 && row_bytes >= 16 && (row_bytes & (row_bytes - 1)) == 0;
+        int64_t expect = q.n;
+        for (int d = q.n_outer - 1; d >= 0 && dense; --d) {
+            if (q.outer_shape[d] != 1 && q.outer_stride[d] != expect) dense = false;
+            expect *= q.outer_shape[d];
+        }
+        int64_t units = q.rows;
+        if (dense) {
+            q.packed = 1;
+            q.seg_vecs = (int32_t) (row_bytes / 16);
+            units = (q.rows * q.n + C::WARP_ELEMS - 1) / C::WARP_ELEMS;
+        }
+        const unsigned grid = (unsigned) ((units + kScanWarpsPerTile - 1) / kScanWarpsPerTile);
+        k_scan_tiles<T, true><<<grid, kScanThreads, 0, ctx->stream>>>(q);
+        note_launch(dense ? "k_scan_tiles[rows packed per warp]" : "k_scan_tiles[warp per row]");
+        return check_launch("k_scan_tiles");
+    }
+    const int64_t row_bytes = q.n * (int64_t) sizeof(T);
+    // staged super-tile configuration: threads per CTA / CTAs per SM / super-tile bytes
+    // staged super-tiles: long rows (several tiles, look-back) use 8 scan warps + the look-back warp on 64 KB,
+    // 3 CTAs per SM; rows of one tile use 4 warps on up to 32 KB, 6 CTAs per SM
+    const bool long_rows = row_bytes > 32 * 1024;
+    const int st_threads = long_rows ? 256 : 128;
+    const int64_t st_max = long_rows ? 64 * 1024 : 32 * 1024;
+    const int64_t granule = (st_threads / 32) * 128 * 16;    // every warp owns whole 128-vector sub-chunks
+    const bool staged = row_bytes >= granule;
+    int64_t tile_elems = C::TILE;
+    if (staged) {
+        int64_t tb = row_bytes <= st_max ? (row_bytes + granule - 1) / granule * granule : st_max;
+        tile_elems = tb / (int64_t) sizeof(T);
+        q.st_elems = (int32_t) tile_elems;
+    }
+    const int64_t tpr = (q.n + tile_elems - 1) / tile_elems;
+    const int64_t tiles = tpr * q.rows;
+    if (tiles >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
+    q.tiles_per_row = (uint32_t) tpr;
+    q.total_tiles = (uint32_t) tiles;
+    if (tpr > 1) {
+        const int64_t bpr = (tpr + kScanWindow - 1) / kScanWindow;
+        const size_t agg_bytes = ((size_t) tiles * C::SLOT + 255) / 256 * 256;
+        const size_t blk_bytes = ((size_t) (bpr * q.rows) * C::SLOT + 255) / 256 * 256;
         void* scratch = nullptr;
-        const size_t state = 256 + ((size_t) q.total_tiles * 4 + 255) / 256 * 256 + 2 * (((size_t) q.total_tiles * sizeof(T) + 255) / 256 * 256);
-        XTB_CUDA(cudaMallocAsync(&scratch, state, ctx->stream));
+        XTB_TRY(ensure_scratch(ctx, 256 + agg_bytes + blk_bytes, &scratch));
         char* s = (char*) scratch;
         q.ticket = (uint32_t*) s;
-        q.status = (uint32_t*) (s + 256);
-        size_t off = 256 + ((size_t) q.total_tiles * 4 + 255) / 256 * 256;
-        q.aggregate = s + off;
-        q.prefix = s + off + ((size_t) q.total_tiles * sizeof(T) + 255) / 256 * 256;
-        q.packed = (unsigned long long*) q.aggregate;
-        XTB_CUDA(cudaMemsetAsync(s, 0, state, ctx->stream));
-        XTB_TRY((launch_scan<T>(q, ctx, false)));
-        ScanParams r = p;
-        r.tile_incl = (const char*) incl;
-        k_scan_lookback<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(r);
-        note_launch("k_scan_lookback[tile prefixes precomputed]");
-        XTB_TRY(check_launch("k_scan_lookback"));
-        XTB_CUDA(cudaFreeAsync(scratch, ctx->stream));
-        XTB_CUDA(cudaFreeAsync(sums, ctx->stream));
-        XTB_CUDA(cudaFreeAsync(incl, ctx->stream));
-        return XTB_OK;
+        q.aggregate = s + 256;
+        q.prefix = s + 256 + agg_bytes;
+        XTB_CUDA(cudaMemsetAsync(s, 0, 256 + agg_bytes + blk_bytes, ctx->stream));
     }
-    k_scan_lookback<T><<<p.total_tiles, kScanThreads, 0, ctx->stream>>>(p);
-    note_launch("k_scan_lookback");
-    return check_launch("k_scan_lookback");
+    if (staged) {
+        const size_t smem = (size_t) tile_elems * sizeof(T);
+        if (tpr > 1) {
+            XTB_CUDA(cudaFuncSetAttribute(k_scan_stile<T, 256, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStMaxBytesLimit));
+            k_scan_stile<T, 256, 3, true><<<q.total_tiles, 256 + 32, smem, ctx->stream>>>(q);
+        } else if (long_rows) {
+            XTB_CUDA(cudaFuncSetAttribute(k_scan_stile<T, 256, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStMaxBytesLimit));
+            k_scan_stile<T, 256, 3, false><<<q.total_tiles, 256, smem, ctx->stream>>>(q);
+        } else {
+            XTB_CUDA(cudaFuncSetAttribute(k_scan_stile<T, 128, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStMaxBytesLimit));
+            k_scan_stile<T, 128, 6, false><<<q.total_tiles, 128, smem, ctx->stream>>>(q);
+        }
+        note_launch(tpr > 1 ? "k_scan_stile[look-back]" : "k_scan_stile");
+        return check_launch("k_scan_stile");
+    }
+    k_scan_tiles<T, false><<<q.total_tiles, kScanThreads, 0, ctx->stream>>>(q);
+    note_launch(tpr > 1 ? "k_scan_tiles[look-back]" : "k_scan_tiles");
+    return check_launch("k_scan_tiles");
 }
 
 }  // namespace xtb
@@ -632,41 +1111,20 @@ extern "C" int xtb_scan(int op, int acc_type, const xtb_operand* in, int axis, c
     for (int d = 0; d < p.n_outer; ++d) p.outer_div[d] = make_fastdiv((uint32_t) std::min<int64_t>(p.outer_shape[d], 0x7fffffff));
     for (int d = 0; d < p.n_inner; ++d) p.inner_div[d] = make_fastdiv((uint32_t) std::min<int64_t>(p.inner_shape[d], 0x7fffffff));
     if (!columns) {
-        const int64_t tpr = (p.n + kScanTile - 1) / kScanTile;
-        const int64_t tiles = tpr * p.rows;
-        if (tiles >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
-        p.tiles_per_row = (uint32_t) tpr;
-        p.total_tiles = (uint32_t) tiles;
-        // ticket + status + aggregate + prefix
         const size_t asz = dtype_size(acc_type);
-        const size_t bytes = 256 + (size_t) tiles * 4 + 256 + 2 * ((size_t) tiles * asz + 256);
-        void* scratch = nullptr;
-        XTB_TRY(ensure_scratch(ctx, bytes, &scratch));
-        char* s = (char*) scratch;
-        p.ticket = (uint32_t*) s;
-        p.status = (uint32_t*) (s + 256);
-        size_t off = 256 + (((size_t) tiles * 4 + 255) / 256) * 256;
-        p.aggregate = s + off;
-        off += (((size_t) tiles * asz + 255) / 256) * 256;
-        p.prefix = s + off;
-        p.packed = (unsigned long long*) p.aggregate;   // 4-byte accumulators: 8 bytes per tile fit in aggregate+prefix
-        XTB_CUDA(cudaMemsetAsync(s, 0, asz == 4 ? off + (((size_t) tiles * asz + 255) / 256) * 256 : 256 + (size_t) tiles * 4, ctx->stream));
         p.vec_io = in->dtype == acc_type && p.in_axis_stride == 1 && ((uintptr_t) p.in % 16 == 0) && ((uintptr_t) p.out % 16 == 0) &&
                    (p.rows == 1 || (p.n * asz) % 16 == 0);
         if (p.vec_io && p.rows > 1)
             for (int d = 0; d < p.n_outer; ++d) p.vec_io = p.vec_io && (p.outer_stride[d] * asz) % 16 == 0;
     } else {
-        // few columns and a long axis: chunk the axis.  The per-chunk totals come from the reduction
-        // kernel (one extra read of the input), their scan from this kernel on a small array.
-        const int64_t cols = p.rows * p.inner;
-        const int64_t target = (int64_t) ctx->sm_count * 2048;
-        if (cols * 4 < target && p.n >= 256) {
-            int64_t nch = std::min<int64_t>(std::max<int64_t>(target / std::max<int64_t>(cols, 1), 1), p.n / 64);
-            nch = std::min<int64_t>(nch, 1024);
-            if (nch > 1) {
-                const int64_t chunk = (p.n + nch - 1) / nch;
-                nch = (p.n + chunk - 1) / chunk;
-                return scan_chunked(acc_type, p, chunk, nch, ctx);
+        // a long axis: column tiles (single pass).  Short axes with very many columns keep the plain
+        // thread-per-column walk (exactly the reference's order, enough parallelism from the columns).
+        if (p.n >= 128 && p.inner < 0x7fffffffLL - 256) {
+            switch (acc_type) {
+                case XTB_I32: case XTB_U32: return scan_coltile<uint32_t>(p, ctx);
+                case XTB_I64: case XTB_U64: return scan_coltile<unsigned long long>(p, ctx);
+                case XTB_F32: return scan_coltile<float>(p, ctx);
+                default: return scan_coltile<double>(p, ctx);
             }
         }
     }

@@ -775,27 +775,27 @@ def stddev(e, axes=None, dtype=None, ddof=0):
     return sqrt(variance(e, axes, dtype, ddof))
 
 
-def _scan(op, e, axis, dtype):
+def _scan(op, e, axis, dtype, out=None):
     a = evaluate(e)
     kind = type(a)
     init_t = a.dtype if dtype is None else dtype
     acc = common_type(init_t, a.dtype)          # decltype(T() + x) (xaccumulator.hpp:224-234)
     if axis is None:
-        out = _alloc_like(kind, (a.size,), acc)
+        out = _alloc_like(kind, (a.size,), acc) if out is None else out
         ax = -1
     else:
         ax = int(axis) + a.ndim if int(axis) < 0 else int(axis)
         if ax >= a.ndim:
             raise RuntimeError("Axis larger than expression dimension in accumulator.")
-        out = _alloc_like(kind, a.shape, acc)
+        out = _alloc_like(kind, a.shape, acc) if out is None else out
     be, pre = _backend_for(kind)
     iop, oop = a.operand(), out.operand()
     _check(kind, getattr(be, pre + "scan")(op, acc, C.byref(iop), ax, C.byref(oop)))
     return out
 
 
-def cumsum(e, axis=None, dtype=None): return _scan(capi.RED_SUM, e, axis, dtype)
-def cumprod(e, axis=None, dtype=None): return _scan(capi.RED_PROD, e, axis, dtype)
+def cumsum(e, axis=None, dtype=None, out=None): return _scan(capi.RED_SUM, e, axis, dtype, out)
+def cumprod(e, axis=None, dtype=None, out=None): return _scan(capi.RED_PROD, e, axis, dtype, out)
 
 
 def sync():
