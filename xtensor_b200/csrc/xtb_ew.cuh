@@ -12,7 +12,6 @@
 #include "xtb_ops.cuh"
 #ifndef XTB_RTC
 #include <algorithm>
-#include <cstdlib>
 #include "xtb_common.hpp"
 #endif
 #include "xtb_static_programs.cuh"
@@ -286,181 +285,6 @@ __global__ void __launch_bounds__(256) k_ew(const __grid_constant__ EwParams p) 
     else ew_body<Eval, S, V, ND, ITEMS, false>(p);
 }
 
-#ifndef XTB_RTC
-// ---- ring kernel: dense operands staged by bulk asynchronous copies -------------------------------
-// The register-staged kernel above keeps 16 B x leaves x ITEMS per thread in flight, and nothing while
-// the thread evaluates (sin / exp take tens of instructions per element).  Here the dense ("linear")
-// leaves of a FAST problem stream through a shared-memory ring instead: a producer thread issues one
-// cp.async.bulk per leaf and tile (mbarrier complete_tx), 256 consumer threads pick their vectors up
-// from shared memory, evaluate, and store straight to global.  Bytes in flight = the ring (4 stages
-// per CTA, 2 persistent CTAs per SM), independent of how long evaluation takes.  Broadcast and strided
-// leaves keep the direct path.
-constexpr int kRingStages = 3;
-constexpr int kRingCtasPerSm = 2;
-constexpr int kRingItems = 4;          // vectors per consumer thread and tile
-
-struct RingParams {
-    uint32_t n_tiles;                      // tiles of 256 * ITEMS vectors
-    uint32_t stage_bytes;                  // shared memory per stage
-    uint32_t tx_bytes;                     // bytes the producer moves per stage
-    int32_t leaf_off[XTB_MAX_LEAVES];      // offset of the leaf's tile inside a stage, -1: not staged
-    uint32_t leaf_bytes[XTB_MAX_LEAVES];   // bytes of one tile of the leaf
-};
-
-XTB_DEV uint32_t ew_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-XTB_DEV void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(ew_smem_u32(bar)), "r"(parity) : "memory");
-    }
-}
-
-// vector from shared memory into register slots (the counterpart of load_vec)
-template <class S, int V> XTB_DEV void lds_vec(const char* p, int dt, S (&x)[V]) {
-    const int sz = dtype_size(dt);
-    if (sz == 4 && V == 4) {
-        const uint4 r = *(const uint4*) p;
-        x[0] = (S) r.x; x[1] = (S) r.y; x[2] = (S) r.z; x[3] = (S) r.w;
-    } else if (sz == 8 && sizeof(S) == 8 && V == 2) {
-        const uint4 r = *(const uint4*) p;
-        x[0] = (S) (((uint64_t) r.y << 32) | r.x);
-        x[1] = (S) (((uint64_t) r.w << 32) | r.z);
-    } else {
-#pragma unroll
-        for (int v = 0; v < V; ++v) x[v] = load_elem<S>(p + sz * v, dt);
-    }
-}
-
-// PASS 0: leaves read directly from global memory; PASS 1: leaves staged in the ring
-template <class Eval, class S, int V, int ND, int ITEMS, int K, int PASS> struct EwRingLoader {
-    template <class PF>
-    static XTB_DEV void run(const EwParams& p, const RingParams& rp, const char* stage, const EwFetch<ND> (&f)[ITEMS], PF& pf) {
-        if constexpr (K < Eval::kLeaves) {
-            constexpr int dt = Eval::template leaf_dtype<K>();
-            constexpr int sz = dtype_size(dt);
-            const EwLeaf& L = p.leaf[K];
-            const bool staged = rp.leaf_off[K] >= 0;
-            if (PASS == 1 && staged) {
-                const char* base = stage + rp.leaf_off[K] + threadIdx.x * (V * sz);
-#pragma unroll
-                for (int it = 0; it < ITEMS; ++it) lds_vec<S, V>(base + it * (256 * V * sz), dt, pf.pre[K][it]);
-            } else if (PASS == 0 && !staged) {
-                const char* addr[ITEMS];
-                if (L.mode == MODE_LINEAR) {
-#pragma unroll
-                    for (int it = 0; it < ITEMS; ++it) addr[it] = L.ptr + (uint64_t) f[it].lin * (uint32_t) sz;
-                } else {
-#pragma unroll
-                    for (int it = 0; it < ITEMS; ++it) {
-                        int32_t off = (int32_t) f[it].col * L.s32[ND - 1];
-#pragma unroll
-                        for (int d = 0; d < ND - 1; ++d) off += (int32_t) f[it].idx[d] * L.s32[d];
-                        addr[it] = L.ptr + (int64_t) off * sz;
-                    }
-                }
-                if (L.mode == MODE_BCAST) {
-#pragma unroll
-                    for (int it = 0; it < ITEMS; ++it) {
-                        const S v0 = load_elem<S>(addr[it], dt);
-#pragma unroll
-                        for (int v = 0; v < V; ++v) pf.pre[K][it][v] = v0;
-                    }
-                } else {
-#pragma unroll
-                    for (int it = 0; it < ITEMS; ++it) load_vec<S, V>(addr[it], dt, pf.pre[K][it]);
-                }
-            }
-            EwRingLoader<Eval, S, V, ND, ITEMS, K + 1, PASS>::run(p, rp, stage, f, pf);
-        }
-    }
-};
-
-template <class Eval, class S, int V, int ND, int ITEMS>
-__global__ void __launch_bounds__(256 + 32, kRingCtasPerSm) k_ew_ring(const __grid_constant__ EwParams p, const __grid_constant__ RingParams rp) {
-    extern __shared__ __align__(128) unsigned char ew_ring[];
-    __shared__ __align__(8) unsigned long long s_full[kRingStages], s_empty[kRingStages];
-    constexpr int NL = Eval::kLeaves > 0 ? Eval::kLeaves : 1;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kRingStages; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ew_smem_u32(&s_full[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(ew_smem_u32(&s_empty[s])));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid >= 256) {
-        // ---- producer ----
-        if (tid == 256) {
-            uint32_t k = 0;
-            for (uint32_t t = blockIdx.x; t < rp.n_tiles; t += gridDim.x, ++k) {
-                const uint32_t s = k % kRingStages, ph = (k / kRingStages) & 1u;
-                mbar_wait(&s_empty[s], ph ^ 1u);
-                const uint32_t bar = ew_smem_u32(&s_full[s]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rp.tx_bytes) : "memory");
-#pragma unroll
-                for (int K = 0; K < Eval::kLeaves; ++K) {
-                    if (rp.leaf_off[K] >= 0) {
-                        const char* src = p.leaf[K].ptr + (uint64_t) t * rp.leaf_bytes[K];
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(ew_smem_u32(ew_ring + s * rp.stage_bytes + rp.leaf_off[K])), "l"(src), "r"(rp.leaf_bytes[K]), "r"(bar)
-                                     : "memory");
-                    }
-                }
-            }
-        }
-        return;
-    }
-    // ---- consumers ----
-    const uint32_t inner = (uint32_t) p.shape[ND - 1];
-    uint32_t k = 0;
-    for (uint32_t t = blockIdx.x; t < rp.n_tiles; t += gridDim.x, ++k) {
-        const uint32_t s = k % kRingStages, ph = (k / kRingStages) & 1u;
-        const uint32_t base = t * (256u * ITEMS) + tid;
-        EwFetch<ND> f[ITEMS] = {};
-#pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            const uint32_t vec = base + it * 256u;
-            uint32_t cv = vec;
-            if constexpr (ND > 1) {
-                uint32_t row = fd_div(vec, p.div_vpr);
-                cv = vec - row * p.vec_per_row;
-                f[it].lin = row * inner + cv * V;
-#pragma unroll
-                for (int d = ND - 2; d >= 0; --d) {
-                    if (d == 0) {
-                        f[it].idx[0] = row;
-                    } else {
-                        uint32_t q = fd_div(row, p.div_dim[d]);
-                        f[it].idx[d] = row - q * (uint32_t) p.shape[d];
-                        row = q;
-                    }
-                }
-            } else {
-                f[it].lin = vec * V;
-            }
-            f[it].col = cv * V;
-            f[it].nvalid = V;
-        }
-        PreFetch<NL, ITEMS, S, V> pf;
-        EwRingLoader<Eval, S, V, ND, ITEMS, 0, 0>::run(p, rp, nullptr, f, pf);
-        mbar_wait(&s_full[s], ph);
-        EwRingLoader<Eval, S, V, ND, ITEMS, 0, 1>::run(p, rp, (const char*) ew_ring + s * rp.stage_bytes, f, pf);
-        __syncwarp();
-        if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ew_smem_u32(&s_empty[s])) : "memory");
-#pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            pf.u = it;
-            S r[V];
-            Eval::template run<S, V>(p.prog, pf, r);
-            ew_store_static<Eval::kResultType, S, V, ND>(p, f[it], r);
-        }
-    }
-}
-#endif  // XTB_RTC
-
 // Any rank, 64-bit indices (slow path: rank > 3 after collapsing, or >= 2^31 vectors).
 template <class Eval, class S, int V>
 __global__ void __launch_bounds__(256) k_ew_generic(const __grid_constant__ EwParams p) {
@@ -499,48 +323,6 @@ static int launch_ew_nd(const EwParams& p, DeviceCtx* ctx, const char* evname) {
     for (int k = 0; k < p.n_leaves; ++k) fast = fast && p.leaf[k].mode != MODE_GATHER;
     q.fast = fast;
     // large FAST problems with dense leaves: ring kernel (bulk copies into shared memory)
-    constexpr int64_t ring_block = 256 * kRingItems;
-    if (fast && p.total_vec >= (int64_t) 1 << 18 && p.total_vec % ring_block == 0 && getenv("XTB_NO_RING") == nullptr) {
-        RingParams rp;
-        memset(&rp, 0, sizeof(rp));
-        uint32_t off = 0;
-        int staged = 0;
-        for (int k = 0; k < XTB_MAX_LEAVES; ++k) rp.leaf_off[k] = -1;
-        for (int k = 0; k < p.n_leaves; ++k) {
-            const int sz = dtype_size(p.leaf[k].dtype);
-            const uint32_t bytes = (uint32_t) (ring_block * V * sz);
-            if (p.leaf[k].mode == MODE_LINEAR && (uintptr_t) p.leaf[k].ptr % 16 == 0 && bytes % 16 == 0) {
-                rp.leaf_off[k] = (int32_t) off;
-                rp.leaf_bytes[k] = bytes;
-                off += (bytes + 127) / 128 * 128;
-                rp.tx_bytes += bytes;
-                ++staged;
-            }
-        }
-        rp.stage_bytes = off;
-        rp.n_tiles = (uint32_t) (p.total_vec / ring_block);
-        const size_t smem = (size_t) off * kRingStages;
-        if (staged > 0 && smem <= 100 * 1024) {
-            const unsigned rgrid = (unsigned) std::min<int64_t>(rp.n_tiles, (int64_t) ctx->sm_count * kRingCtasPerSm);
-            snprintf(name, sizeof(name), "k_ew_ring<%s,S%d,V%d,ND%d>[%d staged]", evname, (int) sizeof(S) * 8, V, nd, staged);
-            switch (nd) {
-                case 1:
-                    XTB_CUDA(cudaFuncSetAttribute(k_ew_ring<Eval, S, V, 1, kRingItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    k_ew_ring<Eval, S, V, 1, kRingItems><<<rgrid, 256 + 32, smem, ctx->stream>>>(q, rp);
-                    break;
-                case 2:
-                    XTB_CUDA(cudaFuncSetAttribute(k_ew_ring<Eval, S, V, 2, kRingItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    k_ew_ring<Eval, S, V, 2, kRingItems><<<rgrid, 256 + 32, smem, ctx->stream>>>(q, rp);
-                    break;
-                default:
-                    XTB_CUDA(cudaFuncSetAttribute(k_ew_ring<Eval, S, V, 3, kRingItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    k_ew_ring<Eval, S, V, 3, kRingItems><<<rgrid, 256 + 32, smem, ctx->stream>>>(q, rp);
-                    break;
-            }
-            note_launch(name);
-            return check_launch(name);
-        }
-    }
     snprintf(name, sizeof(name), "k_ew<%s,S%d,V%d,ND%d>%s", evname, (int) sizeof(S) * 8, V, nd, fast ? "[fast]" : "");
     switch (nd) {
         case 1: k_ew<Eval, S, V, 1, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;
