@@ -206,6 +206,16 @@ int  xtb_graph_end(void** graph_exec);
 int  xtb_graph_launch(void* graph_exec);
 int  xtb_graph_destroy(void* graph_exec);
 
+/* Overlap: calls between xtb_fork_begin and xtb_fork_end are enqueued on a second stream that starts
+ * after everything enqueued so far; calls after xtb_fork_end continue on the main stream concurrently
+ * with them; xtb_fork_join makes the main stream wait for the forked section.  Works inside graph
+ * capture (join before xtb_graph_end).  Used to hide the allreduce of one reduction behind an
+ * independent elementwise kernel (sharded variance || exp(a - mean)).  The forked section must not
+ * write what the concurrent main-stream calls read or write. */
+int  xtb_fork_begin(void);
+int  xtb_fork_end(void);
+int  xtb_fork_join(void);
+
 /* ---- the hot path ---------------------------------------------------------- */
 /* out(i...) = static_cast<out.dtype>( program(leaves...)(i...) ) over out's shape.
  * Every leaf must be broadcastable to out's shape (else XTB_ERR_SHAPE). */

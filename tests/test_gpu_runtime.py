@@ -1,0 +1,63 @@
+"""GPU: stream fork / join and CUDA-graph capture of a call sequence give the same results as the plain
+sequence (the sharded cfg5 step overlaps its variance reduction with the exp(a - mean) map this way)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import assert_bit_exact
+
+pytestmark = pytest.mark.gpu
+
+
+def _step(xt, capi, lib, a, mean_, s_sq, o, fork):
+    if fork:
+        capi.check(lib.xtb_fork_begin())
+    xt._run_reducer(xt.sum(xt.square(a - mean_), [0]), xt.DeviceArray, out=s_sq)
+    if fork:
+        capi.check(lib.xtb_fork_end())
+    xt.assign(o, xt.exp(a - mean_))
+    if fork:
+        capi.check(lib.xtb_fork_join())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fork_join_matches_sequential(xt, gpu, graph):
+    from xtensor_b200 import capi
+    lib = capi.lib()
+    rng = np.random.default_rng(31)
+    an = rng.uniform(-1, 1, (4096, 512)).astype(np.float32)
+    a = xt.DeviceArray.from_numpy(an)
+    mean_ = xt.DeviceArray.from_numpy(an.mean(axis=0).astype(np.float32))
+    outs = []
+    for fork in (False, True):
+        s_sq = xt.DeviceArray.empty((512,), xt.F32)
+        o = xt.DeviceArray.empty(an.shape, xt.F32)
+        _step(xt, capi, lib, a, mean_, s_sq, o, fork)          # also sizes both scratch buffers
+        if graph:
+            g = C.c_void_p()
+            capi.check(lib.xtb_graph_begin())
+            _step(xt, capi, lib, a, mean_, s_sq, o, fork)
+            capi.check(lib.xtb_graph_end(C.byref(g)))
+            capi.check(lib.xtb_memset(C.c_void_p(s_sq.owner.ptr), 0, 512 * 4))
+            capi.check(lib.xtb_memset(C.c_void_p(o.owner.ptr), 0, an.size * 4))
+            for _ in range(3):
+                capi.check(lib.xtb_graph_launch(g))
+            capi.check(lib.xtb_sync())
+            lib.xtb_graph_destroy(g)
+        outs.append((s_sq.numpy(), o.numpy()))
+    assert_bit_exact(outs[0][0], outs[1][0])
+    assert_bit_exact(outs[0][1], outs[1][1])
+    ref = ((an.astype(np.float64) - mean_.numpy()) ** 2).sum(axis=0)
+    assert np.allclose(outs[1][0], ref, rtol=1e-5)
+
+
+def test_fork_misuse_is_an_error(xt, gpu):
+    from xtensor_b200 import capi
+    lib = capi.lib()
+    assert lib.xtb_fork_end() != 0
+    capi.check(lib.xtb_fork_begin())
+    assert lib.xtb_fork_begin() != 0
+    capi.check(lib.xtb_fork_end())
+    capi.check(lib.xtb_fork_join())
+    capi.check(lib.xtb_sync())

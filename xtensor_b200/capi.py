@@ -59,7 +59,7 @@ SYMBOLS = [
     "xtb_abi_version", "xtb_init", "xtb_device_count", "xtb_sync", "xtb_last_error", "xtb_set_stream",
     "xtb_get_stream", "xtb_malloc", "xtb_free", "xtb_memcpy", "xtb_memset", "xtb_host_alloc", "xtb_host_free",
     "xtb_event_create", "xtb_event_record", "xtb_event_elapsed_ms", "xtb_event_destroy",
-    "xtb_graph_begin", "xtb_graph_end", "xtb_graph_launch", "xtb_graph_destroy",
+    "xtb_graph_begin", "xtb_graph_end", "xtb_graph_launch", "xtb_graph_destroy", "xtb_fork_begin", "xtb_fork_end", "xtb_fork_join",
     "xtb_assign", "xtb_assign_host", "xtb_reduce", "xtb_scan", "xtb_comm_unique_id", "xtb_comm_init", "xtb_comm_destroy",
     "xtb_comm_info", "xtb_allreduce", "xtb_launch_count", "xtb_last_kernel", "xtb_program_result_type",
 ]
@@ -87,6 +87,9 @@ def lib():
         "xtb_init": (i32, [i32]),
         "xtb_device_count": (i32, [C.POINTER(i32)]),
         "xtb_sync": (i32, []),
+        "xtb_fork_begin": (i32, []),
+        "xtb_fork_end": (i32, []),
+        "xtb_fork_join": (i32, []),
         "xtb_last_error": (C.c_char_p, []),
         "xtb_set_stream": (i32, [vp]),
         "xtb_get_stream": (vp, []),

@@ -38,6 +38,13 @@ struct DeviceCtx {
     size_t l2_bytes = 0;
     void* scratch = nullptr;             // reduction partials / scan state
     size_t scratch_bytes = 0;
+    // xtb_fork_begin / end / join: a second stream for work that may overlap the main sequence
+    cudaStream_t fork_stream = nullptr;
+    cudaStream_t fork_saved = nullptr;   // the stream to return to at xtb_fork_end
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    bool forked = false;
+    void* fork_scratch = nullptr;        // calls on the fork stream get their own scratch
+    size_t fork_scratch_bytes = 0;
 };
 // Context of the calling thread's device; fails with XTB_ERR_NO_DEVICE when
 // there is no GPU.  (No CPU fallback by design.)

@@ -322,7 +322,6 @@ static int launch_ew_nd(const EwParams& p, DeviceCtx* ctx, const char* evname) {
     bool fast = (p.shape[nd - 1] % V == 0) && (p.total_vec % per_block == 0) && p.out.mode != MODE_GATHER && p.out.mode != MODE_BCAST;
     for (int k = 0; k < p.n_leaves; ++k) fast = fast && p.leaf[k].mode != MODE_GATHER;
     q.fast = fast;
-    // large FAST problems with dense leaves: ring kernel (bulk copies into shared memory)
     snprintf(name, sizeof(name), "k_ew<%s,S%d,V%d,ND%d>%s", evname, (int) sizeof(S) * 8, V, nd, fast ? "[fast]" : "");
     switch (nd) {
         case 1: k_ew<Eval, S, V, 1, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;

@@ -107,15 +107,17 @@ int get_ctx(DeviceCtx** ctx) {
 }
 
 int ensure_scratch(DeviceCtx* ctx, size_t bytes, void** ptr) {
-    if (bytes > ctx->scratch_bytes) {
-        if (ctx->scratch) XTB_CUDA(cudaFreeAsync(ctx->scratch, ctx->stream));
+    void*& buf = ctx->forked ? ctx->fork_scratch : ctx->scratch;
+    size_t& have = ctx->forked ? ctx->fork_scratch_bytes : ctx->scratch_bytes;
+    if (bytes > have) {
+        if (buf) XTB_CUDA(cudaFreeAsync(buf, ctx->stream));
         size_t want = std::max(bytes, (size_t) 1 << 20);
-        ctx->scratch = nullptr;
-        ctx->scratch_bytes = 0;
-        XTB_CUDA(cudaMallocAsync(&ctx->scratch, want, ctx->stream));
-        ctx->scratch_bytes = want;
+        buf = nullptr;
+        have = 0;
+        XTB_CUDA(cudaMallocAsync(&buf, want, ctx->stream));
+        have = want;
     }
-    *ptr = ctx->scratch;
+    *ptr = buf;
     return XTB_OK;
 }
 
@@ -408,6 +410,41 @@ int xtb_event_elapsed_ms(void* start, void* stop, float* ms) {
 
 int xtb_event_destroy(void* event) {
     if (event) XTB_CUDA(cudaEventDestroy((cudaEvent_t) event));
+    return XTB_OK;
+}
+
+int xtb_fork_begin(void) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    if (c->forked) XTB_FAIL(XTB_ERR_INVALID, "xtb_fork_begin: already forked");
+    if (!c->fork_stream) {
+        XTB_CUDA(cudaStreamCreateWithFlags(&c->fork_stream, cudaStreamNonBlocking));
+        XTB_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+        XTB_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
+    }
+    XTB_CUDA(cudaEventRecord(c->fork_ev, c->stream));
+    XTB_CUDA(cudaStreamWaitEvent(c->fork_stream, c->fork_ev, 0));
+    c->fork_saved = c->stream;
+    c->stream = c->fork_stream;
+    c->forked = true;
+    return XTB_OK;
+}
+
+int xtb_fork_end(void) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    if (!c->forked) XTB_FAIL(XTB_ERR_INVALID, "xtb_fork_end without xtb_fork_begin");
+    XTB_CUDA(cudaEventRecord(c->join_ev, c->fork_stream));
+    c->stream = c->fork_saved;
+    c->forked = false;
+    return XTB_OK;
+}
+
+int xtb_fork_join(void) {
+    DeviceCtx* c;
+    XTB_TRY(get_ctx(&c));
+    if (c->forked || !c->join_ev) XTB_FAIL(XTB_ERR_INVALID, "xtb_fork_join: no finished fork section");
+    XTB_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
     return XTB_OK;
 }
 

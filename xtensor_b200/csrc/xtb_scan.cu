@@ -16,6 +16,8 @@
 //                     coalesced across the inner dims.
 #include <algorithm>
 #include <cstdlib>
+#include <cuda.h>              // CUtensorMap (the driver entry point is looked up at run time, libcuda is not linked)
+#include <cudaTypedefs.h>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
 
@@ -44,7 +46,6 @@ struct ScanParams {
     // lookback state
     uint32_t tiles_per_row;
     uint32_t total_tiles;
-    uint32_t* ticket;
     char* aggregate;              // {flag, value} slot per tile
     char* prefix;                 // {flag, value} slot per block of kScanWindow tiles: the block total
     int32_t vec_io;               // input is the accumulator dtype, unit stride, 16-byte aligned rows (in and out)
@@ -113,7 +114,7 @@ template <class T> XTB_DEV T shfl_up_t(T v, int d) {
 // where tree() is a fixed-shape reduction (per-lane ascending partial sums, then a butterfly), so a
 // floating-point result depends only on the tile's position, never on timing: run-to-run
 // deterministic, no serial chain (dependency depth 2), and one read + one write of the data.
-// Tiles take a ticket in launch order, so everything a tile waits for is already running.
+// Tiles are processed in launch order (blockIdx.x), so everything a tile waits for is already running.
 constexpr int kScanWindow = 256;   // tiles per block = 32 lanes x 8
 constexpr int kScanWarpsPerTile = kScanThreads / 32;
 
@@ -420,7 +421,6 @@ __global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_sc
     extern __shared__ __align__(128) unsigned char st_smem[];
     T* sm = (T*) st_smem;
     __shared__ __align__(8) unsigned long long s_bar[kStWarps];
-    __shared__ uint32_t s_tile;
     __shared__ T s_warp[kStWarps];
     __shared__ T s_prefix;
     __shared__ T s_total;
@@ -428,15 +428,12 @@ __global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_sc
     const int op = p.op;
     const T ident = scan_identity<T>(op);
     constexpr bool chained = CHAINED;
-    uint32_t tile = blockIdx.x;
+    // Tiles are taken in launch order: CTAs of a 1-D grid are dispatched by ascending blockIdx.x (the
+    // assumption CUB's decoupled look-back makes too), so every predecessor of a tile is running or done.
+    const uint32_t tile = blockIdx.x;
     if (lane == 0 && warp < kStWarps) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[warp])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (chained) {
-        if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        tile = s_tile;
     }
     __syncwarp();
     const uint32_t row = tile / p.tiles_per_row;
@@ -603,25 +600,54 @@ __global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_sc
 // not depend on timing.  One tile along the axis and >= 256 columns: exactly the reference's order.
 constexpr int kCtThreads = 256;
 constexpr int kCtFan = 16;
-constexpr int kCtMaxLevels = 8;
+constexpr int kCtMaxLevels = 4;
 constexpr int kCtTileBytes = 64 * 1024;
 
 struct ColTileParams {
     int32_t W, R, G;                   // columns / rows per tile, row groups per tile (= 256 / W)
     int32_t strips, chunks, levels;    // tiles across the columns / along the axis, tree levels
     int32_t bulk;                      // tile rows can be fetched with cp.async.bulk
+    int32_t tma;                       // the whole tile is one TMA tensor copy (tensor map passed alongside)
     int64_t units[kCtMaxLevels];       // units along the axis at each tree level: ceil(chunks / 16^l)
     int64_t level_off[kCtMaxLevels];   // first slot of each level
     char* vals;                        // [slot][256] column totals, each a {flag, value} word (zeroed before the launch)
 };
 
+// gather the totals of the `cnt` (< 16) siblings that precede this tile at one tree level, for one column
+template <class T> struct ColGather {
+    T v[kCtFan - 1];
+    uint32_t pending;          // bit j: sibling j not yet seen
+    XTB_DEV void issue(const char* vals, int64_t first, uint32_t cnt, int col) {
+        pending = 0;
+#pragma unroll
+        for (int j = 0; j < kCtFan - 1; ++j) {
+            v[j] = T(0);
+            if ((uint32_t) j < cnt && !slot_try<T>(vals, (uint32_t) ((first + j) * 256 + col), v[j])) pending |= 1u << j;
+        }
+    }
+    XTB_DEV T finish(int op, const char* vals, int64_t first, uint32_t cnt, int col) {
+        while (pending) {
+            __nanosleep(64);
+#pragma unroll
+            for (int j = 0; j < kCtFan - 1; ++j)
+                if ((pending >> j) & 1u)
+                    if (slot_try<T>(vals, (uint32_t) ((first + j) * 256 + col), v[j])) pending &= ~(1u << j);
+        }
+        T acc = scan_identity<T>(op);
+#pragma unroll
+        for (int j = 0; j < kCtFan - 1; ++j)
+            if ((uint32_t) j < cnt) acc = j == 0 ? v[0] : scan_op<T>(op, acc, v[j]);
+        return acc;
+    }
+};
+
 template <class T, bool BULK>
-__global__ void __launch_bounds__(kCtThreads + 32, 3) k_scan_coltile(const __grid_constant__ ScanParams p, const __grid_constant__ ColTileParams c) {
+__global__ void __launch_bounds__(kCtThreads, 3) k_scan_coltile(const __grid_constant__ ScanParams p, const __grid_constant__ ColTileParams c,
+                                                                 const __grid_constant__ CUtensorMap tmap) {
     constexpr int CV = BULK ? 16 / (int) sizeof(T) : 1;   // adjacent columns per scan thread (one 128-bit access)
     extern __shared__ __align__(128) unsigned char ct_smem[];
     T* sm = (T*) ct_smem;                                  // [R][W]
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ uint32_t s_tile;
     __shared__ __align__(16) T s_gt[kCtThreads * CV];      // totals of the row groups [G][W]
     __shared__ T s_tot[kCtThreads];                        // column totals of the tile
     __shared__ T s_off[kCtThreads];                        // exclusive prefix of the tile per column
@@ -632,12 +658,12 @@ __global__ void __launch_bounds__(kCtThreads + 32, 3) k_scan_coltile(const __gri
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (chained) s_tile = atomicAdd(p.ticket, 1u);
     }
     __syncthreads();
-    const uint32_t tile = chained ? s_tile : blockIdx.x;
-    // tickets run strip-fastest, then along the axis, then over the outer index: what a tile waits for
-    // was started at least `strips` tickets earlier
+    // Tiles are taken in launch order (CTAs of a 1-D grid are dispatched by ascending blockIdx.x, the
+    // same assumption CUB's decoupled look-back makes): strip-fastest, then along the axis, then over
+    // the outer index, so whatever a tile waits for was dispatched at least `strips` CTAs earlier.
+    const uint32_t tile = blockIdx.x;
     const uint32_t per_o = (uint32_t) c.chunks * (uint32_t) c.strips;
     const uint32_t o = tile / per_o;
     const uint32_t rem = tile - o * per_o;
@@ -648,87 +674,21 @@ __global__ void __launch_bounds__(kCtThreads + 32, 3) k_scan_coltile(const __gri
     const int wv = (int) (p.inner - col0 < W ? p.inner - col0 : W);        // valid columns
     const int64_t r0 = (int64_t) chunk * R;
     const int rvalid = (int) (p.n - r0 < R ? p.n - r0 : R);
-
-    if (warp == kCtThreads / 32) {
-        // ---- look-back warp (present only when chained) ----
-        // Every published column total is a {flag, value} slot of its own (one 64-/128-bit access), so
-        // neither side needs a fence.  Columns are handled CH at a time per lane to bound registers.
-        constexpr int CH = sizeof(T) == 4 ? 4 : 2;
-        const int64_t lane_base = (int64_t) o * c.strips + strip;
-        bool synced = false;
-        for (int h = 0; h < 8 / CH; ++h) {
-            T low[CH];
-#pragma unroll
-            for (int i = 0; i < CH; ++i) low[i] = ident;
-            uint32_t u = chunk;                            // index of my ancestor unit at level l
-            uint32_t span = 1;                             // chunks per unit at level l
-            for (int l = 0; l < c.levels; ++l) {
-                const uint32_t cnt = u % kCtFan;           // preceding siblings
-                const int64_t first = c.level_off[l] + lane_base * c.units[l] + (u - cnt);
-                T part[CH];
-#pragma unroll
-                for (int i = 0; i < CH; ++i) part[i] = ident;
-                // JU siblings at a time: all their slots are requested before the first is inspected
-                constexpr int JU = 4;
-                for (uint32_t j0 = 0; j0 < cnt; j0 += JU) {
-                    T v[JU][CH];
-                    bool ok[JU][CH];
-#pragma unroll
-                    for (int jj = 0; jj < JU; ++jj) {
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) {
-                            const int cx = lane + 32 * (h * CH + i);
-                            v[jj][i] = ident;
-                            ok[jj][i] = j0 + jj >= cnt || cx >= wv || slot_try<T>(c.vals, (uint32_t) ((first + j0 + jj) * 256 + cx), v[jj][i]);
-                        }
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < JU; ++jj) {
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) {
-                            const int cx = lane + 32 * (h * CH + i);
-                            while (!ok[jj][i]) {
-                                __nanosleep(40);
-                                ok[jj][i] = slot_try<T>(c.vals, (uint32_t) ((first + j0 + jj) * 256 + cx), v[jj][i]);
-                            }
-                            part[i] = scan_op<T>(op, part[i], v[jj][i]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < CH; ++i) low[i] = scan_op<T>(op, part[i], low[i]);
-                // last chunk of a level-(l+1) unit that something follows: publish that unit's total
-                span *= kCtFan;
-                if (l + 1 < c.levels && (chunk + 1) % span == 0 && chunk + 1 < (uint32_t) c.chunks) {
-                    if (!synced) {
-                        asm volatile("bar.sync 2, 64;" ::: "memory");      // the tile's own totals are in s_tot
-                        synced = true;
-                    }
-                    const int64_t slot = c.level_off[l + 1] + lane_base * c.units[l + 1] + u / kCtFan;
-#pragma unroll
-                    for (int i = 0; i < CH; ++i) {
-                        const int cx = lane + 32 * (h * CH + i);
-                        if (cx < wv) slot_publish<T>(c.vals, (uint32_t) (slot * 256 + cx), scan_op<T>(op, low[i], s_tot[cx]));
-                    }
-                }
-                u /= kCtFan;
-            }
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-                const int cx = lane + 32 * (h * CH + i);
-                if (cx < wv) s_off[cx] = low[i];
-            }
-        }
-        if (!synced) asm volatile("bar.sync 2, 64;" ::: "memory");
-        __syncthreads();
-        return;
-    }
-
-    // ---- scan threads ----
     const int isz = dtype_size(p.in_dtype);
     const char* in_o = p.in + scan_offset(o, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
+
+    // ---- fetch the tile ----
     if constexpr (BULK) {
-        if (warp == 0) {
+        if (c.tma) {
+            // one TMA tensor copy for the whole R x W box (rows / columns outside the array are zero-filled
+            // and count as transferred)
+            if (tid == 0) {
+                const uint32_t bar = smem_u32(&s_bar);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (R * W * (int) sizeof(T))) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(smem_u32(sm)), "l"(&tmap), "r"((int) col0), "r"((int) r0), "r"((int) o), "r"(bar) : "memory");
+            }
+        } else if (warp == 0) {
             const uint32_t row_bytes = (uint32_t) wv * (uint32_t) sizeof(T);
             const uint32_t bar = smem_u32(&s_bar);
             if (lane == 0)
@@ -740,13 +700,32 @@ __global__ void __launch_bounds__(kCtThreads + 32, 3) k_scan_coltile(const __gri
                              ::"r"(smem_u32(sm + (size_t) r * W)), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
             }
         }
+    }
+    // ---- look-back, overlapped with the fetch: thread `tid` owns column `tid` of the strip ----
+    // Every published column total is a {flag, value} slot of its own (one 64-/128-bit access): no fences.
+    // Levels >= 1 were published long ago; the level-0 siblings (the tiles right above) may still be in
+    // flight, so their first request goes out now and what is missing is picked up after phase A.
+    const bool lb = chained && tid < wv;
+    const int64_t lane_base = (int64_t) o * c.strips + strip;
+    // the first requests for the two lowest levels go out now; nothing is waited for before this tile
+    // has published its own totals (no tile's publication may depend on another tile's look-back)
+    ColGather<T> g0, g1;
+    g0.pending = g1.pending = 0;
+    const uint32_t cnt0 = chunk % kCtFan, u1 = chunk / kCtFan, cnt1 = u1 % kCtFan;
+    const int64_t first0 = c.level_off[0] + lane_base * c.units[0] + (chunk - cnt0);
+    const int64_t first1 = c.levels > 1 ? c.level_off[1] + lane_base * c.units[1] + (u1 - cnt1) : 0;
+    if (lb) {
+        if (c.levels > 1) g1.issue(c.vals, first1, cnt1, tid);
+        g0.issue(c.vals, first0, cnt0, tid);
+    }
+    if constexpr (BULK) {
         uint32_t done = 0;
         while (!done) {
             asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
                          : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
         }
     }
-    // phase A: thread (g, cv) walks rows [ra, rb) of its CV adjacent columns downwards, in place
+    // ---- phase A: thread (g, cv) walks rows [ra, rb) of its CV adjacent columns downwards, in place ----
     const int wt = W / CV;                                 // threads across a tile row
     const int g = tid / wt, col = (tid - g * wt) * CV;
     const bool active = g < c.G && col < wv;               // wv is a multiple of CV
@@ -794,7 +773,7 @@ __global__ void __launch_bounds__(kCtThreads + 32, 3) k_scan_coltile(const __gri
 #pragma unroll
         for (int k = 0; k < CV; ++k) s_gt[g * W + col + k] = acc[k];
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kCtThreads) : "memory");
+    __syncthreads();
     // offset of my row group inside the tile; column totals
     T go[CV];
 #pragma unroll
@@ -806,22 +785,54 @@ __global__ void __launch_bounds__(kCtThreads + 32, 3) k_scan_coltile(const __gri
         }
     }
     if (chained) {
+        const bool more = chunk + 1 < (uint32_t) c.chunks;          // something follows this tile
         if (active && g == 0) {
-            const bool pub = chunk + 1 < (uint32_t) c.chunks;
-            const int64_t slot = c.level_off[0] + ((int64_t) o * c.strips + strip) * c.units[0] + chunk;
+            const int64_t slot = c.level_off[0] + lane_base * c.units[0] + chunk;
 #pragma unroll
             for (int k = 0; k < CV; ++k) {
                 T tot = s_gt[col + k];
                 for (int gg = 1; gg < c.G; ++gg) tot = scan_op<T>(op, tot, s_gt[gg * W + col + k]);
                 s_tot[col + k] = tot;
-                if (pub) slot_publish<T>(c.vals, (uint32_t) (slot * 256 + col + k), tot);
+                if (more) slot_publish<T>(c.vals, (uint32_t) (slot * 256 + col + k), tot);
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kCtThreads) : "memory");
-        if (warp == 0) asm volatile("bar.arrive 2, 64;" ::: "memory");
-        __syncthreads();                                   // the look-back warp has stored s_off
+        __syncthreads();                                            // s_tot complete
+        if (lb) {
+            // walk up the tree: part[l] = the siblings before me at level l; right after part[l] is known
+            // the total of my level-(l+1) unit can be published if I am its last chunk
+            T below = ident;                                        // part[l-1] + ... + part[0] (position order)
+            T low = ident;                                          // everything above the tile
+            uint32_t u = chunk, span = 1;
+#pragma unroll
+            for (int l = 0; l < kCtMaxLevels; ++l) {
+                if (l < c.levels) {
+                    T part;
+                    if (l == 0) {
+                        part = g0.finish(op, c.vals, first0, cnt0, tid);
+                    } else if (l == 1) {
+                        part = g1.finish(op, c.vals, first1, cnt1, tid);
+                    } else {
+                        const uint32_t cnt = u % kCtFan;
+                        const int64_t first = c.level_off[l] + lane_base * c.units[l] + (u - cnt);
+                        ColGather<T> gl;
+                        gl.issue(c.vals, first, cnt, tid);
+                        part = gl.finish(op, c.vals, first, cnt, tid);
+                    }
+                    below = l == 0 ? part : scan_op<T>(op, part, below);
+                    low = below;
+                    span *= kCtFan;
+                    u /= kCtFan;
+                    if (l + 1 < c.levels && more && (chunk + 1) % span == 0) {
+                        const int64_t slot = c.level_off[l + 1] + lane_base * c.units[l + 1] + chunk / span;
+                        slot_publish<T>(c.vals, (uint32_t) (slot * 256 + tid), scan_op<T>(op, below, s_tot[tid]));
+                    }
+                }
+            }
+            s_off[tid] = low;
+        }
+        __syncthreads();
     }
-    // phase B: add what lies above (other tiles, earlier row groups), stream out
+    // ---- phase B: add what lies above (other tiles, earlier row groups), stream out ----
     if (active && ra < rb) {
         const bool from_tiles = chained && chunk > 0;
         const bool have_off = from_tiles || g > 0;
@@ -887,7 +898,7 @@ template <class T> static int scan_coltile(ScanParams p, DeviceCtx* ctx) {
     if (c.chunks > 1) {
         int64_t slots = 0, units = c.chunks, span = 1;
         while (span < c.chunks) {
-            if (c.levels >= kCtMaxLevels) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: axis too long");
+            if (c.levels >= kCtMaxLevels) return 1;      // axis too long for the tree: the caller walks the columns instead
             c.units[c.levels] = units;
             c.level_off[c.levels] = slots;
             slots += units * c.strips * p.rows;
@@ -898,22 +909,45 @@ template <class T> static int scan_coltile(ScanParams p, DeviceCtx* ctx) {
         if (slots * 256 >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
         const size_t val_bytes = (size_t) slots * 256 * 2 * sizeof(T);
         void* scratch = nullptr;
-        XTB_TRY(ensure_scratch(ctx, 256 + val_bytes, &scratch));
-        char* s = (char*) scratch;
-        p.ticket = (uint32_t*) s;
-        c.vals = s + 256;
-        XTB_CUDA(cudaMemsetAsync(s, 0, 256 + val_bytes, ctx->stream));
+        XTB_TRY(ensure_scratch(ctx, val_bytes, &scratch));
+        c.vals = (char*) scratch;
+        XTB_CUDA(cudaMemsetAsync(scratch, 0, val_bytes, ctx->stream));
     }
     const size_t smem = (size_t) c.R * c.W * sizeof(T);
-    const unsigned threads = kCtThreads + (c.chunks > 1 ? 32 : 0);
+    const unsigned threads = kCtThreads;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (bulk && p.n_outer <= 1 && c.R <= 256 && getenv("XTB_NO_TMA") == nullptr) {
+        // 3-D view (inner, axis, outer) of the input; box = (W, R, 1)
+        static PFN_cuTensorMapEncodeTiled encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                encode = (PFN_cuTensorMapEncodeTiled) fn;
+        }
+        const int64_t outer_stride = p.n_outer == 1 && p.outer_shape[0] > 1 ? p.outer_stride[0] : p.n * p.in_axis_stride;
+        if (encode && (outer_stride * asz) % 16 == 0 && p.in_axis_stride > 0 && outer_stride > 0) {
+            const CUtensorMapDataType dt = std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                         : std::is_same<T, double>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+                                         : sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+            const cuuint64_t gdim[3] = {(cuuint64_t) p.inner, (cuuint64_t) p.n, (cuuint64_t) p.rows};
+            const cuuint64_t gstr[2] = {(cuuint64_t) (p.in_axis_stride * asz), (cuuint64_t) (outer_stride * asz)};
+            const cuuint32_t box[3] = {(cuuint32_t) c.W, (cuuint32_t) c.R, 1u};
+            const cuuint32_t estr[3] = {1u, 1u, 1u};
+            const CUresult r = encode(&tmap, dt, 3, (void*) p.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            c.tma = r == CUDA_SUCCESS ? 1 : 0;
+        }
+    }
     if (bulk) {
         XTB_CUDA(cudaFuncSetAttribute(k_scan_coltile<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtTileBytes));
-        k_scan_coltile<T, true><<<(unsigned) tiles, threads, smem, ctx->stream>>>(p, c);
+        k_scan_coltile<T, true><<<(unsigned) tiles, threads, smem, ctx->stream>>>(p, c, tmap);
     } else {
         XTB_CUDA(cudaFuncSetAttribute(k_scan_coltile<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtTileBytes));
-        k_scan_coltile<T, false><<<(unsigned) tiles, threads, smem, ctx->stream>>>(p, c);
+        k_scan_coltile<T, false><<<(unsigned) tiles, threads, smem, ctx->stream>>>(p, c, tmap);
     }
-    note_launch(c.chunks > 1 ? "k_scan_coltile[look-back]" : "k_scan_coltile");
+    note_launch(c.chunks > 1 ? (c.tma ? "k_scan_coltile[TMA, look-back]" : "k_scan_coltile[look-back]") : (c.tma ? "k_scan_coltile[TMA]" : "k_scan_coltile"));
     return check_launch("k_scan_coltile");
 }
 
@@ -957,7 +991,7 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         note_launch("k_scan_columns");
         return check_launch("k_scan_columns");
     }
-    // contiguous: state = ticket | one slot per tile | one slot per block of kScanWindow tiles
+    // contiguous: state = one slot per tile | one slot per block of kScanWindow tiles
     ScanParams q = p;
     using C = ScanTile<T>;
     if (q.rows > 1 && q.n <= C::WARP_ELEMS) {
@@ -1005,12 +1039,11 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         const size_t agg_bytes = ((size_t) tiles * C::SLOT + 255) / 256 * 256;
         const size_t blk_bytes = ((size_t) (bpr * q.rows) * C::SLOT + 255) / 256 * 256;
         void* scratch = nullptr;
-        XTB_TRY(ensure_scratch(ctx, 256 + agg_bytes + blk_bytes, &scratch));
+        XTB_TRY(ensure_scratch(ctx, agg_bytes + blk_bytes, &scratch));
         char* s = (char*) scratch;
-        q.ticket = (uint32_t*) s;
-        q.aggregate = s + 256;
-        q.prefix = s + 256 + agg_bytes;
-        XTB_CUDA(cudaMemsetAsync(s, 0, 256 + agg_bytes + blk_bytes, ctx->stream));
+        q.aggregate = s;
+        q.prefix = s + agg_bytes;
+        XTB_CUDA(cudaMemsetAsync(s, 0, agg_bytes + blk_bytes, ctx->stream));
     }
     if (staged) {
         const size_t smem = (size_t) tile_elems * sizeof(T);
@@ -1120,12 +1153,14 @@ extern "C" int xtb_scan(int op, int acc_type, const xtb_operand* in, int axis, c
         // a long axis: column tiles (single pass).  Short axes with very many columns keep the plain
         // thread-per-column walk (exactly the reference's order, enough parallelism from the columns).
         if (p.n >= 128 && p.inner < 0x7fffffffLL - 256) {
+            int r;
             switch (acc_type) {
-                case XTB_I32: case XTB_U32: return scan_coltile<uint32_t>(p, ctx);
-                case XTB_I64: case XTB_U64: return scan_coltile<unsigned long long>(p, ctx);
-                case XTB_F32: return scan_coltile<float>(p, ctx);
-                default: return scan_coltile<double>(p, ctx);
+                case XTB_I32: case XTB_U32: r = scan_coltile<uint32_t>(p, ctx); break;
+                case XTB_I64: case XTB_U64: r = scan_coltile<unsigned long long>(p, ctx); break;
+                case XTB_F32: r = scan_coltile<float>(p, ctx); break;
+                default: r = scan_coltile<double>(p, ctx); break;
             }
+            if (r <= 0) return r;
         }
     }
     switch (acc_type) {
