@@ -176,13 +176,8 @@ def run_ours(args):
         dist = dist_
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ident = [None]
-        if rank == 0:
-            buf = C.create_string_buffer(128)
-            capi.check(lib.xtb_comm_unique_id(buf))
-            ident[0] = buf.raw
-        dist.broadcast_object_list(ident, src=0)
-        capi.check(lib.xtb_comm_init(rank, world, C.create_string_buffer(ident[0], 128)))
+        from xtensor_b200 import shard
+        args.p2p_on = shard.init_comm(dist, rank, world)
 
     shape = CFG2["shape"]
     a, b, d = make_inputs(shape, rank)
@@ -424,7 +419,8 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
         var_check = float(var_.numpy()[:8].astype(np.float64).mean())
         out["cfg5_sharded_pipeline"] = {"ms": round(ms, 4), "GBs_aggregate": round(nbytes / ms / 1e6, 1),
                                         "frac_of_measured_peak_per_gpu": round(nbytes / ms / 1e6 / peak / world, 4),
-                                        "rows_per_gpu": rows, "scaling": "strong", "allreduce": world > 1,
+                                        "rows_per_gpu": rows, "scaling": "strong",
+                                        "allreduce": ("peer-memory kernel (NVLink)" if getattr(args, "p2p_on", False) else "nccl") if world > 1 else False,
                                         "cuda_graph": use_graph, "variance_overlaps_map": overlap, "steps": n5, "variance_sample_mean": round(var_check, 6)}
     except Exception as ex:  # the headline number must survive a failure of the side measurements
         out["other_configs_error"] = repr(ex)

@@ -256,6 +256,14 @@ int  xtb_comm_unique_id(void* id128);
 int  xtb_comm_init(int rank, int world, const void* id128);
 int  xtb_comm_destroy(void);
 int  xtb_comm_info(int* rank, int* world);
+/* Optional: peer-memory allreduce for small payloads (<= 256 KB, 32-/64-bit dtypes).  Every rank
+ * calls xtb_comm_p2p_handle (64-byte CUDA IPC handle of its exchange window), the host hands all
+ * handles, in rank order, to every rank, which calls xtb_comm_p2p_attach.  From then on
+ * xtb_allreduce / xtb_reduce(..., allreduce=1) use one kernel over NVLink peer memory (partials added
+ * in rank order: identical bits on every rank) instead of NCCL for such payloads.  Every rank must
+ * finish xtb_comm_p2p_attach before any rank's next allreduce. */
+int  xtb_comm_p2p_handle(void* handle64);
+int  xtb_comm_p2p_attach(const void* handles, int world);
 /* in-place allreduce of `count` elements of storage dtype `dtype` on the stream */
 int  xtb_allreduce(void* buf, size_t count, int dtype, int op);
 

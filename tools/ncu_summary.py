@@ -29,3 +29,20 @@ for r in rows[2:]:
         if k in hdr:
             i = hdr.index(k)
             print(f"   {k:80s} {r[i]:>16s} {units[i]}")
+
+
+def write_csv(rep, path):
+    """Compact CSV (one row per profiled launch) of the metrics above, for profiles/."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    keys = [k for k in KEYS if k in hdr] + [k for k in ("launch__block_size", "lts__t_sector_hit_rate.pct") if k in hdr]
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel"] + [f"{k} [{units[hdr.index(k)]}]" for k in keys])
+        for r in rows[2:]:
+            w.writerow([r[hdr.index("Kernel Name")][:160]] + [r[hdr.index(k)] for k in keys])
+
+
+if len(sys.argv) > 2:
+    write_csv(sys.argv[1], sys.argv[2])

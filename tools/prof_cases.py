@@ -9,7 +9,7 @@ from xtensor_b200 import capi  # noqa: E402
 from xtensor_b200 import expr as xt  # noqa: E402
 
 capi.check(capi.lib().xtb_init(0))
-cases = sys.argv[1:] or ["cfg1", "cfg2", "cfg3a0", "cfg3a2", "cfg4", "cfg5map"]
+cases = sys.argv[1:] or ["cfg1", "cfg2", "cfg3a0", "cfg3a2", "cfg4", "cfg5map", "cfg5sum", "cfg5var", "cumsum_flat", "cumsum_ax1", "cumsum_ax0"]
 rng = np.random.default_rng(0)
 REPS = int(os.environ.get("REPS", "3"))
 for c in cases:

@@ -61,7 +61,7 @@ SYMBOLS = [
     "xtb_event_create", "xtb_event_record", "xtb_event_elapsed_ms", "xtb_event_destroy",
     "xtb_graph_begin", "xtb_graph_end", "xtb_graph_launch", "xtb_graph_destroy", "xtb_fork_begin", "xtb_fork_end", "xtb_fork_join",
     "xtb_assign", "xtb_assign_host", "xtb_reduce", "xtb_scan", "xtb_comm_unique_id", "xtb_comm_init", "xtb_comm_destroy",
-    "xtb_comm_info", "xtb_allreduce", "xtb_launch_count", "xtb_last_kernel", "xtb_program_result_type",
+    "xtb_comm_info", "xtb_comm_p2p_handle", "xtb_comm_p2p_attach", "xtb_allreduce", "xtb_launch_count", "xtb_last_kernel", "xtb_program_result_type",
 ]
 
 _LIB = None
@@ -116,6 +116,8 @@ def lib():
         "xtb_comm_init": (i32, [i32, i32, vp]),
         "xtb_comm_destroy": (i32, []),
         "xtb_comm_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
+        "xtb_comm_p2p_handle": (i32, [vp]),
+        "xtb_comm_p2p_attach": (i32, [vp, i32]),
         "xtb_allreduce": (i32, [vp, sz, i32, i32]),
         "xtb_launch_count": (i64, [i32]),
         "xtb_last_kernel": (C.c_char_p, []),

@@ -5,6 +5,12 @@
 // (include/xtensor/reducers/xblockwise_reducer_functors.hpp:45-260).
 // NCCL is resolved with dlopen at xtb_comm_init so that single-GPU users do not
 // need it at load time.
+//
+// Small payloads (the (8192,) partials of cfg5 are 32 KB) are latency-bound in NCCL; for them
+// k_allreduce_p2p does the exchange itself over NVLink peer memory: every rank owns a window
+// (cudaMalloc + CUDA IPC, mapped into all ranks), drops its partial into it, raises a flag in every
+// peer's window, waits for the peers' flags in its own, and then adds the R partials straight out of
+// the peers' memory in rank order -- one kernel, one NVLink round trip, bit-identical on all ranks.
 #include <dlfcn.h>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
@@ -84,12 +90,114 @@ static int nccl_op(int op) {
     }
 }
 
+
+// ---- peer-memory allreduce -------------------------------------------------------------------------
+constexpr size_t kP2pMaxBytes = 256 * 1024;
+constexpr int kP2pMaxWorld = 8;
+constexpr size_t kP2pHeader = 4096;                           // flags[2][16] at 0, launch counter at 2048
+constexpr size_t kP2pWindow = kP2pHeader + 2 * kP2pMaxBytes;  // two payload slots (epoch parity)
+constexpr int kP2pWindows = 2;                                // [1] serves calls made inside xtb_fork_begin/end
+
+struct P2pParams {
+    char* win[kP2pMaxWorld];
+    int32_t rank, world;
+};
+struct P2p {
+    bool ready = false;
+    char* local = nullptr;                    // kP2pWindows windows
+    char* peer[kP2pMaxWorld] = {nullptr};     // base of every rank's allocation as mapped here
+};
+static P2p g_p2p;
+
+template <class T> XTB_DEV T p2p_op(int op, T a, T b) {
+    switch (op) {
+        case XTB_RED_SUM: return (T) (a + b);
+        case XTB_RED_PROD: return (T) (a * b);
+        case XTB_RED_MAX: return a > b ? a : b;          // math::maximum: (a > b) ? a : b
+        default: return a < b ? a : b;
+    }
+}
+template <class T> XTB_DEV T ld_sys(const T* p) {
+    if constexpr (sizeof(T) == 4) {
+        uint32_t v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        T r;
+        memcpy(&r, &v, 4);
+        return r;
+    } else {
+        unsigned long long v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        T r;
+        memcpy(&r, &v, 8);
+        return r;
+    }
+}
+
+// One CTA: the payload is small and a single block keeps the hand-shake to __syncthreads.
+template <class T>
+__global__ void __launch_bounds__(1024) k_allreduce_p2p(const __grid_constant__ P2pParams w, T* buf, uint32_t count, int op) {
+    __shared__ uint32_t s_epoch;
+    const int tid = threadIdx.x;
+    char* mywin = w.win[w.rank];
+    if (tid == 0) {
+        uint32_t* ctr = (uint32_t*) (mywin + 2048);
+        s_epoch = *ctr + 1;
+        *ctr = s_epoch;
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch, slot = epoch & 1u;
+    // 1. my partial into my window
+    T* mine = (T*) (mywin + kP2pHeader + slot * kP2pMaxBytes);
+    for (uint32_t i = tid; i < count; i += 1024) mine[i] = buf[i];
+    __threadfence_system();
+    __syncthreads();
+    // 2. raise my flag in every rank's window, 3. wait for every rank's flag in mine
+    if (tid < w.world) {
+        uint32_t* theirs = (uint32_t*) w.win[tid] + slot * 16 + w.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+        const uint32_t* f = (const uint32_t*) mywin + slot * 16 + tid;
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while ((int32_t) (v - epoch) < 0);
+    }
+    __syncthreads();
+    // 4. add the partials in rank order, straight from the peers' windows
+    for (uint32_t i = tid; i < count; i += 1024) {
+        T acc = ld_sys<T>((const T*) (w.win[0] + kP2pHeader + slot * kP2pMaxBytes) + i);
+        for (int r = 1; r < w.world; ++r) acc = p2p_op<T>(op, acc, ld_sys<T>((const T*) (w.win[r] + kP2pHeader + slot * kP2pMaxBytes) + i));
+        buf[i] = acc;
+    }
+}
+
+template <class T> static int launch_p2p(DeviceCtx* ctx, void* buf, size_t count, int op) {
+    P2pParams w;
+    memset(&w, 0, sizeof(w));
+    w.rank = g_nccl.rank;
+    w.world = g_nccl.world;
+    const size_t woff = ctx->forked ? kP2pWindow : 0;
+    for (int r = 0; r < w.world; ++r) w.win[r] = g_p2p.peer[r] + woff;
+    k_allreduce_p2p<T><<<1, 1024, 0, ctx->stream>>>(w, (T*) buf, (uint32_t) count, op);
+    note_launch("k_allreduce_p2p");
+    return check_launch("k_allreduce_p2p");
+}
+
 int comm_allreduce(DeviceCtx* ctx, void* buf, size_t count, int dtype, int op) {
     if (g_nccl.world <= 1 && !g_nccl.comm) return XTB_OK;  // single rank: nothing to merge
     if (!g_nccl.comm) XTB_FAIL(XTB_ERR_NCCL, "xtb_comm_init has not been called");
     const int dt = nccl_dtype(dtype), ro = nccl_op(op);
     if (dt < 0 || ro < 0) XTB_FAIL(XTB_ERR_UNSUPPORTED, "allreduce of dtype %d / op %d", dtype, op);
     if (count == 0) return XTB_OK;
+    if (g_p2p.ready && count * (size_t) dtype_size(dtype) <= kP2pMaxBytes && dtype >= XTB_I32) {
+        switch (dtype) {
+            case XTB_I32: return launch_p2p<int32_t>(ctx, buf, count, op);
+            case XTB_U32: return launch_p2p<uint32_t>(ctx, buf, count, op);
+            case XTB_I64: return launch_p2p<long long>(ctx, buf, count, op);
+            case XTB_U64: return launch_p2p<unsigned long long>(ctx, buf, count, op);
+            case XTB_F32: return launch_p2p<float>(ctx, buf, count, op);
+            default: return launch_p2p<double>(ctx, buf, count, op);
+        }
+    }
     XTB_NCCL(g_nccl.all_reduce(buf, buf, count, dt, ro, g_nccl.comm, ctx->stream));
     note_launch("ncclAllReduce");
     return XTB_OK;
@@ -130,7 +238,49 @@ int xtb_comm_init(int rank, int world, const void* id128) {
     return XTB_OK;
 }
 
+int xtb_comm_p2p_handle(void* handle64) {
+    if (!handle64) XTB_FAIL(XTB_ERR_INVALID, "null handle");
+    DeviceCtx* ctx;
+    XTB_TRY(get_ctx(&ctx));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!g_p2p.local) {
+        XTB_CUDA(cudaMalloc((void**) &g_p2p.local, kP2pWindows * kP2pWindow));
+        XTB_CUDA(cudaMemset(g_p2p.local, 0, kP2pWindows * kP2pWindow));
+    }
+    cudaIpcMemHandle_t h;
+    XTB_CUDA(cudaIpcGetMemHandle(&h, g_p2p.local));
+    memcpy(handle64, &h, sizeof(h));
+    return XTB_OK;
+}
+
+int xtb_comm_p2p_attach(const void* handles, int world) {
+    if (!handles) XTB_FAIL(XTB_ERR_INVALID, "null handles");
+    if (world != g_nccl.world || world > kP2pMaxWorld || !g_p2p.local) XTB_FAIL(XTB_ERR_INVALID, "xtb_comm_p2p_attach: call xtb_comm_init and xtb_comm_p2p_handle first (world <= %d)", kP2pMaxWorld);
+    DeviceCtx* ctx;
+    XTB_TRY(get_ctx(&ctx));
+    for (int r = 0; r < world; ++r) {
+        if (r == g_nccl.rank) {
+            g_p2p.peer[r] = g_p2p.local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*) handles + (size_t) r * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        XTB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        g_p2p.peer[r] = (char*) ptr;
+    }
+    g_p2p.ready = true;
+    return XTB_OK;
+}
+
 int xtb_comm_destroy(void) {
+    if (g_p2p.local) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < g_nccl.world; ++r)
+            if (g_p2p.ready && r != g_nccl.rank && g_p2p.peer[r]) cudaIpcCloseMemHandle(g_p2p.peer[r]);
+        cudaFree(g_p2p.local);
+        g_p2p = P2p();
+    }
     if (g_nccl.comm) {
         XTB_NCCL(g_nccl.comm_destroy(g_nccl.comm));
         g_nccl.comm = nullptr;

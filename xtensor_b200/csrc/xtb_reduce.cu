@@ -114,42 +114,23 @@ struct ReducePlanIn {
 
 static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth);
 
-// second pass over partials[K][nsplit]: an inner (contiguous) reduction per output
+// second pass over partials[nsplit][K]
 static int merge_partials(const ReducePlanIn& first, const RdParams& fp, DeviceCtx* ctx, int depth) {
-    ReducePlanIn in;
-    memset(&in.own_prog, 0, sizeof(in.own_prog));
-    in.own_prog.n_insns = 1;
-    in.own_prog.n_leaves = 1;
-    in.own_prog.insns[0] = xtb_insn{XTB_OP_PUSH, (uint8_t) first.acc_rt, XTB_SRC_LEAF, 0};  // PUSH leaf0
-    in.prog = &in.own_prog;
-    in.n_leaves = 1;
-    in.leaf_ptr[0] = fp.part_ptr;
-    in.leaf_dtype[0] = first.acc_rt;
-    Space& s = in.space;
-    s = Space();
-    s.ndim = fp.nk + 1;
-    s.n_ops = 2;
-    int64_t st = fp.nsplit;
-    for (int d = fp.nk - 1; d >= 0; --d) {
-        s.shape[d] = fp.kshape[d];
-        s.reduced[d] = false;
-        s.stride[0][d] = st;
-        s.stride[1][d] = fp.out_kstride[d];
-        st *= fp.kshape[d];
+    (void) depth;
+    if (fp.K >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "too many outputs");
+    // the reported kernel stays the first pass (the one that moves the data), with the merge appended
+    char name[128];
+    snprintf(name, sizeof(name), "%.100s + %s", xtb_last_kernel(), fp.K < 128 ? "k_reduce_merge_few" : "k_reduce_merge");
+    if (fp.K < 128) {
+        if (first.w64) k_reduce_merge_few<uint64_t><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
+        else k_reduce_merge_few<uint32_t><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
+    } else {
+        const unsigned grid = (unsigned) ((fp.K + 127) / 128);
+        if (first.w64) k_reduce_merge<uint64_t><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp);
+        else k_reduce_merge<uint32_t><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp);
     }
-    s.shape[fp.nk] = fp.nsplit;
-    s.reduced[fp.nk] = true;
-    s.stride[0][fp.nk] = 1;
-    s.stride[1][fp.nk] = 0;
-    in.binop = first.binop;
-    in.acc_rt = in.in_rt = first.acc_rt;
-    in.w64 = first.w64;
-    in.out_ptr = first.out_ptr;
-    in.out_dtype = first.out_dtype;
-    in.has_initial = first.has_initial;
-    in.initial_bits = first.initial_bits;
-    in.identity = first.identity;
-    return plan_and_launch(in, ctx, depth + 1);
+    note_launch(name);
+    return check_launch("k_reduce_merge");
 }
 
 static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {

@@ -41,7 +41,7 @@ struct RdParams {
     int64_t out_kstride[XTB_MAX_DIM];
     int32_t out_dtype;
     int32_t out_vec_ok;     // outer kernel: V results can be stored with one vector store
-    int32_t nsplit;         // >1: write acc-typed partials to part_ptr[ko * nsplit + split]
+    int32_t nsplit;         // >1: write acc-typed partials to part_ptr[split * K + ko]
     int32_t has_initial;
     char* part_ptr;
     int64_t chunk;          // reduced positions (outer) / r-vectors (inner) per split
@@ -137,6 +137,97 @@ template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S 
         exec_binary<S, 1, false>(p.binop, p.acc_rt, a, b);
     }
     store_elem<S>(dst, p.out_dtype, p.acc_rt, a[0]);
+}
+
+// Second pass of a split reduction: out[k] = partials[0][k] (+) partials[1][k] (+) ... over part[nsplit][K].
+// A block owns 128 outputs (4 per lane, 128-bit loads); warp w of its 16 warps adds splits w, w+16, ...,
+// eight loads in flight per lane, then the warps are combined in order through shared memory: a fixed
+// order and a couple of memory round trips, however few outputs there are (the case that needs
+// splitting at all).
+constexpr int kMergeWarps = 16;
+template <class S>
+__global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_constant__ RdParams p) {
+    __shared__ S sm[kMergeWarps][128];
+    constexpr int U = 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t k0 = ((int64_t) blockIdx.x * 32 + lane) * 4;
+    const int asz = dtype_size(p.acc_rt);
+    S acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = (S) p.identity_bits;
+    if (k0 < p.K) {
+        const bool vec = p.K % 4 == 0;
+        for (int s0 = warp; s0 < p.nsplit; s0 += kMergeWarps * U) {
+            S x[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int sp = s0 + kMergeWarps * u;
+                const char* src = p.part_ptr + ((int64_t) sp * p.K + k0) * asz;
+                if (sp < p.nsplit && vec) {
+                    load_vec<S, 4>(src, p.acc_rt, x[u]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[u][i] = (sp < p.nsplit && k0 + i < p.K) ? load_elem<S>(src + i * asz, p.acc_rt) : (S) p.identity_bits;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (s0 + kMergeWarps * u < p.nsplit) DynAcc::template step<S, 4>(p, acc, x[u]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sm[warp][lane * 4 + i] = acc[i];
+    __syncthreads();
+    // warp 0..3 finish one of the lane's four outputs each (coalesced stores along k)
+    if (warp < 4) {
+        const int64_t k = (int64_t) blockIdx.x * 128 + warp * 32 + lane;
+        if (k < p.K) {
+            const int c = warp * 32 + lane;
+            S r[1] = {sm[0][c]};
+            for (int w = 1; w < kMergeWarps; ++w) {
+                S y[1] = {sm[w][c]};
+                DynAcc::template step<S, 1>(p, r, y);
+            }
+            const int64_t off = rd_kept_offset(p, (uint32_t) k, p.out_kstride);
+            rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), r[0]);
+        }
+    }
+}
+
+// Few outputs (full reductions, K < 128): one block per output, thread t adds splits t, t+256, ...,
+// then a fixed-shape tree over the block.
+template <class S>
+__global__ void __launch_bounds__(256) k_reduce_merge_few(const __grid_constant__ RdParams p) {
+    __shared__ S sm[256];
+    const int t = threadIdx.x;
+    const int64_t k = blockIdx.x;
+    const int asz = dtype_size(p.acc_rt);
+    S acc[1] = {(S) p.identity_bits};
+    for (int s0 = t; s0 < p.nsplit; s0 += 256 * 4) {
+        S x[4][1];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int sp = s0 + 256 * u;
+            x[u][0] = sp < p.nsplit ? load_elem<S>(p.part_ptr + ((int64_t) sp * p.K + k) * asz, p.acc_rt) : (S) p.identity_bits;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (s0 + 256 * u < p.nsplit) DynAcc::template step<S, 1>(p, acc, x[u]);
+    }
+    sm[t] = acc[0];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) {
+            S a[1] = {sm[t]}, b[1] = {sm[t + o]};
+            DynAcc::template step<S, 1>(p, a, b);
+            sm[t] = a[0];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        const int64_t off = rd_kept_offset(p, (uint32_t) k, p.out_kstride);
+        rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), sm[0]);
+    }
 }
 
 // Stage U vectors of leaf K (and recursively of the following leaves) of a compile-time
@@ -370,7 +461,7 @@ __global__ void __launch_bounds__(256) k_reduce_inner_warp(const __grid_constant
         const int64_t ko = out_base + lane;
         if (ko < p.K) {
             if (p.nsplit > 1) {
-                store_elem<S>(p.part_ptr + (ko * p.nsplit + blockIdx.y) * dtype_size(p.acc_rt), p.acc_rt, p.acc_rt, keep);
+                store_elem<S>(p.part_ptr + ((int64_t) blockIdx.y * p.K + ko) * dtype_size(p.acc_rt), p.acc_rt, p.acc_rt, keep);
             } else {
                 const int64_t off = rd_kept_offset(p, (uint32_t) ko, p.out_kstride);
                 rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), keep);
@@ -466,7 +557,7 @@ __global__ void __launch_bounds__(256) k_reduce_inner_block(const __grid_constan
             }
             if (tid == 0) {
                 if (p.nsplit > 1) {
-                    store_elem<S>(p.part_ptr + (ko * p.nsplit + blockIdx.y) * dtype_size(p.acc_rt), p.acc_rt, p.acc_rt, r[0]);
+                    store_elem<S>(p.part_ptr + ((int64_t) blockIdx.y * p.K + ko) * dtype_size(p.acc_rt), p.acc_rt, p.acc_rt, r[0]);
                 } else {
                     const int64_t off = rd_kept_offset(p, (uint32_t) ko, p.out_kstride);
                     rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), r[0]);
@@ -558,12 +649,12 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
             }
         }
         if (p.nsplit > 1) {
-            // partials[K][nsplit]: the merge pass reads each output's partials contiguously
+            // partials[nsplit][K]: k_reduce_merge streams them with coalesced 128-bit loads
             const int asz = dtype_size(p.acc_rt);
-            char* dst = p.part_ptr + ((int64_t) ko0 * p.nsplit + blockIdx.y) * asz;
+            char* dst = p.part_ptr + ((int64_t) blockIdx.y * p.K + ko0) * asz;
 #pragma unroll
             for (int v = 0; v < V; ++v)
-                if (v < f.nvalid) store_elem<S>(dst + (int64_t) v * p.nsplit * asz, p.acc_rt, p.acc_rt, acc[v]);
+                if (v < f.nvalid) store_elem<S>(dst + (int64_t) v * asz, p.acc_rt, p.acc_rt, acc[v]);
         } else {
             const int osz = dtype_size(p.out_dtype);
             char* dst = p.out_ptr + rd_kept_offset(p, ko0, p.out_kstride) * osz;

@@ -37,6 +37,35 @@ def shard_operand(a: xt.Array, out_rows: int, rank: int, world: int) -> xt.Array
     return a[b:e]
 
 
+def init_comm(dist, rank: int, world: int, p2p: Optional[bool] = None) -> bool:
+    """Bring up the device-side exchange for an initialised torch.distributed group `dist` (used for
+    the rendezvous only): NCCL communicator through the C ABI, then -- unless `p2p` is False or
+    XTB_NO_P2P is set -- the NVLink peer-memory windows that serve small allreduces (the (cols,)
+    partials of an axis-0 reduction) with one kernel instead of an NCCL call.  Returns whether the
+    peer-memory path is attached."""
+    import ctypes as C
+    import os
+    lib = capi.lib()
+    ident = [None]
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        capi.check(lib.xtb_comm_unique_id(buf))
+        ident[0] = buf.raw
+    dist.broadcast_object_list(ident, src=0)
+    capi.check(lib.xtb_comm_init(rank, world, C.create_string_buffer(ident[0], 128)))
+    if p2p is None:
+        p2p = os.environ.get("XTB_NO_P2P") is None
+    if not p2p or world > 8:
+        return False
+    h = C.create_string_buffer(64)
+    capi.check(lib.xtb_comm_p2p_handle(h))
+    handles = [None] * world
+    dist.all_gather_object(handles, h.raw)
+    capi.check(lib.xtb_comm_p2p_attach(C.create_string_buffer(b"".join(handles), 64 * world), world))
+    dist.barrier()      # every rank attached before anyone's next allreduce
+    return True
+
+
 HostAllreduce = Callable[[np.ndarray, int], np.ndarray]
 
 
