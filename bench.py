@@ -233,7 +233,7 @@ def run_ours(args):
     # end to end through the C ABI with HOST buffers: xtb_assign_host streams the pinned host
     # operands through the device (H2D | kernel | D2H pipelined over chunks of the leading axis)
     # and returns when the host result is complete.  Nothing is resident on the device beforehand.
-    e2e_steps = max(1, min(args.steps, 10))
+    e2e_steps = max(1, min(args.steps, 10)) if not args.quick else 1
     hp = []
     for x in (a, b, d, np.empty(shape, np.float32)):
         p = C.c_void_p()
@@ -315,7 +315,7 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
                 "kernel": lib.xtb_last_kernel().decode()}
 
     try:
-        if world == 1:
+        if world == 1 and not args.quick:
             rng = np.random.default_rng(1)
             # cfg1: fp64 1-D 2^24 a + b
             n = 1 << 24
@@ -338,7 +338,7 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
             e = xt.transpose(a) + xt.view(b, slice(0, None, 2), slice(None))
             out["cfg4_transpose_view_f64"] = timed(lambda: xt.assign(o, e), 3 * 8192 * 8192 * 8, iters=5)
             del a, b, o, e
-        if world == 1:
+        if world == 1 and not args.quick:
             # cumsum (north_star: xaccumulator as a decoupled look-back scan); 2 x element size per element
             x = xt.DeviceArray.from_numpy(np.random.default_rng(2).uniform(-1, 1, 1 << 26).astype(np.float32))
             y = xt.DeviceArray.empty((1 << 26,), xt.F32)
@@ -356,7 +356,7 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
             out["jit_hypot_div_f32_2^26"] = timed(lambda: xt.assign(o3, e3), 16 * n)
             del a3, o3, e3
         # cfg5: sharded (262144, 8192) fp32: mean / variance over axis 0 (allreduce) + exp(a - mean)
-        rows = 262144 // world
+        rows = args.cfg5_rows or 262144 // world
         cols = 8192
         blk = np.random.default_rng(9 + rank).uniform(-1, 1, (4096, cols)).astype(np.float32)
         a = xt.DeviceArray.empty((rows, cols), xt.F32)
@@ -456,6 +456,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="development: one e2e step, only the cfg5 side measurement")
+    ap.add_argument("--cfg5-rows", type=int, default=0, help="development: rows per GPU of the cfg5 pipeline (default 262144 / gpus)")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of cfg1/3/4/5")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -88,6 +88,21 @@ def main():
     if not np.allclose(v, v_ref, rtol=1e-6, atol=0):
         fails.append("sharded variance")
 
+    # split reductions over the sharded axis: local merge + cross-GPU merge in one kernel
+    fused_kernel = None
+    for npdt in (np.float32, np.float64, np.int32, np.int64):
+        for name, fn in (("sum", np.sum), ("amax", np.max), ("amin", np.min)):
+            for cols_ in (1000, 8192, 131):
+                rows_ = 256 * world + 5
+                fl = np.random.default_rng(cols_).integers(-8, 9, (rows_, cols_)).astype(npdt)
+                b_, e_ = shard.row_block(rows_, rank, world)
+                got = xt._run_reducer(getattr(xt, name)(xt.DeviceArray.from_numpy(fl[b_:e_]), [0]), xt.DeviceArray, allreduce=True)
+                if npdt is np.float32 and name == "sum" and cols_ == 8192:
+                    fused_kernel = lib.xtb_last_kernel().decode()
+                checks += 1
+                if not np.array_equal(got.numpy().astype(np.float64), fn(fl, axis=0).astype(np.float64)):
+                    fails.append(f"sharded {name} {npdt.__name__} cols {cols_}")
+
     s_sum, mean_, s_sq, var_ = (xt.DeviceArray.empty((cols,), xt.F32) for _ in range(4))
     o = xt.DeviceArray.empty((e - b, cols), xt.F32)
     n_rows = np.float32(rows)
@@ -135,7 +150,8 @@ def main():
         print(f"rank {rank} FAILED: {fails}", flush=True)
     if rank == 0:
         print(json.dumps({"dist_check": "ok" if int(nf.item()) == 0 else "FAILED", "world": world, "checks_per_rank": checks,
-                          "peer_memory_allreduce": p2p, "small_allreduce_kernel": kernel_small}), flush=True)
+                          "peer_memory_allreduce": p2p, "small_allreduce_kernel": kernel_small,
+                          "split_reduce_kernel": fused_kernel}), flush=True)
     dist.barrier()
     lib.xtb_comm_destroy()
     dist.destroy_process_group()

@@ -8,12 +8,14 @@
 //
 // Small payloads (the (8192,) partials of cfg5 are 32 KB) are latency-bound in NCCL; for them
 // k_allreduce_p2p does the exchange itself over NVLink peer memory: every rank owns a window
-// (cudaMalloc + CUDA IPC, mapped into all ranks), drops its partial into it, raises a flag in every
-// peer's window, waits for the peers' flags in its own, and then adds the R partials straight out of
-// the peers' memory in rank order -- one kernel, one NVLink round trip, bit-identical on all ranks.
+// (cudaMalloc + CUDA IPC, mapped into all ranks); a rank pushes its partial, word by word with the
+// call's epoch packed next to each word, into every peer's window and then combines what the peers
+// pushed into its own window in rank order -- one kernel, one one-way NVLink trip, no fences, and
+// bit-identical results on all ranks.
 #include <dlfcn.h>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
+#include "xtb_p2p.cuh"
 
 namespace xtb {
 
@@ -91,17 +93,7 @@ static int nccl_op(int op) {
 }
 
 
-// ---- peer-memory allreduce -------------------------------------------------------------------------
-constexpr size_t kP2pMaxBytes = 256 * 1024;
-constexpr int kP2pMaxWorld = 8;
-constexpr size_t kP2pHeader = 4096;                           // flags[2][16] at 0, launch counter at 2048
-constexpr size_t kP2pWindow = kP2pHeader + 2 * kP2pMaxBytes;  // two payload slots (epoch parity)
-constexpr int kP2pWindows = 2;                                // [1] serves calls made inside xtb_fork_begin/end
-
-struct P2pParams {
-    char* win[kP2pMaxWorld];
-    int32_t rank, world;
-};
+// ---- peer-memory allreduce (protocol: xtb_p2p.cuh) ---------------------------------------------------
 struct P2p {
     bool ready = false;
     char* local = nullptr;                    // kP2pWindows windows
@@ -117,67 +109,48 @@ template <class T> XTB_DEV T p2p_op(int op, T a, T b) {
         default: return a < b ? a : b;
     }
 }
-template <class T> XTB_DEV T ld_sys(const T* p) {
-    if constexpr (sizeof(T) == 4) {
-        uint32_t v;
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-        T r;
-        memcpy(&r, &v, 4);
-        return r;
-    } else {
-        unsigned long long v;
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-        T r;
-        memcpy(&r, &v, 8);
-        return r;
-    }
-}
 
-// One CTA: the payload is small and a single block keeps the hand-shake to __syncthreads.
+// thread i owns element i
 template <class T>
-__global__ void __launch_bounds__(1024) k_allreduce_p2p(const __grid_constant__ P2pParams w, T* buf, uint32_t count, int op) {
-    __shared__ uint32_t s_epoch;
-    const int tid = threadIdx.x;
-    char* mywin = w.win[w.rank];
-    if (tid == 0) {
-        uint32_t* ctr = (uint32_t*) (mywin + 2048);
-        s_epoch = *ctr + 1;
-        *ctr = s_epoch;
-    }
-    __syncthreads();
-    const uint32_t epoch = s_epoch, slot = epoch & 1u;
-    // 1. my partial into my window
-    T* mine = (T*) (mywin + kP2pHeader + slot * kP2pMaxBytes);
-    for (uint32_t i = tid; i < count; i += 1024) mine[i] = buf[i];
-    __threadfence_system();
-    __syncthreads();
-    // 2. raise my flag in every rank's window, 3. wait for every rank's flag in mine
-    if (tid < w.world) {
-        uint32_t* theirs = (uint32_t*) w.win[tid] + slot * 16 + w.rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
-        const uint32_t* f = (const uint32_t*) mywin + slot * 16 + tid;
-        uint32_t v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        } while ((int32_t) (v - epoch) < 0);
-    }
-    __syncthreads();
-    // 4. add the partials in rank order, straight from the peers' windows
-    for (uint32_t i = tid; i < count; i += 1024) {
-        T acc = ld_sys<T>((const T*) (w.win[0] + kP2pHeader + slot * kP2pMaxBytes) + i);
-        for (int r = 1; r < w.world; ++r) acc = p2p_op<T>(op, acc, ld_sys<T>((const T*) (w.win[r] + kP2pHeader + slot * kP2pMaxBytes) + i));
+__global__ void __launch_bounds__(256) k_allreduce_p2p(const __grid_constant__ P2pParams w, T* buf, uint32_t count, int op) {
+    constexpr int W = sizeof(T) / 4;
+    const uint32_t epoch = p2p_epoch(w);
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < count) {
+        const T mine = buf[i];
+        uint32_t mw[W], got[kP2pMaxWorld][W];
+        memcpy(mw, &mine, sizeof(T));
+        p2p_exchange<W>(w, epoch, (size_t) i * W, mw, got);
+        T acc = mine;
+#pragma unroll
+        for (int r = 0; r < kP2pMaxWorld; ++r) {
+            if (r < w.world) {
+                T v = mine;
+                if (r != w.rank) memcpy(&v, got[r], sizeof(T));
+                acc = r == 0 ? v : p2p_op<T>(op, acc, v);
+            }
+        }
         buf[i] = acc;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) p2p_finish(w, epoch);
+}
+
+// the windows an exchange issued now (on ctx's current stream) uses; false when peer memory is not attached
+bool comm_p2p_params(DeviceCtx* ctx, P2pParams* w) {
+    if (!g_p2p.ready) return false;
+    memset(w, 0, sizeof(*w));
+    w->rank = g_nccl.rank;
+    w->world = g_nccl.world;
+    const size_t woff = ctx->forked ? kP2pWindow : 0;
+    for (int r = 0; r < w->world; ++r) w->win[r] = g_p2p.peer[r] + woff;
+    return true;
 }
 
 template <class T> static int launch_p2p(DeviceCtx* ctx, void* buf, size_t count, int op) {
     P2pParams w;
-    memset(&w, 0, sizeof(w));
-    w.rank = g_nccl.rank;
-    w.world = g_nccl.world;
-    const size_t woff = ctx->forked ? kP2pWindow : 0;
-    for (int r = 0; r < w.world; ++r) w.win[r] = g_p2p.peer[r] + woff;
-    k_allreduce_p2p<T><<<1, 1024, 0, ctx->stream>>>(w, (T*) buf, (uint32_t) count, op);
+    comm_p2p_params(ctx, &w);
+    k_allreduce_p2p<T><<<(unsigned) ((count + 255) / 256), 256, 0, ctx->stream>>>(w, (T*) buf, (uint32_t) count, op);
     note_launch("k_allreduce_p2p");
     return check_launch("k_allreduce_p2p");
 }

@@ -13,6 +13,7 @@
 namespace xtb {
 
 int comm_allreduce(DeviceCtx* ctx, void* buf, size_t count, int dtype, int op);  // xtb_comm.cu
+bool comm_p2p_params(DeviceCtx* ctx, P2pParams* w);                               // xtb_comm.cu
 
 static uint64_t identity_bits(int op, int rt) {
     union { uint64_t u; double d; float f[2]; int32_t i32[2]; uint32_t u32[2]; int64_t i64; } v;
@@ -110,24 +111,38 @@ struct ReducePlanIn {
     int out_dtype;
     bool has_initial;
     uint64_t initial_bits, identity;
+    bool want_xchg = false;   // in: the caller asked for the cross-GPU merge of the result
+    bool xchg_done = false;   // out: the merge pass did it (k_reduce_merge<XCHG>); else the caller still has to
 };
 
 static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth);
 
 // second pass over partials[nsplit][K]
-static int merge_partials(const ReducePlanIn& first, const RdParams& fp, DeviceCtx* ctx, int depth) {
+static int merge_partials(ReducePlanIn& first, const RdParams& fp, DeviceCtx* ctx, int depth) {
     (void) depth;
     if (fp.K >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "too many outputs");
+    // fused local + cross-GPU merge: same values as xtb_allreduce on the stored result when the result is
+    // stored in the accumulator type and no initial value is folded in
+    P2pParams xw;
+    memset(&xw, 0, sizeof(xw));
+    const size_t words = (size_t) fp.K * (size_t) (dtype_size(first.acc_rt) / 4);
+    const bool xchg = first.want_xchg && fp.K >= 128 && !first.has_initial && first.out_dtype == first.acc_rt &&
+                      words <= kP2pMaxWords && comm_p2p_params(ctx, &xw) && xw.world > 1;
     // the reported kernel stays the first pass (the one that moves the data), with the merge appended
     char name[128];
-    snprintf(name, sizeof(name), "%.100s + %s", xtb_last_kernel(), fp.K < 128 ? "k_reduce_merge_few" : "k_reduce_merge");
-    if (fp.K < 128) {
+    snprintf(name, sizeof(name), "%.90s + %s", xtb_last_kernel(), fp.K < 128 ? "k_reduce_merge_few" : xchg ? "k_reduce_merge[+p2p exchange]" : "k_reduce_merge");
+    if (xchg) {
+        const unsigned grid = (unsigned) ((fp.K + 127) / 128);
+        if (first.w64) k_reduce_merge<uint64_t, true><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+        else k_reduce_merge<uint32_t, true><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+        first.xchg_done = true;
+    } else if (fp.K < 128) {
         if (first.w64) k_reduce_merge_few<uint64_t><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
         else k_reduce_merge_few<uint32_t><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
     } else {
         const unsigned grid = (unsigned) ((fp.K + 127) / 128);
-        if (first.w64) k_reduce_merge<uint64_t><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp);
-        else k_reduce_merge<uint32_t><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp);
+        if (first.w64) k_reduce_merge<uint64_t, false><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+        else k_reduce_merge<uint32_t, false><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
     }
     note_launch(name);
     return check_launch("k_reduce_merge");
@@ -384,8 +399,9 @@ extern "C" int xtb_reduce(int op, int acc_type, const xtb_program* prog, const x
             if (red[d]) s.shape[d] = 1;
         in.empty = true;
     }
+    in.want_xchg = allreduce != 0;
     XTB_TRY(plan_and_launch(in, ctx, 0));
-    if (allreduce) {
+    if (allreduce && !in.xchg_done) {
         // out must be dense for the in-place collective
         XTB_TRY(comm_allreduce(ctx, in.out_ptr, (size_t) K, out->dtype, op));
     }

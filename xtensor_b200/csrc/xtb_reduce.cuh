@@ -14,6 +14,7 @@
 // Any expression can be fused in front of the reduction (xreducer over xfunction).
 #pragma once
 #include "xtb_ew.cuh"
+#include "xtb_p2p.cuh"
 
 namespace xtb {
 
@@ -144,10 +145,17 @@ template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S 
 // eight loads in flight per lane, then the warps are combined in order through shared memory: a fixed
 // order and a couple of memory round trips, however few outputs there are (the case that needs
 // splitting at all).
+//
+// XCHG: the reduction runs over the axis that is sharded across GPUs, so the merged value is only this
+// rank's partial.  The thread that finishes output k then exchanges it with the other ranks over NVLink
+// peer memory (xtb_p2p.cuh) and combines the R partials in rank order before the one store: the local
+// merge and the cross-GPU merge are one kernel, and the partial never travels through HBM in between.
 constexpr int kMergeWarps = 16;
-template <class S>
-__global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_constant__ RdParams p) {
+template <class S, bool XCHG>
+__global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_constant__ RdParams p, const __grid_constant__ P2pParams xw) {
     __shared__ S sm[kMergeWarps][128];
+    uint32_t epoch = 0;
+    if constexpr (XCHG) epoch = p2p_epoch(xw);
     constexpr int U = 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t k0 = ((int64_t) blockIdx.x * 32 + lane) * 4;
@@ -188,9 +196,42 @@ __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_
                 S y[1] = {sm[w][c]};
                 DynAcc::template step<S, 1>(p, r, y);
             }
+            if constexpr (XCHG) {
+                // same word layout as k_allreduce_p2p on the accumulator type (a 32-bit value sits in the low half of a 64-bit slot)
+                const S mine = r[0];
+                S theirs[kP2pMaxWorld];
+                bool wide = false;
+                if constexpr (sizeof(S) == 8) wide = dtype_size(p.acc_rt) == 8;
+                if (wide) {
+                    if constexpr (sizeof(S) == 8) {
+                        uint32_t mw[2], got[kP2pMaxWorld][2];
+                        memcpy(mw, &mine, 8);
+                        p2p_exchange<2>(xw, epoch, (size_t) k * 2, mw, got);
+#pragma unroll
+                        for (int q = 0; q < kP2pMaxWorld; ++q) memcpy(&theirs[q], got[q], 8);
+                    }
+                } else {
+                    uint32_t mw[1] = {(uint32_t) mine}, got[kP2pMaxWorld][1];
+                    p2p_exchange<1>(xw, epoch, (size_t) k, mw, got);
+#pragma unroll
+                    for (int q = 0; q < kP2pMaxWorld; ++q) theirs[q] = (S) got[q][0];
+                }
+#pragma unroll
+                for (int q = 0; q < kP2pMaxWorld; ++q) {
+                    if (q < xw.world) {
+                        S y[1] = {q == xw.rank ? mine : theirs[q]};
+                        if (q == 0) r[0] = y[0];
+                        else DynAcc::template step<S, 1>(p, r, y);
+                    }
+                }
+            }
             const int64_t off = rd_kept_offset(p, (uint32_t) k, p.out_kstride);
             rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), r[0]);
         }
+    }
+    if constexpr (XCHG) {
+        __syncthreads();
+        if (threadIdx.x == 0) p2p_finish(xw, epoch);
     }
 }
 

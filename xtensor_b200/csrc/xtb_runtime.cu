@@ -418,7 +418,11 @@ int xtb_fork_begin(void) {
     XTB_TRY(get_ctx(&c));
     if (c->forked) XTB_FAIL(XTB_ERR_INVALID, "xtb_fork_begin: already forked");
     if (!c->fork_stream) {
-        XTB_CUDA(cudaStreamCreateWithFlags(&c->fork_stream, cudaStreamNonBlocking));
+        // highest priority: the forked section is the short side chain (reduce, merge, exchange, finalize);
+        // its blocks are placed ahead of the main sequence's bulk kernel so that the exchange overlaps it
+        int prio_lo = 0, prio_hi = 0;
+        XTB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        XTB_CUDA(cudaStreamCreateWithPriority(&c->fork_stream, cudaStreamNonBlocking, prio_hi));
         XTB_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
         XTB_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
     }
