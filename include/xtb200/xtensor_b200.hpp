@@ -923,6 +923,56 @@ namespace xtb
             static constexpr int value = XTB_RED_MIN;
         };
 
+        // nan_plus / nan_multiplies ("!isnan(rhs) ? lhs (+|*) rhs : lhs", core/xmath.hpp:2365-2381) are the
+        // plain merges over the operand with its NaNs replaced by the merge's identity; the replacement
+        // is fused into the reduction kernel's map program (no temporary)
+        template <>
+        struct reduce_op_of<xt::detail::nan_plus>
+        {
+            static constexpr int value = XTB_RED_SUM;
+        };
+
+        template <>
+        struct reduce_op_of<xt::detail::nan_multiplies>
+        {
+            static constexpr int value = XTB_RED_PROD;
+        };
+
+        template <class F>
+        struct nan_fill_of
+        {
+            static constexpr int value = -1;   // not a nan-skipping merge
+        };
+
+        template <>
+        struct nan_fill_of<xt::detail::nan_plus>
+        {
+            static constexpr int value = 0;
+        };
+
+        template <>
+        struct nan_fill_of<xt::detail::nan_multiplies>
+        {
+            static constexpr int value = 1;
+        };
+
+        // program + leaves of a reducer's operand, NaNs replaced when the merge skips them
+        template <class F, class E>
+        inline void emit_reducer_operand(context& c, const E& e)
+        {
+            constexpr int fill = nan_fill_of<F>::value;
+            using vt = typename std::decay_t<E>::value_type;
+            if constexpr (fill >= 0 && std::is_floating_point<vt>::value)
+            {
+                auto mapped = xt::where(xt::isnan(e), vt(fill), e);
+                emit_value(c, mapped, -1);
+            }
+            else
+            {
+                emit_value(c, e, -1);
+            }
+        }
+
         template <class R>
         struct reducer_traits;
 
@@ -965,10 +1015,10 @@ namespace xtb
         {
             using functors = typename R::reduce_functor_type;
             constexpr int op = reduce_op_of<std::decay_t<functors>>::value;
-            static_assert(op >= 0, "xtb200: only sum / prod / amax / amin reducers can be lowered");
+            static_assert(op >= 0, "xtb200: only sum / prod / amax / amin (and nansum / nanprod) reducers can be lowered");
             using acc_t = typename R::value_type;
             context c;
-            emit_value(c, r.expression(), -1);
+            emit_reducer_operand<std::decay_t<functors>>(c, r.expression());
             const auto& sh = r.expression().shape();
             std::int64_t shape[XTB_MAX_DIM] = {0};
             int nd = 0;
@@ -1060,7 +1110,7 @@ namespace xt
         using options_t = reducer_options<result_type, std::decay_t<O>>;
         options_t options(raw_options);
         constexpr int op = xtb::lower::reduce_op_of<reduce_functor_type>::value;
-        static_assert(op >= 0, "xtb200: only sum / prod / amax / amin reducers can be lowered");
+        static_assert(op >= 0, "xtb200: only sum / prod / amax / amin (and nansum / nanprod) reducers can be lowered");
         (void) f;
 
         const std::size_t nd = e.dimension();
@@ -1092,7 +1142,7 @@ namespace xt
         xtb::xarray<result_type> result;
         result.resize(out_shape);
         xtb::lower::context c;
-        xtb::lower::emit_value(c, e, -1);
+        xtb::lower::emit_reducer_operand<reduce_functor_type>(c, e);
         std::int64_t shape[XTB_MAX_DIM] = {0};
         for (std::size_t d = 0; d < nd; ++d)
         {

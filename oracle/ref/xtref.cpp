@@ -261,6 +261,69 @@ extern "C"
         return (int) r.size();
     }
 
+    // ---- nan-aware reducers, counts, nan_to_num (core/xmath.hpp:2307-2860) -------------------------
+    // name: nansum nanprod nanmin nanmax (result T) | nanmean nanvar nanstd (result double; "<name>_t": result T)
+    //       | count_nonzero count_nonnan (result uint64)
+    extern "C++"
+    {
+        template <class T> int nanfn_impl(const std::string& name, const void* in, int nd, const int64_t* shape, int n_axes,
+                                          const int32_t* axes, void* out)
+        {
+            try
+            {
+                auto A = in_arr<T>(in, mk_shape(nd, shape));
+                std::vector<std::size_t> ax(axes, axes + n_axes);
+    #define XTREF_NAN(NAME, RT, CALL)                                       \
+                if (name == NAME)                                           \
+                {                                                           \
+                    xt::xarray<RT> r = CALL;                                \
+                    std::copy(r.begin(), r.end(), static_cast<RT*>(out));   \
+                    return (int) r.size();                                  \
+                }
+                XTREF_NAN("nansum", T, xt::nansum(A, ax))
+                XTREF_NAN("nanprod", T, xt::nanprod(A, ax))
+                XTREF_NAN("nanmin", T, xt::nanmin(A, ax))
+                XTREF_NAN("nanmax", T, xt::nanmax(A, ax))
+                XTREF_NAN("nanmean", double, xt::nanmean(A, ax))
+                XTREF_NAN("nanvar", double, xt::nanvar(A, ax))
+                XTREF_NAN("nanstd", double, xt::nanstd(A, ax))
+                XTREF_NAN("nanmean_t", T, xt::nanmean<T>(A, ax))
+                XTREF_NAN("nanvar_t", T, xt::nanvar<T>(A, ax))
+                XTREF_NAN("count_nonzero", uint64_t, xt::count_nonzero(A, ax))
+                XTREF_NAN("count_nonnan", uint64_t, xt::count_nonnan(A, ax))
+    #undef XTREF_NAN
+                g_err = "unknown function " + name;
+                return -2;
+            }
+            catch (std::exception& e) { g_err = e.what(); return -3; }
+        }
+    }
+    int xtref_nanfn(const char* name, int dtype, const void* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes, void* out)
+    {
+        switch (dtype)
+        {
+            case 9: return nanfn_impl<float>(name, in, nd, shape, n_axes, axes, out);
+            case 10: return nanfn_impl<double>(name, in, nd, shape, n_axes, axes, out);
+        }
+        g_err = "unsupported dtype";
+        return -1;
+    }
+    int xtref_count_nonzero_i32(const int32_t* in, int nd, const int64_t* shape, int n_axes, const int32_t* axes, uint64_t* out)
+    {
+        auto A = in_arr<int32_t>(in, mk_shape(nd, shape));
+        std::vector<std::size_t> ax(axes, axes + n_axes);
+        xt::xarray<uint64_t> r = xt::count_nonzero(A, ax);
+        std::copy(r.begin(), r.end(), out);
+        return (int) r.size();
+    }
+    int xtref_nan_to_num(int is_f64, const void* in, void* out, int64_t n)
+    {
+        shape_t s{(std::size_t) n};
+        if (is_f64) { auto A = in_arr<double>(in, s); auto O = out_arr<double>(out, s); xt::noalias(O) = xt::nan_to_num(A); }
+        else { auto A = in_arr<float>(in, s); auto O = out_arr<float>(out, s); xt::noalias(O) = xt::nan_to_num(A); }
+        return 0;
+    }
+
     // ---- accumulators --------------------------------------------------------------------------------
     extern "C++"
     {

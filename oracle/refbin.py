@@ -169,3 +169,38 @@ def run_cfg2(sample_rows: int):
     return {"gbs": nbytes / dt / 1e9, "seconds": dt, "cores": 1,
             "how": "real xtensor 0.27.1 headers (oracle/_ref/libxtref_fast.so: -O3 -march=x86-64-v3 -fopenmp "
                    "-DXTENSOR_USE_OPENMP, xtl stand-in, no xsimd); this expression runs xtensor's single-threaded stepper_assigner"}
+
+
+def nanfn(name, a, axes):
+    """xt::nansum / nanprod / nanmin / nanmax / nanmean / nanvar / nanstd / count_nonzero / count_nonnan over `axes`
+    ("nanmean_t" / "nanvar_t": result type = input type)."""
+    a = np.ascontiguousarray(a)
+    dt = {np.dtype(np.float32): 9, np.dtype(np.float64): 10}[a.dtype]
+    out_shape = tuple(s for d, s in enumerate(a.shape) if d not in axes)
+    if name.startswith("count"):
+        odt = np.uint64
+    elif name in ("nanmean", "nanvar", "nanstd"):
+        odt = np.float64
+    else:
+        odt = a.dtype
+    out = np.empty(out_shape, odt)
+    r = lib().xtref_nanfn(name.encode(), dt, _p(a), a.ndim, _i64(a.shape), len(axes), _i32(axes), _p(out))
+    if r < 0:
+        raise RuntimeError(lib().xtref_last_error().decode())
+    assert r == out.size
+    return out
+
+
+def count_nonzero_i32(a, axes):
+    a = np.ascontiguousarray(a, np.int32)
+    out = np.empty(tuple(s for d, s in enumerate(a.shape) if d not in axes), np.uint64)
+    r = lib().xtref_count_nonzero_i32(_p(a), a.ndim, _i64(a.shape), len(axes), _i32(axes), _p(out))
+    assert r == out.size
+    return out
+
+
+def nan_to_num(a):
+    a = np.ascontiguousarray(a)
+    out = np.empty_like(a)
+    lib().xtref_nan_to_num(int(a.dtype == np.float64), _p(a), _p(out), C.c_int64(a.size))
+    return out

@@ -180,6 +180,23 @@ int main()
         xt::xarray<double> hcp = xt::cumprod(a * 0.5 + 1.0, 2);
         CHECK(max_abs_diff(xtb::to_host(cp), hcp) <= 1e-9 * std::fabs(hcp(0, 0, 8)) + 1e-6);
     }
+    // nan-skipping reducers (core/xmath.hpp:2365-2473, test/test_xnan_functions.cpp): nansum / nanprod lower to
+    // the sum / prod kernels with the NaN replacement fused into the map program; nanmean composes them
+    {
+        xt::xarray<double> a = xt::round(rnd<double>(16, -3, 3, 10, 12, 7));
+        a(0, 0, 0) = std::nan("");
+        a(3, 5, 2) = std::nan("");
+        for (std::size_t i = 0; i < 10; ++i) a(i, 4, 6) = std::nan("");     // an all-NaN lane along axis 0
+        xtb::xarray<double> da = xtb::to_device(a);
+        xtb::xarray<double> ns0 = xt::nansum(da, {0}), ns12 = xt::nansum(da, {1, 2}), np2 = xt::nanprod(da, {2});
+        xt::xarray<double> hs0 = xt::nansum(a, {0}), hs12 = xt::nansum(a, {1, 2}), hp2 = xt::nanprod(a, {2});
+        CHECK(same_bits(xtb::to_host(ns0), hs0));
+        CHECK(same_bits(xtb::to_host(ns12), hs12));
+        CHECK(same_bits(xtb::to_host(np2), hp2));
+        auto nsi = xt::nansum(da, {0, 2}, xt::evaluation_strategy::immediate);
+        xt::xarray<double> hnsi = xt::nansum(a, {0, 2}, xt::evaluation_strategy::immediate);
+        CHECK(same_bits(xtb::to_host(nsi), hnsi));
+    }
     // view on the left-hand side (xview_semantic, core/xsemantic.hpp:726-796): strided store and
     // broadcasting into a view (test_strided_assign.cpp:178-196, test_extended_broadcast_view.cpp:811-1033)
     {

@@ -775,6 +775,90 @@ def stddev(e, axes=None, dtype=None, ddof=0):
     return sqrt(variance(e, axes, dtype, ddof))
 
 
+# ---- nan-aware reducers, counts (core/xmath.hpp:2307-2860) ---------------------------------------
+# The reference builds these from custom reducer functors (nan_plus: "!isnan(rhs) ? lhs + rhs : lhs", ...).
+# Here they are the SAME values written as fused map-reduce programs over the existing merge operators, so
+# they run on the map-reduce kernels with one pass over the data:
+#   nan_plus over x        ==  plus over where(isnan(x), 0, x)       (acc + 0 == acc: the accumulator starts at
+#                                                                      +0 and can never be -0)
+#   nan_multiplies over x  ==  multiplies over where(isnan(x), 1, x)
+#   count_nonzero          ==  plus over size_t(x != 0)
+def _const_like(e: Expr, v) -> Scalar:
+    return Scalar(NP_OF[e.dtype](v), e.dtype)
+
+
+def nan_to_num(e):
+    """nan -> 0, +inf -> max, -inf -> lowest (detail::nan_to_num_functor, core/xmath.hpp:2309-2331)."""
+    e = as_expr(e)
+    if e.dtype not in (F32, F64):
+        return e
+    fi = np.finfo(NP_OF[e.dtype])
+    return where(isnan(e), _const_like(e, 0), where(isinf(e), where(e < _const_like(e, 0), _const_like(e, fi.min), _const_like(e, fi.max)), e))
+
+
+def nansum(e, axes=None, keep_dims=False, dtype=None):
+    e = as_expr(e)
+    return sum(where(isnan(e), _const_like(e, 0), e), axes, keep_dims, dtype=dtype)
+
+
+def nanprod(e, axes=None, keep_dims=False, dtype=None):
+    e = as_expr(e)
+    return prod(where(isnan(e), _const_like(e, 1), e), axes, keep_dims, dtype=dtype)
+
+
+def count_nonzero(e, axes=None, keep_dims=False):
+    """result type std::size_t (xreducer_size_type_t, reducers/xreducer.hpp:1178-1185)."""
+    e = as_expr(e)
+    return sum(cast(e.ne(_const_like(e, 0)), U64), axes, keep_dims)
+
+
+def count_nonnan(e, axes=None, keep_dims=False):
+    """count_nonzero(!isnan(e)) (core/xmath.hpp:2540-2570)."""
+    return count_nonzero(logical_not(isnan(as_expr(e))), axes, keep_dims)
+
+
+def _nan_extreme(red, fill, e, axes, keep_dims):
+    # nan_min / nan_max start from NaN and skip NaN operands (core/xmath.hpp:2333-2363, 2427-2443): the
+    # extreme of the non-NaN values, NaN where there is none
+    e = as_expr(e)
+    if e.dtype not in (F32, F64):
+        return red(e, axes, keep_dims)
+    m = red(where(isnan(e), _const_like(e, fill), e), axes, keep_dims)
+    n = count_nonnan(e, axes, keep_dims)
+    return where(n.eq(Scalar(np.uint64(0), U64)), _const_like(e, np.nan), m)
+
+
+def nanmin(e, axes=None, keep_dims=False): return _nan_extreme(amin, np.inf, e, axes, keep_dims)
+def nanmax(e, axes=None, keep_dims=False): return _nan_extreme(amax, -np.inf, e, axes, keep_dims)
+
+
+def nanmean(e, axes=None, dtype=None, keep_dims=False):
+    """nansum<sum_type>(e, axes) / cast<value_type>(count_nonnan(e, axes)); value_type = double unless T is
+    given, sum_type = common_type(E::value_type, double) unless T is given (core/xmath.hpp:2694-2712)."""
+    e = as_expr(e)
+    vt = F64 if dtype is None else dtype
+    st = common_type(e.dtype, F64) if dtype is None else dtype
+    return nansum(e, axes, keep_dims, dtype=st) / cast(count_nonnan(e, axes, keep_dims), vt)
+
+
+def nanvar(e, axes=None, dtype=None):
+    """nanmean<R>(square(cast<R>(e) - reshape_view(nanmean<R>(e, axes), keep_dims shape)), axes), R = double
+    unless T is given (core/xmath.hpp:2785-2808)."""
+    e = as_expr(e)
+    nd = len(e.shape)
+    ax = list(range(nd)) if axes is None else ([axes] if isinstance(axes, (int, np.integer)) else list(axes))
+    ax = [a + nd if a < 0 else a for a in ax]
+    rt = F64 if dtype is None else dtype
+    inner = evaluate(nanmean(e, ax, dtype=rt))
+    keep = [1 if d in ax else sh for d, sh in enumerate(e.shape)]
+    ce = e if e.dtype == rt else cast(e, rt)
+    return nanmean(square(ce - inner.reshape_view(keep)), ax, dtype=rt)
+
+
+def nanstd(e, axes=None, dtype=None):
+    return sqrt(nanvar(e, axes, dtype))
+
+
 def _scan(op, e, axis, dtype, out=None):
     a = evaluate(e)
     kind = type(a)
