@@ -315,14 +315,15 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
                 "kernel": lib.xtb_last_kernel().decode()}
 
     try:
-        if world == 1 and not args.quick:
+        if world == 1:
             rng = np.random.default_rng(1)
             # cfg1: fp64 1-D 2^24 a + b
-            n = 1 << 24
-            a, b = (xt.DeviceArray.from_numpy(rng.uniform(-1, 1, n)) for _ in range(2))
-            c = xt.DeviceArray.empty((n,), xt.F64)
-            out["cfg1_add_f64"] = timed(lambda: xt.assign(c, a + b), 3 * n * 8)
-            del a, b, c
+            if not args.quick:
+                n = 1 << 24
+                a, b = (xt.DeviceArray.from_numpy(rng.uniform(-1, 1, n)) for _ in range(2))
+                c = xt.DeviceArray.empty((n,), xt.F64)
+                out["cfg1_add_f64"] = timed(lambda: xt.assign(c, a + b), 3 * n * 8)
+                del a, b, c
             # cfg3: fp32 (4096,4096,16) sum / amax over axis 0 and axis 2
             x = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (4096, 4096, 16)).astype(np.float32))
             nb = 4096 * 4096 * 16 * 4
@@ -331,13 +332,14 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
             out["cfg3_sum_axis2"] = timed(lambda: xt.evaluate(xt.sum(x, [2])), nb + 4096 * 4096 * 4)
             out["cfg3_amax_axis2"] = timed(lambda: xt.evaluate(xt.amax(x, [2])), nb + 4096 * 4096 * 4)
             del x
-            # cfg4: fp64 (8192,8192) transpose(a) + view(b, range(0,_,2), all())
-            a = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (8192, 8192)))
-            b = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (16384, 8192)))
-            o = xt.DeviceArray.empty((8192, 8192), xt.F64)
-            e = xt.transpose(a) + xt.view(b, slice(0, None, 2), slice(None))
-            out["cfg4_transpose_view_f64"] = timed(lambda: xt.assign(o, e), 3 * 8192 * 8192 * 8, iters=5)
-            del a, b, o, e
+            if not args.quick:
+                # cfg4: fp64 (8192,8192) transpose(a) + view(b, range(0,_,2), all())
+                a = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (8192, 8192)))
+                b = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (16384, 8192)))
+                o = xt.DeviceArray.empty((8192, 8192), xt.F64)
+                e = xt.transpose(a) + xt.view(b, slice(0, None, 2), slice(None))
+                out["cfg4_transpose_view_f64"] = timed(lambda: xt.assign(o, e), 3 * 8192 * 8192 * 8, iters=5)
+                del a, b, o, e
         if world == 1 and not args.quick:
             # cumsum (north_star: xaccumulator as a decoupled look-back scan); 2 x element size per element
             x = xt.DeviceArray.from_numpy(np.random.default_rng(2).uniform(-1, 1, 1 << 26).astype(np.float32))

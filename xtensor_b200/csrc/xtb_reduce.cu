@@ -118,6 +118,29 @@ struct ReducePlanIn {
 static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth);
 
 // second pass over partials[nsplit][K]
+template <int BINOP, int ACC_RT>
+static void launch_merge(const RdParams& fp, DeviceCtx* ctx, bool xchg, const P2pParams& xw) {
+    if (xchg) {
+        k_reduce_merge<BINOP, ACC_RT, true><<<(unsigned) ((fp.K + 127) / 128), kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+    } else if (fp.K < 128) {
+        k_reduce_merge_few<BINOP, ACC_RT><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
+    } else {
+        k_reduce_merge<BINOP, ACC_RT, false><<<(unsigned) ((fp.K + 127) / 128), kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+    }
+}
+template <int BINOP>
+static int launch_merge_rt(int acc_rt, const RdParams& fp, DeviceCtx* ctx, bool xchg, const P2pParams& xw) {
+    switch (acc_rt) {
+        case XTB_I32: launch_merge<BINOP, XTB_I32>(fp, ctx, xchg, xw); return XTB_OK;
+        case XTB_U32: launch_merge<BINOP, XTB_U32>(fp, ctx, xchg, xw); return XTB_OK;
+        case XTB_I64: launch_merge<BINOP, XTB_I64>(fp, ctx, xchg, xw); return XTB_OK;
+        case XTB_U64: launch_merge<BINOP, XTB_U64>(fp, ctx, xchg, xw); return XTB_OK;
+        case XTB_F32: launch_merge<BINOP, XTB_F32>(fp, ctx, xchg, xw); return XTB_OK;
+        case XTB_F64: launch_merge<BINOP, XTB_F64>(fp, ctx, xchg, xw); return XTB_OK;
+        default: XTB_FAIL(XTB_ERR_INVALID, "merge: accumulator type %d", acc_rt);
+    }
+}
+
 static int merge_partials(ReducePlanIn& first, const RdParams& fp, DeviceCtx* ctx, int depth) {
     (void) depth;
     if (fp.K >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "too many outputs");
@@ -130,20 +153,15 @@ static int merge_partials(ReducePlanIn& first, const RdParams& fp, DeviceCtx* ct
                       words <= kP2pMaxWords && comm_p2p_params(ctx, &xw) && xw.world > 1;
     // the reported kernel stays the first pass (the one that moves the data), with the merge appended
     char name[128];
-    snprintf(name, sizeof(name), "%.90s + %s", xtb_last_kernel(), fp.K < 128 ? "k_reduce_merge_few" : xchg ? "k_reduce_merge[+p2p exchange]" : "k_reduce_merge");
-    if (xchg) {
-        const unsigned grid = (unsigned) ((fp.K + 127) / 128);
-        if (first.w64) k_reduce_merge<uint64_t, true><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
-        else k_reduce_merge<uint32_t, true><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
-        first.xchg_done = true;
-    } else if (fp.K < 128) {
-        if (first.w64) k_reduce_merge_few<uint64_t><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
-        else k_reduce_merge_few<uint32_t><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
-    } else {
-        const unsigned grid = (unsigned) ((fp.K + 127) / 128);
-        if (first.w64) k_reduce_merge<uint64_t, false><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
-        else k_reduce_merge<uint32_t, false><<<grid, kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+    snprintf(name, sizeof(name), "%.90s + %s", xtb_last_kernel(), xchg ? "k_reduce_merge[+p2p exchange]" : fp.K < 128 ? "k_reduce_merge_few" : "k_reduce_merge");
+    switch (first.binop) {
+        case XTB_OP_ADD: XTB_TRY(launch_merge_rt<XTB_OP_ADD>(first.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_MUL: XTB_TRY(launch_merge_rt<XTB_OP_MUL>(first.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_MAXIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MAXIMUM>(first.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_MINIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MINIMUM>(first.acc_rt, fp, ctx, xchg, xw)); break;
+        default: XTB_FAIL(XTB_ERR_INVALID, "merge: operator %d", first.binop);
     }
+    if (xchg) first.xchg_done = true;
     note_launch(name);
     return check_launch("k_reduce_merge");
 }

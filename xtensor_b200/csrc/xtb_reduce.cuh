@@ -140,7 +140,21 @@ template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S 
     store_elem<S>(dst, p.out_dtype, p.acc_rt, a[0]);
 }
 
+// final value of a typed merge -> (merge initial) -> cast -> store
+template <int BINOP, int ACC_RT, class S> XTB_DEV void rd_finish_store_c(const RdParams& p, char* dst, S v) {
+    S a[1] = {v};
+    if (p.has_initial) {
+        S b[1] = {(S) p.initial_bits};
+        exec_binary_c<BINOP, ACC_RT, S, 1>(a, b);
+    }
+    using T = reg_t<ACC_RT>;
+    store_as<T>(dst, p.out_dtype, get<T>(a[0]));
+}
+
 // Second pass of a split reduction: out[k] = partials[0][k] (+) partials[1][k] (+) ... over part[nsplit][K].
+// The merge operator and the accumulator type are compile-time (4 x 6 small instantiations): the kernel is
+// a few hundred instructions, which matters because it runs for microseconds between two bandwidth-bound
+// kernels (the run-time-typed version spent its time fetching instructions).
 // A block owns 128 outputs (4 per lane, 128-bit loads); warp w of its 16 warps adds splits w, w+16, ...,
 // eight loads in flight per lane, then the warps are combined in order through shared memory: a fixed
 // order and a couple of memory round trips, however few outputs there are (the case that needs
@@ -150,16 +164,20 @@ template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S 
 // rank's partial.  The thread that finishes output k then exchanges it with the other ranks over NVLink
 // peer memory (xtb_p2p.cuh) and combines the R partials in rank order before the one store: the local
 // merge and the cross-GPU merge are one kernel, and the partial never travels through HBM in between.
+// Word layout = k_allreduce_p2p on the accumulator type.
 constexpr int kMergeWarps = 16;
-template <class S, bool XCHG>
+template <int ACC_RT> struct MergeSlot { using type = std::conditional_t<dtype_size(ACC_RT) == 8, uint64_t, uint32_t>; };
+
+template <int BINOP, int ACC_RT, bool XCHG>
 __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_constant__ RdParams p, const __grid_constant__ P2pParams xw) {
+    using S = typename MergeSlot<ACC_RT>::type;
+    constexpr int asz = dtype_size(ACC_RT);
     __shared__ S sm[kMergeWarps][128];
     uint32_t epoch = 0;
     if constexpr (XCHG) epoch = p2p_epoch(xw);
     constexpr int U = 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t k0 = ((int64_t) blockIdx.x * 32 + lane) * 4;
-    const int asz = dtype_size(p.acc_rt);
     S acc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i] = (S) p.identity_bits;
@@ -172,15 +190,15 @@ __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_
                 const int sp = s0 + kMergeWarps * u;
                 const char* src = p.part_ptr + ((int64_t) sp * p.K + k0) * asz;
                 if (sp < p.nsplit && vec) {
-                    load_vec<S, 4>(src, p.acc_rt, x[u]);
+                    load_vec<S, 4>(src, ACC_RT, x[u]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) x[u][i] = (sp < p.nsplit && k0 + i < p.K) ? load_elem<S>(src + i * asz, p.acc_rt) : (S) p.identity_bits;
+                    for (int i = 0; i < 4; ++i) x[u][i] = (sp < p.nsplit && k0 + i < p.K) ? load_elem<S>(src + i * asz, ACC_RT) : (S) p.identity_bits;
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (s0 + kMergeWarps * u < p.nsplit) DynAcc::template step<S, 4>(p, acc, x[u]);
+                if (s0 + kMergeWarps * u < p.nsplit) exec_binary_c<BINOP, ACC_RT, S, 4>(acc, x[u]);
         }
     }
 #pragma unroll
@@ -192,41 +210,29 @@ __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_
         if (k < p.K) {
             const int c = warp * 32 + lane;
             S r[1] = {sm[0][c]};
+#pragma unroll
             for (int w = 1; w < kMergeWarps; ++w) {
                 S y[1] = {sm[w][c]};
-                DynAcc::template step<S, 1>(p, r, y);
+                exec_binary_c<BINOP, ACC_RT, S, 1>(r, y);
             }
             if constexpr (XCHG) {
-                // same word layout as k_allreduce_p2p on the accumulator type (a 32-bit value sits in the low half of a 64-bit slot)
+                constexpr int W = sizeof(S) / 4;
                 const S mine = r[0];
-                S theirs[kP2pMaxWorld];
-                bool wide = false;
-                if constexpr (sizeof(S) == 8) wide = dtype_size(p.acc_rt) == 8;
-                if (wide) {
-                    if constexpr (sizeof(S) == 8) {
-                        uint32_t mw[2], got[kP2pMaxWorld][2];
-                        memcpy(mw, &mine, 8);
-                        p2p_exchange<2>(xw, epoch, (size_t) k * 2, mw, got);
-#pragma unroll
-                        for (int q = 0; q < kP2pMaxWorld; ++q) memcpy(&theirs[q], got[q], 8);
-                    }
-                } else {
-                    uint32_t mw[1] = {(uint32_t) mine}, got[kP2pMaxWorld][1];
-                    p2p_exchange<1>(xw, epoch, (size_t) k, mw, got);
-#pragma unroll
-                    for (int q = 0; q < kP2pMaxWorld; ++q) theirs[q] = (S) got[q][0];
-                }
+                uint32_t mw[W], got[kP2pMaxWorld][W];
+                memcpy(mw, &mine, sizeof(S));
+                p2p_exchange<W>(xw, epoch, (size_t) k * W, mw, got);
 #pragma unroll
                 for (int q = 0; q < kP2pMaxWorld; ++q) {
                     if (q < xw.world) {
-                        S y[1] = {q == xw.rank ? mine : theirs[q]};
+                        S y[1] = {mine};
+                        if (q != xw.rank) memcpy(&y[0], got[q], sizeof(S));
                         if (q == 0) r[0] = y[0];
-                        else DynAcc::template step<S, 1>(p, r, y);
+                        else exec_binary_c<BINOP, ACC_RT, S, 1>(r, y);
                     }
                 }
             }
             const int64_t off = rd_kept_offset(p, (uint32_t) k, p.out_kstride);
-            rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), r[0]);
+            rd_finish_store_c<BINOP, ACC_RT, S>(p, p.out_ptr + off * dtype_size(p.out_dtype), r[0]);
         }
     }
     if constexpr (XCHG) {
@@ -237,37 +243,38 @@ __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_
 
 // Few outputs (full reductions, K < 128): one block per output, thread t adds splits t, t+256, ...,
 // then a fixed-shape tree over the block.
-template <class S>
+template <int BINOP, int ACC_RT>
 __global__ void __launch_bounds__(256) k_reduce_merge_few(const __grid_constant__ RdParams p) {
+    using S = typename MergeSlot<ACC_RT>::type;
+    constexpr int asz = dtype_size(ACC_RT);
     __shared__ S sm[256];
     const int t = threadIdx.x;
     const int64_t k = blockIdx.x;
-    const int asz = dtype_size(p.acc_rt);
     S acc[1] = {(S) p.identity_bits};
     for (int s0 = t; s0 < p.nsplit; s0 += 256 * 4) {
         S x[4][1];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int sp = s0 + 256 * u;
-            x[u][0] = sp < p.nsplit ? load_elem<S>(p.part_ptr + ((int64_t) sp * p.K + k) * asz, p.acc_rt) : (S) p.identity_bits;
+            x[u][0] = sp < p.nsplit ? load_elem<S>(p.part_ptr + ((int64_t) sp * p.K + k) * asz, ACC_RT) : (S) p.identity_bits;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (s0 + 256 * u < p.nsplit) DynAcc::template step<S, 1>(p, acc, x[u]);
+            if (s0 + 256 * u < p.nsplit) exec_binary_c<BINOP, ACC_RT, S, 1>(acc, x[u]);
     }
     sm[t] = acc[0];
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if (t < o) {
             S a[1] = {sm[t]}, b[1] = {sm[t + o]};
-            DynAcc::template step<S, 1>(p, a, b);
+            exec_binary_c<BINOP, ACC_RT, S, 1>(a, b);
             sm[t] = a[0];
         }
         __syncthreads();
     }
     if (t == 0) {
         const int64_t off = rd_kept_offset(p, (uint32_t) k, p.out_kstride);
-        rd_finish_store<S>(p, p.out_ptr + off * dtype_size(p.out_dtype), sm[0]);
+        rd_finish_store_c<BINOP, ACC_RT, S>(p, p.out_ptr + off * dtype_size(p.out_dtype), sm[0]);
     }
 }
 
