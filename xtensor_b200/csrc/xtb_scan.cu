@@ -591,6 +591,284 @@ __global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_sc
     }
 }
 
+// ---- contiguous scan, chained rows: persistent CTAs over a ring of tiles (opt-in: XTB_SCAN_RING=1) ----
+// k_scan_stile holds a 64 KB super-tile in shared memory from its load until the look-back of the tile has
+// finished; a tile cannot finish before EVERY older tile has published its aggregate, and under bandwidth
+// saturation those loads complete with a spread of several microseconds -- the shared memory (and with it
+// the bytes in flight) idles meanwhile: 0.59 of the copy peak on the flat scan.
+// Here one CTA per SM stays resident and cycles 16 KB tiles through a ring of kRgStages shared-memory
+// slots; every hand-over is an mbarrier, so no warp ever waits for a warp doing something else:
+//   producer warp : next tile of this CTA (tiles are dealt round robin over the resident CTAs), waits for
+//                   its slot to be free, issues ONE bulk copy -> full[s]
+//   scan warps    : 2 groups x 8 warps, group g owns the CTA's tiles g, g+2, ..: wait full[s], scan the
+//                   warp's 128 vectors in place, hand the warp total over (agg[s]); phase B (add the tile's
+//                   base, stream out, empty[s]) runs kRgSkew tiles of the group later, so a look-back has
+//                   several tile times to complete before anybody has to wait for it
+//   totals warp   : agg[s] -> warp offsets + tile total, publishes the aggregate at once (tot[s])
+//   look-back warps (4, round robin): tile_lookback as in the other kernels (same fixed-shape trees: the
+//                   result depends only on the tile's position), then pre[s]
+// Reads and writes of the data: one each.
+constexpr int kRgTileBytes = 16 * 1024;
+constexpr int kRgStages = 13;
+constexpr int kRgGroups = 2;
+constexpr int kRgGroupWarps = 8;
+constexpr int kRgScanWarps = kRgGroups * kRgGroupWarps;
+constexpr int kRgLookWarps = 4;
+constexpr int kRgSkew = 2;                                       // in tiles of one group
+constexpr int kRgWarpP = kRgScanWarps, kRgWarpT = kRgScanWarps + 1, kRgWarpL0 = kRgScanWarps + 2;
+constexpr int kRgThreads = (kRgScanWarps + 2 + kRgLookWarps) * 32;
+constexpr int kRgSentinels = kRgLookWarps > kRgGroups ? kRgLookWarps : kRgGroups;
+
+XTB_DEV void mbar_init(unsigned long long* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+XTB_DEV void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+XTB_DEV void mbar_wait(unsigned long long* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kRgThreads, 1) k_scan_ring(const __grid_constant__ ScanParams p) {
+    constexpr int VEC = 16 / (int) sizeof(T), NV = 4;
+    constexpr int TE = kRgTileBytes / (int) sizeof(T);           // elements per tile
+    constexpr int WE = TE / kRgGroupWarps;                       // elements per scan warp = 128 vectors
+    static_assert(WE == 32 * NV * VEC, "a scan warp owns NV vectors per lane");
+    extern __shared__ __align__(128) unsigned char rg_smem[];
+    __shared__ __align__(8) unsigned long long b_full[kRgStages], b_agg[kRgStages], b_tot[kRgStages], b_pre[kRgStages], b_empty[kRgStages];
+    __shared__ int32_t s_tile[kRgStages];
+    __shared__ int32_t s_valid[kRgStages];
+    __shared__ T s_wtot[kRgStages][kRgGroupWarps];
+    __shared__ T s_woff[kRgStages][kRgGroupWarps];
+    __shared__ T s_total[kRgStages];
+    __shared__ T s_prefix[kRgStages];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int op = p.op;
+    const T ident = scan_identity<T>(op);
+    if (tid == 0) {
+        for (int s = 0; s < kRgStages; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_agg[s], kRgGroupWarps);
+            mbar_init(&b_tot[s], 1);
+            mbar_init(&b_pre[s], 1);
+            mbar_init(&b_empty[s], kRgGroupWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int isz = (int) sizeof(T);
+
+    if (warp == kRgWarpP) {
+        // ---- producer ----
+        if (lane == 0) {
+            int posted = 0;   // sentinels posted after the CTA's last tile (every consumer role sees one)
+            for (int n = 0;; ++n) {
+                const int s = n % kRgStages, r = n / kRgStages;
+                if (r > 0) mbar_wait(&b_empty[s], (uint32_t) ((r - 1) & 1));
+                // CTA c owns tiles c, c + grid, ..: every CTA is resident (grid <= SM count, one CTA per SM), so
+                // all predecessors of a tile are in flight at about the same ring position of their CTAs
+                const uint64_t tile64 = (uint64_t) blockIdx.x + (uint64_t) n * gridDim.x;
+                const uint32_t tile = tile64 < p.total_tiles ? (uint32_t) tile64 : 0xffffffffu;
+                if (tile >= p.total_tiles) {
+                    s_tile[s] = -1;
+                    mbar_arrive(&b_full[s]);
+                    if (++posted == kRgSentinels) break;
+                    continue;
+                }
+                const uint32_t row = tile / p.tiles_per_row;
+                const uint32_t trow = tile - row * p.tiles_per_row;
+                const int64_t tbase = (int64_t) trow * TE;
+                const int64_t left = p.n - tbase;
+                const int valid = left < TE ? (int) left : TE;
+                s_tile[s] = (int32_t) tile;
+                s_valid[s] = valid;
+                const char* src = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz + tbase * isz;
+                const uint32_t bytes = (uint32_t) valid * (uint32_t) sizeof(T);
+                const uint32_t bar = smem_u32(&b_full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(rg_smem + (size_t) s * kRgTileBytes)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+            }
+        }
+        return;
+    }
+    if (warp == kRgWarpT) {
+        // ---- totals: warp offsets, tile total, aggregate published at once ----
+        for (int n = 0;; ++n) {
+            const int s = n % kRgStages;
+            const uint32_t par = (uint32_t) ((n / kRgStages) & 1);
+            mbar_wait(&b_full[s], par);
+            const int32_t tile = s_tile[s];
+            if (tile < 0) break;
+            mbar_wait(&b_agg[s], par);
+            T wv = lane < kRgGroupWarps ? s_wtot[s][lane] : ident;
+#pragma unroll
+            for (int d = 1; d < kRgGroupWarps; d <<= 1) {
+                const T y = shfl_up_t<T>(wv, d);
+                if (lane >= d) wv = scan_op<T>(op, y, wv);
+            }
+            const T total = shfl_idx_t<T>(wv, kRgGroupWarps - 1);
+            const T excl = shfl_up_t<T>(wv, 1);
+            if (lane < kRgGroupWarps) s_woff[s][lane] = lane == 0 ? ident : excl;
+            if (lane == 0) {
+                const uint32_t row = (uint32_t) tile / p.tiles_per_row;
+                const uint32_t trow = (uint32_t) tile - row * p.tiles_per_row;
+                s_total[s] = total;
+                if (trow + 1 < p.tiles_per_row) slot_publish<T>(p.aggregate, (uint32_t) tile, total);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_tot[s]);
+        }
+        return;
+    }
+    if (warp >= kRgWarpL0) {
+        // ---- look-back: tiles l, l + kRgLookWarps, .. of this CTA ----
+        for (int n = warp - kRgWarpL0;; n += kRgLookWarps) {
+            const int s = n % kRgStages;
+            const uint32_t par = (uint32_t) ((n / kRgStages) & 1);
+            mbar_wait(&b_full[s], par);
+            const int32_t tile = s_tile[s];
+            if (tile < 0) break;
+            const uint32_t row = (uint32_t) tile / p.tiles_per_row;
+            const uint32_t trow = (uint32_t) tile - row * p.tiles_per_row;
+            T part;
+            const T e = tile_lookback<T>(p, op, row, trow, lane, &part);
+            mbar_wait(&b_tot[s], par);
+            if (lane == 0) {
+                const uint32_t kb = trow / kScanWindow;
+                if (trow - kb * kScanWindow == kScanWindow - 1 && trow + 1 < p.tiles_per_row) {
+                    const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
+                    slot_publish<T>(p.prefix, row * blocks_per_row + kb, scan_op<T>(op, part, *(volatile T*) &s_total[s]));
+                }
+                s_prefix[s] = e;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_pre[s]);
+        }
+        return;
+    }
+    // ---- scan warps ----
+    const int g = warp / kRgGroupWarps, wl = warp % kRgGroupWarps;
+    bool ended = false;
+    int jend = 0;
+    for (int j = 0;; ++j) {
+        if (!ended) {
+            const int n = g + j * kRgGroups;
+            const int s = n % kRgStages;
+            mbar_wait(&b_full[s], (uint32_t) ((n / kRgStages) & 1));
+            const int32_t tile = s_tile[s];
+            if (tile < 0) {
+                ended = true;
+                jend = j;
+            } else {
+                // phase A: scan my 128 vectors in place, striped over the lanes
+                int myvalid = s_valid[s] - wl * WE;
+                myvalid = myvalid < 0 ? 0 : (myvalid > WE ? WE : myvalid);
+                T* my = (T*) (rg_smem + (size_t) s * kRgTileBytes) + wl * WE;
+                T x[NV][VEC];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int e0 = (q * 32 + lane) * VEC;
+                    if (e0 + VEC <= myvalid) {
+                        const uint4 rr = *(const uint4*) (my + e0);
+                        memcpy(&x[q][0], &rr, 16);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) x[q][i] = ident;   // valid counts are multiples of VEC
+                    }
+                }
+                T inc[NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+#pragma unroll
+                    for (int i = 1; i < VEC; ++i) x[q][i] = scan_op<T>(op, x[q][i - 1], x[q][i]);
+                    inc[q] = x[q][VEC - 1];
+                }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) {
+                        const T y = shfl_up_t<T>(inc[q], d);
+                        if (lane >= d) inc[q] = scan_op<T>(op, y, inc[q]);
+                    }
+                }
+                T carry = ident;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const T ex = shfl_up_t<T>(inc[q], 1);
+                    const T rowtot = shfl_idx_t<T>(inc[q], 31);
+                    if (q == 0) {
+                        if (lane > 0) {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) x[q][i] = scan_op<T>(op, ex, x[q][i]);
+                        }
+                        carry = rowtot;
+                    } else {
+                        const T o = lane == 0 ? carry : scan_op<T>(op, carry, ex);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) x[q][i] = scan_op<T>(op, o, x[q][i]);
+                        carry = scan_op<T>(op, carry, rowtot);
+                    }
+                    uint4 rr;
+                    memcpy(&rr, &x[q][0], 16);
+                    *(uint4*) (my + (q * 32 + lane) * VEC) = rr;
+                }
+                if (lane == 0) s_wtot[s][wl] = carry;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_agg[s]);
+            }
+        }
+        const int jb = j - kRgSkew;
+        if (jb >= 0 && (!ended || jb < jend)) {
+            // phase B of an earlier tile of my group: add its base, stream out, free the slot
+            const int n = g + jb * kRgGroups;
+            const int s = n % kRgStages;
+            mbar_wait(&b_pre[s], (uint32_t) ((n / kRgStages) & 1));
+            const uint32_t tile = (uint32_t) s_tile[s];
+            const uint32_t row = tile / p.tiles_per_row;
+            const uint32_t trow = tile - row * p.tiles_per_row;
+            int myvalid = s_valid[s] - wl * WE;
+            myvalid = myvalid < 0 ? 0 : (myvalid > WE ? WE : myvalid);
+            const T woff = s_woff[s][wl];
+            T base = woff;
+            bool have = wl > 0;
+            if (trow > 0) {
+                const T e = s_prefix[s];
+                base = wl > 0 ? scan_op<T>(op, e, woff) : e;
+                have = true;
+            }
+            const T* my = (const T*) (rg_smem + (size_t) s * kRgTileBytes) + wl * WE;
+            T* dst = (T*) p.out + (int64_t) row * p.n + (int64_t) trow * TE + wl * WE;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int e0 = (q * 32 + lane) * VEC;
+                if (e0 + VEC <= myvalid) {
+                    T v[VEC];
+                    const uint4 rr = *(const uint4*) (my + e0);
+                    memcpy(&v[0], &rr, 16);
+                    if (have) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) v[i] = scan_op<T>(op, base, v[i]);
+                    }
+                    uint4 w;
+                    memcpy(&w, &v[0], 16);
+                    stg_stream_16(dst + e0, w);
+                }
+            }
+            // my generic-proxy accesses to the slot are ordered before the next bulk copy into it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_empty[s]);
+        }
+        if (ended && jb >= jend - 1) break;
+    }
+}
+
 // ---- strided axis, long axis: single-pass column tiles -------------------------------------------
 // A CTA owns R rows x W <= 256 columns (<= 64 KB) of one (outer, column-strip): warp 0 fetches the rows
 // with bulk asynchronous copies, every scan thread walks one column of the tile downwards in shared
@@ -1015,6 +1293,31 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         return check_launch("k_scan_tiles");
     }
     const int64_t row_bytes = q.n * (int64_t) sizeof(T);
+    if (getenv("XTB_SCAN_RING") && q.vec_io && row_bytes >= 16 * (int64_t) kRgTileBytes && q.n % C::VEC == 0) {
+        // opt-in: persistent CTAs over a ring of 16 KB tiles (k_scan_ring)
+        const int64_t te = kRgTileBytes / (int64_t) sizeof(T);
+        const int64_t tpr = (q.n + te - 1) / te;
+        const int64_t tiles = tpr * q.rows;
+        if (tiles >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
+        q.tiles_per_row = (uint32_t) tpr;
+        q.total_tiles = (uint32_t) tiles;
+        q.st_elems = (int32_t) te;
+        const int64_t bpr = (tpr + kScanWindow - 1) / kScanWindow;
+        const size_t agg_bytes = ((size_t) tiles * C::SLOT + 255) / 256 * 256;
+        const size_t blk_bytes = ((size_t) (bpr * q.rows) * C::SLOT + 255) / 256 * 256;
+        void* scratch = nullptr;
+        XTB_TRY(ensure_scratch(ctx, agg_bytes + blk_bytes, &scratch));
+        char* s = (char*) scratch;
+        q.aggregate = s;
+        q.prefix = s + agg_bytes;
+        XTB_CUDA(cudaMemsetAsync(s, 0, agg_bytes + blk_bytes, ctx->stream));
+        const size_t smem = (size_t) kRgStages * kRgTileBytes;
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_ring<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        const unsigned grid = (unsigned) std::min<int64_t>(tiles, (int64_t) ctx->sm_count);
+        k_scan_ring<T><<<grid, kRgThreads, smem, ctx->stream>>>(q);
+        note_launch("k_scan_ring[look-back]");
+        return check_launch("k_scan_ring");
+    }
     // staged super-tile configuration: threads per CTA / CTAs per SM / super-tile bytes
     // staged super-tiles: long rows (several tiles, look-back) use 8 scan warps + the look-back warp on 64 KB,
     // 3 CTAs per SM; rows of one tile use 4 warps on up to 32 KB, 6 CTAs per SM
