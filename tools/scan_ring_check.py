@@ -55,8 +55,7 @@ for shape, axis, dt, prod in CASES:
     if prod:
         x = np.where(rng.random(shape) < 0.5, 1.0, -1.0).astype(dt)     # exact products
     elif np.prod(shape) > (1 << 24) and np.dtype(dt).kind == "f":
-        x = rng.integers(0, 2, shape).astype(dt)                          # exact fp32 sums up to 2^24
-        x[..., 1::3] = 0
+        x = (rng.random(shape) < 0.2).astype(dt)                          # sums stay below 2^24: exact in fp32
     else:
         x = rng.integers(-4, 5, shape).astype(dt)
     got, kern = run(x, axis, True, prod)
