@@ -69,23 +69,22 @@ for shape, axis, dt, prod in CASES:
         rec["n_bad"] = int(bad.size)
     print(json.dumps(rec), flush=True)
 
-# timing: flat 2^26 fp32, ring vs default
+# timing: flat 2^26 fp32, ring variants (XTB_SCAN_RING=1..4: look-back warps / skew) vs default
 x = np.random.default_rng(2).uniform(-1, 1, 1 << 26).astype(np.float32)
 d = xt.DeviceArray.from_numpy(x)
 y = xt.DeviceArray.empty((1 << 26,), xt.F32)
+xi = np.random.default_rng(4).integers(-4, 5, (1 << 22) + 12).astype(np.int32)
+di = xt.DeviceArray.from_numpy(xi)
 nbytes = 2 * (1 << 26) * 4
 res = {}
-for ring in (True, False, True):
-    if ring:
-        os.environ["XTB_SCAN_RING"] = "1"
+for variant in ("1", "2", "3", "4", None, "1"):
+    if variant:
+        os.environ["XTB_SCAN_RING"] = variant
     else:
         os.environ.pop("XTB_SCAN_RING", None)
+    good = bool(np.array_equal(xt.cumsum(di).numpy(), np.cumsum(xi)))
+    ok_all = ok_all and good
     ms = timed(lambda: xt.cumsum(d, out=y))
-    res[lib.xtb_last_kernel().decode()] = {"ms": round(ms, 4), "GBs": round(nbytes / ms / 1e6, 1)}
-ring_out = y.numpy()
+    res[f"{variant}:{lib.xtb_last_kernel().decode()}"] = {"ms": round(ms, 4), "GBs": round(nbytes / ms / 1e6, 1), "int32_exact": good}
 os.environ.pop("XTB_SCAN_RING", None)
-xt.cumsum(d, out=y)
-xt.sync()
-base_out = y.numpy()
-rel = float(np.max(np.abs(ring_out.astype(np.float64) - base_out) / (np.abs(np.cumsum(np.abs(x.astype(np.float64)))) + 1e-30)))
-print(json.dumps({"timing_flat_f32_2^26": res, "ring_vs_default_max_rel_of_sum_abs": rel, "all_ok": ok_all}), flush=True)
+print(json.dumps({"timing_flat_f32_2^26": res, "all_ok": ok_all}), flush=True)

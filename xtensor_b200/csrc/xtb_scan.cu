@@ -613,11 +613,9 @@ constexpr int kRgStages = 13;
 constexpr int kRgGroups = 2;
 constexpr int kRgGroupWarps = 8;
 constexpr int kRgScanWarps = kRgGroups * kRgGroupWarps;
-constexpr int kRgLookWarps = 4;
-constexpr int kRgSkew = 2;                                       // in tiles of one group
 constexpr int kRgWarpP = kRgScanWarps, kRgWarpT = kRgScanWarps + 1, kRgWarpL0 = kRgScanWarps + 2;
-constexpr int kRgThreads = (kRgScanWarps + 2 + kRgLookWarps) * 32;
-constexpr int kRgSentinels = kRgLookWarps > kRgGroups ? kRgLookWarps : kRgGroups;
+// LOOKW look-back warps, SKEW = tiles of one group between a tile's phase A and its phase B
+template <int LOOKW> constexpr int rg_threads() { return (kRgScanWarps + 2 + LOOKW) * 32; }
 
 XTB_DEV void mbar_init(unsigned long long* b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -633,8 +631,10 @@ XTB_DEV void mbar_wait(unsigned long long* b, uint32_t parity) {
     }
 }
 
-template <class T>
-__global__ void __launch_bounds__(kRgThreads, 1) k_scan_ring(const __grid_constant__ ScanParams p) {
+template <class T, int LOOKW, int SKEW>
+__global__ void __launch_bounds__(rg_threads<LOOKW>(), 1) k_scan_ring(const __grid_constant__ ScanParams p) {
+    constexpr int kRgLookWarps = LOOKW, kRgSkew = SKEW;
+    constexpr int kRgSentinels = LOOKW > kRgGroups ? LOOKW : kRgGroups;
     constexpr int VEC = 16 / (int) sizeof(T), NV = 4;
     constexpr int TE = kRgTileBytes / (int) sizeof(T);           // elements per tile
     constexpr int WE = TE / kRgGroupWarps;                       // elements per scan warp = 128 vectors
@@ -669,7 +669,12 @@ __global__ void __launch_bounds__(kRgThreads, 1) k_scan_ring(const __grid_consta
             int posted = 0;   // sentinels posted after the CTA's last tile (every consumer role sees one)
             for (int n = 0;; ++n) {
                 const int s = n % kRgStages, r = n / kRgStages;
-                if (r > 0) mbar_wait(&b_empty[s], (uint32_t) ((r - 1) & 1));
+                if (r > 0) {
+                    mbar_wait(&b_empty[s], (uint32_t) ((r - 1) & 1));
+                    // the scan warps' generic-proxy accesses to the slot (observed through the barrier) are
+                    // ordered before the bulk copy that overwrites it
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
                 // CTA c owns tiles c, c + grid, ..: every CTA is resident (grid <= SM count, one CTA per SM), so
                 // all predecessors of a tile are in flight at about the same ring position of their CTAs
                 const uint64_t tile64 = (uint64_t) blockIdx.x + (uint64_t) n * gridDim.x;
@@ -860,8 +865,6 @@ __global__ void __launch_bounds__(kRgThreads, 1) k_scan_ring(const __grid_consta
                     stg_stream_16(dst + e0, w);
                 }
             }
-            // my generic-proxy accesses to the slot are ordered before the next bulk copy into it
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_empty[s]);
         }
@@ -1312,9 +1315,20 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         q.prefix = s + agg_bytes;
         XTB_CUDA(cudaMemsetAsync(s, 0, agg_bytes + blk_bytes, ctx->stream));
         const size_t smem = (size_t) kRgStages * kRgTileBytes;
-        XTB_CUDA(cudaFuncSetAttribute(k_scan_ring<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         const unsigned grid = (unsigned) std::min<int64_t>(tiles, (int64_t) ctx->sm_count);
-        k_scan_ring<T><<<grid, kRgThreads, smem, ctx->stream>>>(q);
+        const int variant = atoi(getenv("XTB_SCAN_RING"));
+#define XTB_RING_LAUNCH(LW, SK)                                                                                              \
+    do {                                                                                                                     \
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_ring<T, LW, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));     \
+        k_scan_ring<T, LW, SK><<<grid, rg_threads<LW>(), smem, ctx->stream>>>(q);                                            \
+    } while (0)
+        switch (variant) {
+            case 2: XTB_RING_LAUNCH(8, 2); break;
+            case 3: XTB_RING_LAUNCH(4, 3); break;
+            case 4: XTB_RING_LAUNCH(4, 1); break;
+            default: XTB_RING_LAUNCH(4, 2); break;
+        }
+#undef XTB_RING_LAUNCH
         note_launch("k_scan_ring[look-back]");
         return check_launch("k_scan_ring");
     }
