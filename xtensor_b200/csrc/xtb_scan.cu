@@ -1322,7 +1322,7 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         XTB_CUDA(cudaFuncSetAttribute(k_scan_ring<T, LW, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));     \
         k_scan_ring<T, LW, SK><<<grid, rg_threads<LW>(), smem, ctx->stream>>>(q);                                            \
     } while (0)
-        switch (variant) {
+        switch (variant) {   // measured on flat 2^26 fp32: 1 -> 0.193 ms, 2 -> 0.217, 3 -> 0.158, 4 -> 0.297 (k_scan_stile: 0.142)
             case 2: XTB_RING_LAUNCH(8, 2); break;
             case 3: XTB_RING_LAUNCH(4, 3); break;
             case 4: XTB_RING_LAUNCH(4, 1); break;
