@@ -286,6 +286,102 @@ namespace xtb
         a.swap(b);
     }
 
+    // ---------------------------------------------------------------- foreign device memory
+    // device_span<T>: the storage of an adaptor over device memory that somebody else owns (cudaMalloc, a
+    // torch tensor's data_ptr(), a DLPack capsule).  Counterpart of xbuffer_adaptor<T*, no_ownership>
+    // (containers/xbuffer_adaptor.hpp:365, containers/xadapt.hpp:105-215): never allocates or frees,
+    // `resize` to another size is an error, assignment from a temporary copies into the adapted buffer
+    // (xbuffer_adaptor::operator=(temporary_type&&), :1058-1064) with a device-to-device copy.
+    template <class T>
+    class device_span
+    {
+    public:
+
+        using allocator_type = std::allocator<T>;
+        using value_type = T;
+        using reference = T&;
+        using const_reference = const T&;
+        using pointer = T*;
+        using const_pointer = const T*;
+        using size_type = std::size_t;
+        using difference_type = std::ptrdiff_t;
+        using iterator = pointer;
+        using const_iterator = const_pointer;
+        using reverse_iterator = std::reverse_iterator<iterator>;
+        using const_reverse_iterator = std::reverse_iterator<const_iterator>;
+        using temporary_type = device_uvector<T>;
+
+        device_span() noexcept = default;
+
+        device_span(pointer device_ptr, size_type n) noexcept
+            : m_ptr(device_ptr)
+            , m_size(n)
+        {
+        }
+
+        device_span(const device_span&) noexcept = default;
+        device_span& operator=(const device_span&) noexcept = default;
+
+        device_span& operator=(temporary_type&& tmp)
+        {
+            resize(tmp.size());
+            if (m_size)
+            {
+                check(xtb_memcpy(m_ptr, tmp.data(), m_size * sizeof(T), XTB_D2D));
+            }
+            return *this;
+        }
+
+        void resize(size_type n)
+        {
+            if (n != m_size)
+            {
+                XTENSOR_THROW(std::runtime_error, "xtb200: an adaptor over foreign device memory cannot be resized");
+            }
+        }
+
+        bool empty() const noexcept { return m_size == 0; }
+        size_type size() const noexcept { return m_size; }
+        pointer data() noexcept { return m_ptr; }
+        const_pointer data() const noexcept { return m_ptr; }
+        // device addresses: valid for pointer arithmetic only (same contract as device_uvector)
+        iterator begin() noexcept { return m_ptr; }
+        iterator end() noexcept { return m_ptr + m_size; }
+        const_iterator begin() const noexcept { return m_ptr; }
+        const_iterator end() const noexcept { return m_ptr + m_size; }
+        const_iterator cbegin() const noexcept { return m_ptr; }
+        const_iterator cend() const noexcept { return m_ptr + m_size; }
+        reverse_iterator rbegin() noexcept { return reverse_iterator(end()); }
+        reverse_iterator rend() noexcept { return reverse_iterator(begin()); }
+        const_reverse_iterator rbegin() const noexcept { return const_reverse_iterator(end()); }
+        const_reverse_iterator rend() const noexcept { return const_reverse_iterator(begin()); }
+        const_reverse_iterator crbegin() const noexcept { return const_reverse_iterator(end()); }
+        const_reverse_iterator crend() const noexcept { return const_reverse_iterator(begin()); }
+        reference operator[](size_type i) { return m_ptr[i]; }
+        const_reference operator[](size_type i) const { return m_ptr[i]; }
+        reference front() { return m_ptr[0]; }
+        const_reference front() const { return m_ptr[0]; }
+        reference back() { return m_ptr[m_size - 1]; }
+        const_reference back() const { return m_ptr[m_size - 1]; }
+
+        void swap(device_span& rhs) noexcept
+        {
+            std::swap(m_ptr, rhs.m_ptr);
+            std::swap(m_size, rhs.m_size);
+        }
+
+    private:
+
+        pointer m_ptr = nullptr;
+        size_type m_size = 0;
+    };
+
+    template <class T>
+    inline void swap(device_span<T>& a, device_span<T>& b) noexcept
+    {
+        a.swap(b);
+    }
+
     // ---------------------------------------------------------------- containers
     template <class T, std::size_t N, xt::layout_type L = XTENSOR_DEFAULT_LAYOUT>
     using xtensor = xt::xtensor_container<device_uvector<T>, N, L, b200_expression_tag>;
@@ -293,10 +389,58 @@ namespace xtb
     template <class T, xt::layout_type L = XTENSOR_DEFAULT_LAYOUT>
     using xarray = xt::xarray_container<device_uvector<T>, L, xt::dynamic_shape<std::size_t>, b200_expression_tag>;
 
+    // adaptors over foreign device memory (xarray_adaptor / xtensor_adaptor with the device tag)
+    template <class T, xt::layout_type L = XTENSOR_DEFAULT_LAYOUT>
+    using xarray_adaptor = xt::xarray_adaptor<device_span<T>, L, xt::dynamic_shape<std::size_t>, b200_expression_tag>;
+
+    template <class T, std::size_t N, xt::layout_type L = XTENSOR_DEFAULT_LAYOUT>
+    using xtensor_adaptor = xt::xtensor_adaptor<device_span<T>, N, L, b200_expression_tag>;
+
     template <class E>
     struct is_b200_expression : std::is_same<xt::xexpression_tag_t<E>, b200_expression_tag>
     {
     };
+
+    // xtb::adapt(device_ptr, shape[, strides]) -- xt::adapt(ptr, size, xt::no_ownership(), shape[, strides])
+    // (containers/xadapt.hpp:105-215) for device memory: no copy, no ownership; usable on both sides of an
+    // assignment (`xt::noalias(xtb::adapt(out_ptr, shape)) = xt::sin(xtb::adapt(in_ptr, shape))`).
+    template <class T, class SC>
+    inline xarray_adaptor<T> adapt(T* device_ptr, const SC& shape)
+    {
+        xt::dynamic_shape<std::size_t> sh(shape.begin(), shape.end());
+        std::size_t n = 1;
+        for (auto e : sh)
+        {
+            n *= e;
+        }
+        return xarray_adaptor<T>(device_span<T>(device_ptr, n), sh);
+    }
+
+    template <class T, class SC, class SS>
+    inline xarray_adaptor<T> adapt(T* device_ptr, const SC& shape, const SS& strides)
+    {
+        xt::dynamic_shape<std::size_t> sh(shape.begin(), shape.end());
+        xt::get_strides_t<xt::dynamic_shape<std::size_t>> st(strides.begin(), strides.end());
+        std::size_t span = 1;   // elements covered by the strided view
+        std::size_t d = 0;
+        for (auto e : sh)
+        {
+            if (e == 0)
+            {
+                span = 0;
+                break;
+            }
+            span += (e - 1) * static_cast<std::size_t>(st[d] < 0 ? -st[d] : st[d]);
+            ++d;
+        }
+        return xarray_adaptor<T>(device_span<T>(device_ptr, span), sh, st);
+    }
+
+    template <class T>
+    inline xarray_adaptor<T> adapt(T* device_ptr, std::initializer_list<std::size_t> shape)
+    {
+        return adapt(device_ptr, std::vector<std::size_t>(shape));
+    }
 }
 
 // ======================================================================== xt:: hooks
@@ -314,6 +458,18 @@ namespace xt
 
         template <class EC, layout_type L, class SC>
         struct xarray_container_base<EC, L, SC, xtb::b200_expression_tag>
+        {
+            using type = xtb::b200_empty_base;
+        };
+
+        template <class EC, layout_type L, class SC>
+        struct xarray_adaptor_base<EC, L, SC, xtb::b200_expression_tag>
+        {
+            using type = xtb::b200_empty_base;
+        };
+
+        template <class EC, std::size_t N, layout_type L>
+        struct xtensor_adaptor_base<EC, N, L, xtb::b200_expression_tag>
         {
             using type = xtb::b200_empty_base;
         };
@@ -357,6 +513,13 @@ namespace xt
             using type = xfunction<F, E...>;
         };
     }
+
+    // an adaptor's temporary is an owning device container (containers/xbuffer_adaptor.hpp:584-609)
+    template <class T>
+    struct temporary_container<xtb::device_span<T>>
+    {
+        using type = xtb::device_uvector<T>;
+    };
 
     // temporaries of device expressions are device containers of the same rank / value type
     template <class T>

@@ -197,6 +197,42 @@ int main()
         xt::xarray<double> hnsi = xt::nansum(a, {0, 2}, xt::evaluation_strategy::immediate);
         CHECK(same_bits(xtb::to_host(nsi), hnsi));
     }
+    // adaptors over foreign device memory (xt::adapt with no_ownership, containers/xadapt.hpp:105-215): operands
+    // and destination are raw device pointers, nothing is copied or owned
+    {
+        xt::xarray<float> a = rnd<float>(41, -2, 2, 6, 40), b = rnd<float>(42, -2, 2, 40);
+        float *pa = nullptr, *pb = nullptr, *po = nullptr;
+        xtb::check(xtb_malloc(a.size() * sizeof(float), reinterpret_cast<void**>(&pa)));
+        xtb::check(xtb_malloc(b.size() * sizeof(float), reinterpret_cast<void**>(&pb)));
+        xtb::check(xtb_malloc(a.size() * sizeof(float), reinterpret_cast<void**>(&po)));
+        xtb::check(xtb_memcpy(pa, a.data(), a.size() * sizeof(float), XTB_H2D));
+        xtb::check(xtb_memcpy(pb, b.data(), b.size() * sizeof(float), XTB_H2D));
+        auto da = xtb::adapt(pa, {6, 40});
+        auto db = xtb::adapt(pb, {40});
+        auto dout = xtb::adapt(po, {6, 40});
+        xt::noalias(dout) = da * db + 2.0f;                               // broadcast, written straight into po
+        xt::xarray<float> expect = a * b + 2.0f, got = xt::zeros<float>({6, 40});
+        xtb::check(xtb_memcpy(got.data(), po, got.size() * sizeof(float), XTB_D2H));
+        xtb::check(xtb_sync());
+        CHECK(same_bits(got, expect));
+        std::vector<std::size_t> tshape = {40, 6};
+        std::vector<std::ptrdiff_t> tstrides = {1, 40};                   // the same memory seen transposed
+        auto dat = xtb::adapt(pa, tshape, tstrides);
+        xtb::xarray<float> tsum = xt::sum(dat, {1});
+        xt::xarray<float> hsum = xt::sum(xt::transpose(a), {1});
+        CHECK(max_abs_diff(xtb::to_host(tsum), hsum) <= 1e-5);
+        xtb::xarray<float> owned = da + 1.0f;                             // adaptor operand, owning destination
+        xt::xarray<float> howned = a + 1.0f;
+        CHECK(same_bits(xtb::to_host(owned), howned));
+        dout = xt::sqrt(xt::abs(da));                                     // aliasing path: temporary, then copied into po
+        xt::xarray<float> expect2 = xt::sqrt(xt::abs(a));
+        xtb::check(xtb_memcpy(got.data(), po, got.size() * sizeof(float), XTB_D2H));
+        xtb::check(xtb_sync());
+        CHECK(same_bits(got, expect2));
+        xtb::check(xtb_free(pa));
+        xtb::check(xtb_free(pb));
+        xtb::check(xtb_free(po));
+    }
     // view on the left-hand side (xview_semantic, core/xsemantic.hpp:726-796): strided store and
     // broadcasting into a view (test_strided_assign.cpp:178-196, test_extended_broadcast_view.cpp:811-1033)
     {
