@@ -416,8 +416,9 @@ namespace xtb
         return xarray_adaptor<T>(device_span<T>(device_ptr, n), sh);
     }
 
+    // custom strides need a dynamic-layout adaptor, as in the reference (containers/xadapt.hpp:158-180)
     template <class T, class SC, class SS>
-    inline xarray_adaptor<T> adapt(T* device_ptr, const SC& shape, const SS& strides)
+    inline xarray_adaptor<T, xt::layout_type::dynamic> adapt(T* device_ptr, const SC& shape, const SS& strides)
     {
         xt::dynamic_shape<std::size_t> sh(shape.begin(), shape.end());
         xt::get_strides_t<xt::dynamic_shape<std::size_t>> st(strides.begin(), strides.end());
@@ -433,7 +434,7 @@ namespace xtb
             span += (e - 1) * static_cast<std::size_t>(st[d] < 0 ? -st[d] : st[d]);
             ++d;
         }
-        return xarray_adaptor<T>(device_span<T>(device_ptr, span), sh, st);
+        return xarray_adaptor<T, xt::layout_type::dynamic>(device_span<T>(device_ptr, span), sh, st);
     }
 
     template <class T>
