@@ -61,3 +61,35 @@ def test_fork_misuse_is_an_error(xt, gpu):
     capi.check(lib.xtb_fork_end())
     capi.check(lib.xtb_fork_join())
     capi.check(lib.xtb_sync())
+
+
+def test_foreign_device_memory(xt, gpu):
+    """xtb::adapt / DeviceArray.from_pointer: operands and destination in memory the library does not own
+    (here: raw xtb_malloc allocations handled by the test), contiguous and with custom strides."""
+    import ctypes as C
+    from xtensor_b200 import capi
+    rng = np.random.default_rng(11)
+    a = rng.integers(-9, 10, (6, 40)).astype(np.float32)
+    b = rng.integers(-9, 10, (40,)).astype(np.float32)
+    ptrs = []
+    for nbytes in (a.nbytes, b.nbytes, a.nbytes):
+        p = C.c_void_p()
+        capi.check(gpu.xtb_malloc(nbytes, C.byref(p)))
+        ptrs.append(p)
+    try:
+        capi.check(gpu.xtb_memcpy(ptrs[0], C.c_void_p(a.ctypes.data), a.nbytes, capi.H2D))
+        capi.check(gpu.xtb_memcpy(ptrs[1], C.c_void_p(b.ctypes.data), b.nbytes, capi.H2D))
+        A = xt.DeviceArray.from_pointer(ptrs[0].value, a.shape, xt.F32)
+        B = xt.DeviceArray.from_pointer(ptrs[1].value, b.shape, xt.F32)
+        O = xt.DeviceArray.from_pointer(ptrs[2].value, a.shape, xt.F32)
+        xt.assign(O, A * B + np.float32(2.0))                       # written straight into the foreign buffer
+        got = np.empty_like(a)
+        capi.check(gpu.xtb_memcpy(C.c_void_p(got.ctypes.data), ptrs[2], got.nbytes, capi.D2H))
+        capi.check(gpu.xtb_sync())
+        assert np.array_equal(got, a * b + np.float32(2.0))
+        At = xt.DeviceArray.from_pointer(ptrs[0].value, (40, 6), xt.F32, strides=(1, 40))   # the same memory, transposed
+        assert np.array_equal(xt.evaluate(xt.sum(At, [1])).numpy(), a.T.sum(axis=1))
+        assert np.array_equal(At.numpy(), a.T)
+    finally:
+        for p in ptrs:
+            gpu.xtb_free(p)

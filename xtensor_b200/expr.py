@@ -386,8 +386,36 @@ class DeviceBuffer:
             pass
 
 
+class ForeignBuffer:
+    """xtb::device_span: device memory owned by somebody else (cudaMalloc, torch, DLPack); never freed here.
+    `keepalive` pins the owner object for as long as arrays over the buffer exist."""
+
+    def __init__(self, ptr: int, nbytes: int, keepalive=None):
+        self.ptr, self.nbytes, self.keepalive = int(ptr), int(nbytes), keepalive
+
+
 class DeviceArray(Array):
     """Container with device storage (xtensor_container<device_uvector<T>, ...>)."""
+
+    @staticmethod
+    def from_pointer(ptr: int, shape, dtype: int, strides=None, keepalive=None) -> "DeviceArray":
+        """xtb::adapt(device_ptr, shape[, strides]) (xt::adapt with no_ownership, containers/xadapt.hpp:105-215):
+        an array over foreign device memory, element strides, no copy."""
+        shape = tuple(int(s) for s in shape)
+        strides = compute_strides(shape) if strides is None else tuple(int(s) for s in strides)
+        span = 0 if 0 in shape else 1 + builtins.sum((e - 1) * builtins.abs(st) for e, st in zip(shape, strides))
+        return DeviceArray(shape, strides, 0, dtype, ForeignBuffer(ptr, span * SIZE_OF[dtype], keepalive))
+
+    @staticmethod
+    def from_torch(t) -> "DeviceArray":
+        """Zero-copy view of a CUDA torch tensor (data_ptr / shape / stride); the tensor is kept alive.  The
+        caller orders the streams (torch.cuda.synchronize() or a shared stream via xtb_set_stream)."""
+        import torch
+        names = {torch.float32: F32, torch.float64: F64, torch.int32: I32, torch.int64: I64, torch.int16: I16,
+                 torch.int8: I8, torch.uint8: U8, torch.bool: BOOL}
+        if not t.is_cuda:
+            raise ValueError("from_torch needs a CUDA tensor (there is no CPU path)")
+        return DeviceArray.from_pointer(t.data_ptr(), tuple(t.shape), names[t.dtype], tuple(t.stride()), keepalive=t)
 
     @staticmethod
     def empty(shape, dtype: int) -> "DeviceArray":
