@@ -15,6 +15,9 @@
 #pragma once
 #include "xtb_ew.cuh"
 #include "xtb_p2p.cuh"
+#ifndef XTB_RTC
+#include <cstdlib>
+#endif
 
 namespace xtb {
 
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(256) k_reduce_merge_few(const __grid_constant_
 
 // Stage U vectors of leaf K (and recursively of the following leaves) of a compile-time
 // program.  dtype / element size are constants; the access mode is one uniform branch per leaf.
-template <class Eval, class S, int V, int U, int K> struct RdLeafLoader {
+template <class Eval, class S, int V, int U, int K, int INV = 0> struct RdLeafLoader {
     template <class PF, class AddrFn>
     static XTB_DEV void run(const RdParams& p, const int (&nvalid)[U], int64_t gather_stride_elems_sel, PF& pf, AddrFn addr_of,
                             bool skip_invariant = false) {
@@ -288,8 +291,15 @@ template <class Eval, class S, int V, int U, int K> struct RdLeafLoader {
             constexpr int dt = Eval::template leaf_dtype<K>();
             constexpr int sz = dtype_size(dt);
             const RdLeaf& L = p.leaf[K];
+            if constexpr (((INV >> K) & 1) != 0) {
+                // compile-time invariant leaf (the host checked rstride == 0, vector access, whole vectors):
+                // ONE vector, loaded by the first iteration only
+                if (!skip_invariant) load_vec<S, V>(addr_of(L, sz, 0), dt, pf.inv[K]);
+                RdLeafLoader<Eval, S, V, U, K + 1, INV>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
+                return;
+            }
             if (skip_invariant && L.rstride[0] == 0 && p.nr == 1) {
-                RdLeafLoader<Eval, S, V, U, K + 1>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
+                RdLeafLoader<Eval, S, V, U, K + 1, INV>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
                 return;
             }
             const char* addr[U];
@@ -322,7 +332,7 @@ template <class Eval, class S, int V, int U, int K> struct RdLeafLoader {
 #pragma unroll
                     for (int v = 0; v < V; ++v) pf.pre[K][u][v] = (v < nvalid[u]) ? load_elem<S>(addr[u] + v * step, dt) : S(0);
             }
-            RdLeafLoader<Eval, S, V, U, K + 1>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
+            RdLeafLoader<Eval, S, V, U, K + 1, INV>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
         }
     }
 };
@@ -616,8 +626,9 @@ __global__ void __launch_bounds__(256) k_reduce_inner_block(const __grid_constan
 }
 
 // ---- innermost dim kept --------------------------------------------------------------------
-template <class Eval, class Acc, class S, int V>
-__global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ RdParams p) {
+// INV (opt-in, XTB_REDUCE_INV=1): bit mask of leaves the host found invariant along the reduced dim
+template <class Eval, class Acc, class S, int V, int INV = 0>
+__global__ void __launch_bounds__(256, INV != 0 ? 3 : 1) k_reduce_outer(const __grid_constant__ RdParams p) {
     constexpr int NL = Eval::kLeaves;
     const int64_t rbeg = (int64_t) blockIdx.y * p.chunk;
     int64_t rend = rbeg + p.chunk;
@@ -650,14 +661,14 @@ __global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ Rd
                 // U rows of every leaf in flight before any arithmetic; rows are then accumulated in
                 // the reference's order (row r before row r + 1)
                 constexpr int U = 8;
-                PreFetch<NL, U, S, V> pf;
+                std::conditional_t<INV != 0, PreFetchInv<NL, U, S, V, INV>, PreFetch<NL, U, S, V>> pf;
                 for (int64_t r = rbeg; r < rend; r += U) {
                     int nvalid[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) nvalid[u] = (r + u < rend) ? f.nvalid : 0;
                     // leaves that do not depend on the reduced index (e.g. the mean in square(a - mean))
                     // keep the registers staged by the first iteration
-                    RdLeafLoader<Eval, S, V, U, 0>::run(p, nvalid, 0, pf, [&](const RdLeaf& L, int sz, int u) -> const char* {
+                    RdLeafLoader<Eval, S, V, U, 0, INV>::run(p, nvalid, 0, pf, [&](const RdLeaf& L, int sz, int u) -> const char* {
                         const int64_t koff = rd_kept_offset(p, ko0, L.kstride);
                         const int64_t ru = nvalid[u] > 0 ? r + u : rbeg;
                         return L.ptr + (koff + ru * L.rstride[0]) * sz;
@@ -778,7 +789,18 @@ static int launch_reduce(const RdParams& p, DeviceCtx* ctx, bool inner, const ch
         const int64_t blocks = (p.kvec_total + 255) / 256;
         dim3 grid((unsigned) std::min<int64_t>(blocks, (int64_t) ctx->sm_count * 64), (unsigned) p.nsplit);
         snprintf(name, sizeof(name), "k_reduce_outer<%s,S%d,V%d>[split=%d]", evname, (int) sizeof(S) * 8, V, p.nsplit);
-        k_reduce_outer<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
+        bool inv1 = false;
+        if constexpr (Eval::kPrefetch && Eval::kLeaves == 2 && V > 1) {
+            // opt-in: leaf 1 staged once when it does not move along the reduced dim and every thread owns whole vectors
+            const RdLeaf& L = p.leaf[1];
+            inv1 = getenv("XTB_REDUCE_INV") != nullptr && p.nr == 1 && p.n_leaves == 2 && L.rstride[0] == 0 && L.mode == MODE_VEC &&
+                   p.leaf[0].rstride[0] != 0 && p.kshape[p.nk - 1] % V == 0;
+            if (inv1) {
+                snprintf(name, sizeof(name), "k_reduce_outer<%s,S%d,V%d,inv1>[split=%d]", evname, (int) sizeof(S) * 8, V, p.nsplit);
+                k_reduce_outer<Eval, Acc, S, V, 2><<<grid, 256, 0, ctx->stream>>>(p);
+            }
+        }
+        if (!inv1) k_reduce_outer<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
     }
     note_launch(name);
     return check_launch(name);
