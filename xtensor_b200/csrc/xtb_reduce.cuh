@@ -626,9 +626,9 @@ __global__ void __launch_bounds__(256) k_reduce_inner_block(const __grid_constan
 }
 
 // ---- innermost dim kept --------------------------------------------------------------------
-// INV (opt-in, XTB_REDUCE_INV=1): bit mask of leaves the host found invariant along the reduced dim
-template <class Eval, class Acc, class S, int V, int INV = 0>
-__global__ void __launch_bounds__(256, INV != 0 ? 3 : 1) k_reduce_outer(const __grid_constant__ RdParams p) {
+// INV: bit mask of leaves the host found invariant along the reduced dim (k_reduce_outer_inv, opt-in)
+template <class Eval, class Acc, class S, int V, int INV>
+XTB_DEV void reduce_outer_body(const RdParams& p) {
     constexpr int NL = Eval::kLeaves;
     const int64_t rbeg = (int64_t) blockIdx.y * p.chunk;
     int64_t rend = rbeg + p.chunk;
@@ -735,6 +735,16 @@ __global__ void __launch_bounds__(256, INV != 0 ? 3 : 1) k_reduce_outer(const __
     }
 }
 
+template <class Eval, class Acc, class S, int V>
+__global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ RdParams p) {
+    reduce_outer_body<Eval, Acc, S, V, 0>(p);
+}
+// opt-in (XTB_REDUCE_INV=1): invariant leaves staged once; 80 registers -> 3 CTAs per SM
+template <class Eval, class Acc, class S, int V, int INV>
+__global__ void __launch_bounds__(256, 3) k_reduce_outer_inv(const __grid_constant__ RdParams p) {
+    reduce_outer_body<Eval, Acc, S, V, INV>(p);
+}
+
 #ifndef XTB_RTC
 // launch geometry shared by the ahead-of-time and the run-time specialised kernels
 struct RdLaunch {
@@ -797,7 +807,7 @@ static int launch_reduce(const RdParams& p, DeviceCtx* ctx, bool inner, const ch
                    p.leaf[0].rstride[0] != 0 && p.kshape[p.nk - 1] % V == 0;
             if (inv1) {
                 snprintf(name, sizeof(name), "k_reduce_outer<%s,S%d,V%d,inv1>[split=%d]", evname, (int) sizeof(S) * 8, V, p.nsplit);
-                k_reduce_outer<Eval, Acc, S, V, 2><<<grid, 256, 0, ctx->stream>>>(p);
+                k_reduce_outer_inv<Eval, Acc, S, V, 2><<<grid, 256, 0, ctx->stream>>>(p);
             }
         }
         if (!inv1) k_reduce_outer<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
