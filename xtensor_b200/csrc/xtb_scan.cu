@@ -249,6 +249,35 @@ XTB_DEV T tile_lookback(const ScanParams& p, int op, uint32_t row, uint32_t trow
     return e;
 }
 
+// The window-local half of tile_lookback: tree(aggregates of the tiles of my window before me), in every lane.
+// Same shape as in tile_lookback, so "part (+) my aggregate" is the same block total whoever publishes it.
+template <class T>
+XTB_DEV T window_part(const ScanParams& p, int op, uint32_t row, uint32_t trow, int lane) {
+    const T ident = scan_identity<T>(op);
+    const uint32_t kb = trow / kScanWindow;
+    const uint32_t cnt = trow - kb * kScanWindow;
+    const uint32_t first = row * p.tiles_per_row + kb * kScanWindow;
+    T v[8];
+    bool ok[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t idx = (uint32_t) j * 32 + lane;
+        v[j] = ident;
+        ok[j] = idx >= cnt || slot_try<T>(p.aggregate, first + idx, v[j]);
+    }
+    T a = ident;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t idx = (uint32_t) j * 32 + lane;
+        while (!ok[j]) {
+            __nanosleep(40);
+            ok[j] = slot_try<T>(p.aggregate, first + idx, v[j]);
+        }
+        if (idx < cnt) a = scan_op<T>(op, a, v[j]);
+    }
+    return warp_total<T>(op, a);
+}
+
 // WARP_ROWS: rows of at most 32*ITEMS elements, one warp per row (no block or tile combine)
 template <class T, bool WARP_ROWS>
 __global__ void __launch_bounds__(kScanThreads, 4) k_scan_tiles(const __grid_constant__ ScanParams p) {
@@ -610,12 +639,19 @@ __global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_sc
 // Reads and writes of the data: one each.
 constexpr int kRgTileBytes = 16 * 1024;
 constexpr int kRgStages = 13;
-constexpr int kRgGroups = 2;
 constexpr int kRgGroupWarps = 8;
-constexpr int kRgScanWarps = kRgGroups * kRgGroupWarps;
-constexpr int kRgWarpP = kRgScanWarps, kRgWarpT = kRgScanWarps + 1, kRgWarpL0 = kRgScanWarps + 2;
-// LOOKW look-back warps, SKEW = tiles of one group between a tile's phase A and its phase B
-template <int LOOKW> constexpr int rg_threads() { return (kRgScanWarps + 2 + LOOKW) * 32; }
+constexpr int kRgAheadWarps = 8;
+// LOOKW look-back warps, SKEW = tiles of one group between a tile's phase A and its phase B.
+// AHEAD = 0: two scan groups.  AHEAD > 0 ("reduce ahead"): one scan group plus kRgAheadWarps warps that
+// reduce the CTA's tiles AHEAD positions before they are scanned and publish the aggregates then: by the
+// time a tile is scanned everything its look-back needs was published long ago (no waiting), and its data
+// is re-read from the L2 (AHEAD x grid x 16 KB in between must stay L2-resident), so HBM still sees one
+// read and one write.  The published aggregate comes from the reduce pass (per-lane ascending sums, then a
+// butterfly: fixed shape), the tile's own elements from the scan pass.
+template <int AHEAD> constexpr int rg_groups() { return AHEAD > 0 ? 1 : 2; }
+template <int LOOKW, int AHEAD> constexpr int rg_threads() {
+    return (rg_groups<AHEAD>() * kRgGroupWarps + 2 + LOOKW + (AHEAD > 0 ? kRgAheadWarps : 0)) * 32;
+}
 
 XTB_DEV void mbar_init(unsigned long long* b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -631,9 +667,13 @@ XTB_DEV void mbar_wait(unsigned long long* b, uint32_t parity) {
     }
 }
 
-template <class T, int LOOKW, int SKEW>
-__global__ void __launch_bounds__(rg_threads<LOOKW>(), 1) k_scan_ring(const __grid_constant__ ScanParams p) {
+template <class T, int LOOKW, int SKEW, int AHEAD>
+__global__ void __launch_bounds__(rg_threads<LOOKW, AHEAD>(), 1) k_scan_ring(const __grid_constant__ ScanParams p) {
     constexpr int kRgLookWarps = LOOKW, kRgSkew = SKEW;
+    constexpr int kRgGroups = rg_groups<AHEAD>();
+    constexpr int kRgScanWarps = kRgGroups * kRgGroupWarps;
+    constexpr int kRgWarpP = kRgScanWarps, kRgWarpT = kRgScanWarps + 1, kRgWarpL0 = kRgScanWarps + 2;
+    constexpr int kRgWarpR0 = kRgWarpL0 + LOOKW;
     constexpr int kRgSentinels = LOOKW > kRgGroups ? LOOKW : kRgGroups;
     constexpr int VEC = 16 / (int) sizeof(T), NV = 4;
     constexpr int TE = kRgTileBytes / (int) sizeof(T);           // elements per tile
@@ -647,10 +687,12 @@ __global__ void __launch_bounds__(rg_threads<LOOKW>(), 1) k_scan_ring(const __gr
     __shared__ T s_woff[kRgStages][kRgGroupWarps];
     __shared__ T s_total[kRgStages];
     __shared__ T s_prefix[kRgStages];
+    __shared__ int s_done;                                       // tiles of this CTA whose phase B has run (reduce-ahead throttle)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int op = p.op;
     const T ident = scan_identity<T>(op);
     if (tid == 0) {
+        s_done = 0;
         for (int s = 0; s < kRgStages; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_agg[s], kRgGroupWarps);
@@ -724,7 +766,9 @@ __global__ void __launch_bounds__(rg_threads<LOOKW>(), 1) k_scan_ring(const __gr
                 const uint32_t row = (uint32_t) tile / p.tiles_per_row;
                 const uint32_t trow = (uint32_t) tile - row * p.tiles_per_row;
                 s_total[s] = total;
-                if (trow + 1 < p.tiles_per_row) slot_publish<T>(p.aggregate, (uint32_t) tile, total);
+                if constexpr (AHEAD == 0) {
+                    if (trow + 1 < p.tiles_per_row) slot_publish<T>(p.aggregate, (uint32_t) tile, total);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_tot[s]);
@@ -745,10 +789,12 @@ __global__ void __launch_bounds__(rg_threads<LOOKW>(), 1) k_scan_ring(const __gr
             const T e = tile_lookback<T>(p, op, row, trow, lane, &part);
             mbar_wait(&b_tot[s], par);
             if (lane == 0) {
-                const uint32_t kb = trow / kScanWindow;
-                if (trow - kb * kScanWindow == kScanWindow - 1 && trow + 1 < p.tiles_per_row) {
-                    const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
-                    slot_publish<T>(p.prefix, row * blocks_per_row + kb, scan_op<T>(op, part, *(volatile T*) &s_total[s]));
+                if constexpr (AHEAD == 0) {
+                    const uint32_t kb = trow / kScanWindow;
+                    if (trow - kb * kScanWindow == kScanWindow - 1 && trow + 1 < p.tiles_per_row) {
+                        const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
+                        slot_publish<T>(p.prefix, row * blocks_per_row + kb, scan_op<T>(op, part, *(volatile T*) &s_total[s]));
+                    }
                 }
                 s_prefix[s] = e;
             }
@@ -756,6 +802,59 @@ __global__ void __launch_bounds__(rg_threads<LOOKW>(), 1) k_scan_ring(const __gr
             if (lane == 0) mbar_arrive(&b_pre[s]);
         }
         return;
+    }
+    if constexpr (AHEAD > 0) {
+        if (warp >= kRgWarpR0) {
+            // ---- reduce ahead: tiles r, r + kRgAheadWarps, .. of this CTA, at most AHEAD tiles before their scan ----
+            constexpr int NB = 16;                                   // 128-bit loads in flight per lane
+            for (int m = warp - kRgWarpR0;; m += kRgAheadWarps) {
+                const uint64_t tile64 = (uint64_t) blockIdx.x + (uint64_t) m * gridDim.x;
+                if (tile64 >= p.total_tiles) break;
+                const uint32_t tile = (uint32_t) tile64;
+                while (m > *(volatile int*) &s_done + AHEAD) __nanosleep(200);
+                const uint32_t row = tile / p.tiles_per_row;
+                const uint32_t trow = tile - row * p.tiles_per_row;
+                if (trow + 1 >= p.tiles_per_row) continue;           // the last tile of a row has no successor
+                const int64_t tbase = (int64_t) trow * TE;
+                const int64_t left = p.n - tbase;
+                const int nvec = (int) (left < TE ? left : TE) / VEC;
+                const char* src = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz + tbase * isz;
+                T acc = ident;
+                for (int v0 = 0; v0 < TE / VEC; v0 += 32 * NB) {
+                    if (v0 >= nvec) break;                           // warp-uniform
+                    uint4 raw[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const int vi = v0 + b * 32 + lane;
+                        raw[b] = vi < nvec ? ldg_stream_16(src + (size_t) vi * 16) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const int vi = v0 + b * 32 + lane;
+                        if (vi < nvec) {
+                            T e[VEC];
+                            memcpy(&e[0], &raw[b], 16);
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc = scan_op<T>(op, acc, e[i]);
+                        }
+                    }
+                }
+                acc = warp_total<T>(op, acc);
+                if (lane == 0) slot_publish<T>(p.aggregate, tile, acc);
+                // the last tile of a window also publishes the window's total (needed by every later window) now,
+                // not when it is scanned: it waits only for the aggregates of its own window, which are being
+                // published by the other CTAs' reduce-ahead warps at this very moment
+                const uint32_t kb = trow / kScanWindow;
+                if (trow - kb * kScanWindow == kScanWindow - 1) {
+                    const T part = window_part<T>(p, op, row, trow, lane);
+                    if (lane == 0) {
+                        const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
+                        slot_publish<T>(p.prefix, row * blocks_per_row + kb, scan_op<T>(op, part, acc));
+                    }
+                }
+            }
+            return;
+        }
     }
     // ---- scan warps ----
     const int g = warp / kRgGroupWarps, wl = warp % kRgGroupWarps;
@@ -867,6 +966,9 @@ __global__ void __launch_bounds__(rg_threads<LOOKW>(), 1) k_scan_ring(const __gr
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_empty[s]);
+            if constexpr (AHEAD > 0) {
+                if (wl == 0 && lane == 0) *(volatile int*) &s_done = n + 1;
+            }
         }
         if (ended && jb >= jend - 1) break;
     }
@@ -1317,19 +1419,22 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         const size_t smem = (size_t) kRgStages * kRgTileBytes;
         const unsigned grid = (unsigned) std::min<int64_t>(tiles, (int64_t) ctx->sm_count);
         const int variant = atoi(getenv("XTB_SCAN_RING"));
-#define XTB_RING_LAUNCH(LW, SK)                                                                                              \
+#define XTB_RING_LAUNCH(LW, SK, AH)                                                                                          \
     do {                                                                                                                     \
-        XTB_CUDA(cudaFuncSetAttribute(k_scan_ring<T, LW, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));     \
-        k_scan_ring<T, LW, SK><<<grid, rg_threads<LW>(), smem, ctx->stream>>>(q);                                            \
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_ring<T, LW, SK, AH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        k_scan_ring<T, LW, SK, AH><<<grid, rg_threads<LW, AH>(), smem, ctx->stream>>>(q);                                    \
     } while (0)
         switch (variant) {   // measured on flat 2^26 fp32: 1 -> 0.193 ms, 2 -> 0.217, 3 -> 0.158, 4 -> 0.297 (k_scan_stile: 0.142)
-            case 2: XTB_RING_LAUNCH(8, 2); break;
-            case 3: XTB_RING_LAUNCH(4, 3); break;
-            case 4: XTB_RING_LAUNCH(4, 1); break;
-            default: XTB_RING_LAUNCH(4, 2); break;
+            case 2: XTB_RING_LAUNCH(8, 2, 0); break;
+            case 3: XTB_RING_LAUNCH(4, 3, 0); break;
+            case 4: XTB_RING_LAUNCH(4, 1, 0); break;
+            case 5: XTB_RING_LAUNCH(4, 2, 8); break;     // reduce ahead (not yet run on the device)
+            case 6: XTB_RING_LAUNCH(4, 2, 16); break;
+            case 7: XTB_RING_LAUNCH(4, 2, 32); break;
+            default: XTB_RING_LAUNCH(4, 2, 0); break;
         }
 #undef XTB_RING_LAUNCH
-        note_launch("k_scan_ring[look-back]");
+        note_launch(variant >= 5 ? "k_scan_ring[reduce-ahead]" : "k_scan_ring[look-back]");
         return check_launch("k_scan_ring");
     }
     // staged super-tile configuration: threads per CTA / CTAs per SM / super-tile bytes
