@@ -1,0 +1,176 @@
+"""(Named test_zz_* so that it runs after the oracle-sized parity tests.)
+
+BASELINE.json's configurations at their FULL sizes on the device, checked through properties that do not
+need the (slow, scalar) oracle at that size:
+  * integer-valued inputs make every sum / prefix sum exact in any order, so numpy's result is the reference's
+    result bit for bit (cfg1, cfg3, cfg4, cfg5 sum / mean, cumsum);
+  * transcendental maps are held to the north-star tolerance (<= 2 ulp of the correctly rounded value of the
+    same fp32 argument) against a float64 evaluation (cfg2, cfg5 map);
+  * cfg5's (262144, 8192) matrix is 64 copies of one (4096, 8192) block: the sum over axis 0 must be exactly 64x
+    the block's, the variance the block's, and every output block of the map identical to the first.
+The same checks run without a GPU on reduced shapes with the oracle as evaluator (that pins the test logic
+itself); the `gpu` variants run the full shapes through libxtb200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+F32 = np.float32
+
+
+def _ulps(got, want64):
+    """|got - want| in units of the fp32 spacing at want."""
+    w32 = want64.astype(F32)
+    return np.abs(got.astype(np.float64) - want64) / np.spacing(np.abs(w32)).astype(np.float64)
+
+
+def _tiled(xt, kind, blk, reps):
+    """`reps` copies of `blk` stacked along axis 0 (the device copy is filled block by block)."""
+    if kind is xt.HostArray:
+        return xt.HostArray.from_numpy(np.tile(blk, (reps, 1)))
+    from xtensor_b200 import capi
+    lib = capi.lib()
+    a = xt.DeviceArray.empty((reps * blk.shape[0], blk.shape[1]), xt.DT_OF[blk.dtype])
+    for r in range(reps):
+        capi.check(lib.xtb_memcpy(C.c_void_p(a.owner.ptr + r * blk.nbytes), C.c_void_p(blk.ctypes.data), blk.nbytes, capi.H2D))
+    capi.check(lib.xtb_sync())
+    return a
+
+
+def _rows(xt, arr, r0, r1):
+    """Rows [r0, r1) of a dense 2-D array on the host (a device array is read block-wise, not as a whole)."""
+    if isinstance(arr, xt.HostArray):
+        return arr[r0:r1].numpy()
+    from xtensor_b200 import capi
+    lib = capi.lib()
+    assert arr.strides == xt.compute_strides(arr.shape) and arr.offset == 0
+    host = np.empty((r1 - r0, arr.shape[1]), dtype=xt.NP_OF[arr.dtype])
+    capi.check(lib.xtb_memcpy(C.c_void_p(host.ctypes.data), C.c_void_p(arr.owner.ptr + r0 * arr.shape[1] * host.itemsize),
+                              host.nbytes, capi.D2H))
+    capi.check(lib.xtb_sync())
+    return host
+
+
+def check_cfg1(xt, make, n):
+    rng = np.random.default_rng(1)
+    a, b = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    got = xt.evaluate(make(a) + make(b)).numpy()
+    assert got.dtype == np.float64 and np.array_equal(got, a + b)
+
+
+def check_cfg2(xt, make, n0):
+    rng = np.random.default_rng(3)
+    shape = (n0, 1024, 64)
+    a = rng.uniform(-np.pi, np.pi, shape).astype(F32)
+    b = rng.uniform(0.5, 1.5, (1, 1024, 1)).astype(F32)
+    d = rng.uniform(-np.pi, np.pi, shape).astype(F32)
+    got = xt.evaluate(xt.sin(make(a)) * make(b) + F32(2.0) * make(d)).numpy()
+    assert got.shape == shape and got.dtype == F32
+    sn = np.sin(a.astype(np.float64))
+    want = sn * b + 2.0 * d
+    # sin within 2 ulp, one rounding in the product, one in the sum (fp32, no contraction)
+    bound = (2 * np.spacing(np.abs(sn).astype(F32)).astype(np.float64) * np.abs(b) + np.spacing(np.abs(sn * b).astype(F32))
+             + np.spacing(np.maximum(np.abs(want).astype(F32), np.abs(got))))
+    assert float((np.abs(got - want) / bound).max()) <= 1.0
+
+
+def check_cfg3(xt, make, n0):
+    rng = np.random.default_rng(6)
+    x = rng.integers(-8, 9, (n0, 4096, 16), dtype=np.int8).astype(F32)      # |sum| <= 8 * n0 < 2^24: exact
+    X = make(x)
+    for axes in ([0], [2]):
+        got = xt.evaluate(xt.sum(X, axes)).numpy()
+        assert got.dtype == F32 and np.array_equal(got, x.sum(axis=axes[0], dtype=F32))
+        got = xt.evaluate(xt.amax(X, axes)).numpy()
+        assert np.array_equal(got, x.max(axis=axes[0]))
+
+
+def check_cfg4(xt, make, n):
+    rng = np.random.default_rng(7)
+    a, b = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (2 * n, n))
+    got = xt.evaluate(xt.transpose(make(a)) + xt.view(make(b), slice(0, None, 2), slice(None))).numpy()
+    assert np.array_equal(got, a.T + b[::2])
+
+
+def check_cfg5(xt, kind, blk_rows, reps, cols):
+    rng = np.random.default_rng(9)
+    blk = rng.integers(-8, 9, (blk_rows, cols)).astype(F32)
+    rows = blk_rows * reps
+    a = _tiled(xt, kind, blk, reps)
+    s = xt.evaluate(xt.sum(a, [0])).numpy()
+    s_blk = blk.sum(axis=0, dtype=np.float64)
+    assert np.array_equal(s, (reps * s_blk).astype(F32))                   # integers below 2^24: exact in any order
+    m = xt.evaluate(xt.mean(a, [0], dtype=xt.F32))
+    m32 = (reps * s_blk).astype(F32) / F32(rows)
+    assert np.array_equal(m.numpy(), m32)
+    v = xt.evaluate(xt.variance(a, [0], dtype=xt.F32)).numpy()
+    v_ref = np.square(blk.astype(np.float64) - m32.astype(np.float64)).mean(axis=0)
+    # against the fp64 value: fp32 accumulation over `rows` positive terms (sequential in the reference, per-split
+    # sequential + merge on the device) is itself only good to a few 1e-6; the 1e-6 parity bound against the
+    # reference's own fp32 order is tested on oracle-sized inputs in test_gpu_reduce.py
+    assert np.allclose(v, v_ref, rtol=2e-5, atol=0)
+    out = xt.evaluate(xt.exp(a - m))
+    first = _rows(xt, out, 0, blk_rows)
+    for r in sorted({1 % reps, reps // 2, reps - 1}):
+        assert np.array_equal(_rows(xt, out, r * blk_rows, (r + 1) * blk_rows), first)   # every copy of the block maps alike
+    arg32 = blk - m32                                                       # the same fp32 subtraction
+    assert float(_ulps(first, np.exp(arg32.astype(np.float64))).max()) <= 2.0
+
+
+def check_cumsum(xt, make, side):
+    rng = np.random.default_rng(2)
+    x = (rng.random((side, side)) < 0.2).astype(F32)                        # totals stay below 2^24: exact
+    X = make(x)
+    assert np.array_equal(xt.cumsum(X.reshape_view((side * side,))).numpy(), np.cumsum(x.reshape(-1), dtype=F32))
+    assert np.array_equal(xt.cumsum(X, 1).numpy(), np.cumsum(x, axis=1, dtype=F32))
+    assert np.array_equal(xt.cumsum(X, 0).numpy(), np.cumsum(x, axis=0, dtype=F32))
+
+
+# ---- reduced shapes, oracle as evaluator (CPU) ---------------------------------------------------------
+@pytest.fixture(scope="module")
+def H(xt):
+    return xt.HostArray.from_numpy
+
+
+def test_oracle_reduced_cfg1(xt, H): check_cfg1(xt, H, 1 << 12)
+def test_oracle_reduced_cfg2(xt, H): check_cfg2(xt, H, 2)
+def test_oracle_reduced_cfg3(xt, H): check_cfg3(xt, H, 8)
+def test_oracle_reduced_cfg4(xt, H): check_cfg4(xt, H, 96)
+def test_oracle_reduced_cfg5(xt): check_cfg5(xt, xt.HostArray, 64, 4, 256)
+def test_oracle_reduced_cumsum(xt, H): check_cumsum(xt, H, 96)
+
+
+# ---- full shapes on the device -------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def D(xt, gpu):
+    return xt.DeviceArray.from_numpy
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_gpu_full_cfg1(xt, D): check_cfg1(xt, D, 1 << 24)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_gpu_full_cfg2(xt, D): check_cfg2(xt, D, 1024)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_gpu_full_cfg3(xt, D): check_cfg3(xt, D, 4096)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_gpu_full_cfg4(xt, D): check_cfg4(xt, D, 8192)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_gpu_full_cfg5(xt, gpu): check_cfg5(xt, xt.DeviceArray, 4096, 64, 8192)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_gpu_full_cumsum(xt, D): check_cumsum(xt, D, 8192)
