@@ -54,6 +54,38 @@ def _check_misc(xt, make):
     assert_bit_exact(kd.reshape(6, 7), G["nansum_f64_ax1"])
 
 
+def _check_reference_kats(xt, make):
+    """Literal expectations of the reference's own tests (test/test_xnan_functions.cpp:38-120, 130-215)."""
+    nan, inf = np.nan, np.inf
+    a = np.array([[0, 1, 2, 3], [nan, nan, nan, nan], [3, nan, 1, nan]])
+    assert int(xt.evaluate(xt.count_nonnan(make(a))).numpy()) == 6                        # :60-64
+    assert np.array_equal(xt.evaluate(xt.count_nonnan(make(a), [0])).numpy(), np.array([2, 1, 2, 1], np.uint64))
+    assert np.array_equal(xt.evaluate(xt.count_nonnan(make(a), [1])).numpy(), np.array([4, 0, 2], np.uint64))
+    b = np.array([[nan, nan, 123], [0.5123, -inf, inf]])
+    fi = np.finfo(np.float64)
+    assert np.array_equal(xt.evaluate(xt.nan_to_num(make(b))).numpy(), np.array([[0, 0, 123], [0.5123, fi.min, fi.max]]))   # :76-99
+    aN = np.array([[nan, nan, 123, 3], [1, 2, nan, 3], [1, 1, nan, 3]])
+    aR = np.where(np.isnan(aN), 0.0, aN)
+    aP = np.where(np.isnan(aN), 1.0, aN)
+    aI = np.where(np.isnan(aN), fi.max, aN)
+    aA = np.where(np.isnan(aN), fi.tiny, aN)
+    for ax in (None, [0], [1]):
+        axis = None if ax is None else ax[0]
+        assert np.array_equal(xt.evaluate(xt.nansum(make(aN), ax)).numpy(), aR.sum(axis=axis))      # nansum(aN) == sum(aR)
+        assert np.array_equal(xt.evaluate(xt.nanprod(make(aN), ax)).numpy(), aP.prod(axis=axis))    # nanprod(aN) == prod(aP)
+        assert np.array_equal(xt.evaluate(xt.nanmin(make(aN), ax)).numpy(), aI.min(axis=axis))      # nanmin(aN) == amin(aI)
+        assert np.array_equal(xt.evaluate(xt.nanmax(make(aN), ax)).numpy(), aA.max(axis=axis))      # nanmax(aN) == amax(aA)
+    xN = np.array([[[nan, nan], [1, 2]], [[3, nan], [nan, 5]]])
+    for i in range(3):   # NAN_SENSITIVE_EQ: NaN exactly where no value exists along the axis
+        got = xt.evaluate(xt.nanmin(make(xN), [i])).numpy()
+        with np.errstate(all="ignore"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = np.nanmin(xN, axis=i)
+        assert np.array_equal(got, want, equal_nan=True)
+
+
 @pytest.fixture(scope="module")
 def H(xt):
     return xt.HostArray.from_numpy
@@ -75,6 +107,10 @@ def test_oracle_nan_misc(xt, H):
     _check_misc(xt, H)
 
 
+def test_oracle_reference_kats(xt, H):
+    _check_reference_kats(xt, H)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("ax", AXES, ids=lambda a: "ax" + "".join(map(str, a)))
 @pytest.mark.parametrize("tag", ["f32", "f64"])
@@ -86,3 +122,8 @@ def test_gpu_nan_reducers(xt, D, name, tag, ax):
 @pytest.mark.gpu
 def test_gpu_nan_misc(xt, D):
     _check_misc(xt, D)
+
+
+@pytest.mark.gpu
+def test_gpu_reference_kats(xt, D):
+    _check_reference_kats(xt, D)
