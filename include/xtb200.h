@@ -261,7 +261,8 @@ int  xtb_comm_info(int* rank, int* world);
  * handles, in rank order, to every rank, which calls xtb_comm_p2p_attach.  From then on
  * xtb_allreduce / xtb_reduce(..., allreduce=1) use one kernel over NVLink peer memory (partials added
  * in rank order: identical bits on every rank) instead of NCCL for such payloads.  Every rank must
- * finish xtb_comm_p2p_attach before any rank's next allreduce. */
+ * finish xtb_comm_p2p_attach before any rank's next allreduce.  xtb_comm_p2p_attach(NULL, 0) detaches (every
+ * payload goes through NCCL again); a rank whose attach failed must make all ranks detach. */
 int  xtb_comm_p2p_handle(void* handle64);
 int  xtb_comm_p2p_attach(const void* handles, int world);
 /* in-place allreduce of `count` elements of storage dtype `dtype` on the stream */

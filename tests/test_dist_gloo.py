@@ -83,3 +83,58 @@ def test_sharded_path_world2_gloo(xt):
     assert np.array_equal(np.concatenate([out[0]["sum1"], out[1]["sum1"]]), full.sum(axis=1))
     whole = xt.evaluate(xt.exp(H(full) - H(mvec))).numpy()
     assert np.array_equal(np.concatenate([out[0]["map"], out[1]["map"]]), whole)
+
+
+class _FakeLib:
+    """Stands in for libxtb200 in the rendezvous test: records the calls, rank `fail_rank` cannot map the windows."""
+
+    def __init__(self, rank, fail_rank):
+        self.rank, self.fail_rank, self.calls = rank, fail_rank, []
+
+    def xtb_comm_unique_id(self, buf): return 0
+    def xtb_comm_init(self, rank, world, ident): return 0
+    def xtb_comm_p2p_handle(self, h): return 0
+    def xtb_last_error(self): return b"mock"
+
+    def xtb_comm_p2p_attach(self, handles, world):
+        self.calls.append(world)
+        return 1 if (world > 0 and self.rank == self.fail_rank) else 0
+
+
+def _init_comm_worker(rank, world, port, fail_rank, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch.distributed as dist
+    from xtensor_b200 import capi, shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fake = _FakeLib(rank, fail_rank)
+    capi.lib = lambda: fake
+    attached = shard.init_comm(dist, rank, world)
+    q.put((rank, attached, fake.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_init_comm_is_collective(fail_rank):
+    """shard.init_comm: the peer-memory windows are attached on every rank or on none (a rank that cannot map them
+    makes all ranks detach and fall back to NCCL) -- otherwise the ranks would wait for each other on different routes."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_init_comm_worker, args=(r, 2, port, fail_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if fail_rank < 0:
+        assert res == [(0, True, [2]), (1, True, [2])]
+    else:
+        assert res == [(0, False, [2, 0]), (1, False, [2, 0])]

@@ -227,6 +227,10 @@ int xtb_comm_p2p_handle(void* handle64) {
 }
 
 int xtb_comm_p2p_attach(const void* handles, int world) {
+    if (!handles && world == 0) {   // detach: back to NCCL for every payload (all ranks must do the same)
+        g_p2p.ready = false;
+        return XTB_OK;
+    }
     if (!handles) XTB_FAIL(XTB_ERR_INVALID, "null handles");
     if (world != g_nccl.world || world > kP2pMaxWorld || !g_p2p.local) XTB_FAIL(XTB_ERR_INVALID, "xtb_comm_p2p_attach: call xtb_comm_init and xtb_comm_p2p_handle first (world <= %d)", kP2pMaxWorld);
     DeviceCtx* ctx;

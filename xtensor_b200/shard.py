@@ -57,12 +57,20 @@ def init_comm(dist, rank: int, world: int, p2p: Optional[bool] = None) -> bool:
         p2p = os.environ.get("XTB_NO_P2P") is None
     if not p2p or world > 8:
         return False
+    # every step is collective: a rank that cannot export or map a window makes ALL ranks fall back to NCCL
     h = C.create_string_buffer(64)
-    capi.check(lib.xtb_comm_p2p_handle(h))
+    ok = lib.xtb_comm_p2p_handle(h) == 0
     handles = [None] * world
-    dist.all_gather_object(handles, h.raw)
-    capi.check(lib.xtb_comm_p2p_attach(C.create_string_buffer(b"".join(handles), 64 * world), world))
-    dist.barrier()      # every rank attached before anyone's next allreduce
+    dist.all_gather_object(handles, h.raw if ok else None)
+    if all(x is not None for x in handles):
+        ok = lib.xtb_comm_p2p_attach(C.create_string_buffer(b"".join(handles), 64 * world), world) == 0
+    else:
+        ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, bool(ok))      # also the barrier: every rank attached before anyone's next allreduce
+    if not all(oks):
+        capi.check(lib.xtb_comm_p2p_attach(None, 0))
+        return False
     return True
 
 
