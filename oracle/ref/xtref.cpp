@@ -324,6 +324,30 @@ extern "C"
         return 0;
     }
 
+    // xt::average (core/xmath.hpp:1925-2010): weights 1-d along the (single) axis, or of the expression's shape
+    int xtref_average_f64(const double* in, int nd, const int64_t* shape, const double* w, int w_nd, const int64_t* w_shape,
+                          int n_axes, const int32_t* axes, double* out)
+    {
+        try
+        {
+            auto A = in_arr<double>(in, mk_shape(nd, shape));
+            auto W = in_arr<double>(w, mk_shape(w_nd, w_shape));
+            xt::xarray<double> r;
+            if (n_axes == 0)
+            {
+                r = xt::average(A, W);
+            }
+            else
+            {
+                std::vector<std::size_t> ax(axes, axes + n_axes);
+                r = xt::average(A, W, ax);
+            }
+            std::copy(r.begin(), r.end(), out);
+            return (int) r.size();
+        }
+        catch (std::exception& e) { g_err = e.what(); return -3; }
+    }
+
     // ---- accumulators --------------------------------------------------------------------------------
     extern "C++"
     {

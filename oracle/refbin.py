@@ -204,3 +204,14 @@ def nan_to_num(a):
     out = np.empty_like(a)
     lib().xtref_nan_to_num(int(a.dtype == np.float64), _p(a), _p(out), C.c_int64(a.size))
     return out
+
+
+def average(a, w, axes):
+    """xt::average(a, w[, axes]) on fp64; axes == [] is the whole-array form."""
+    a, w = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(w, np.float64)
+    out = np.empty(tuple(s for d, s in enumerate(a.shape) if d not in axes) if axes else (), np.float64)
+    r = lib().xtref_average_f64(_p(a), a.ndim, _i64(a.shape), _p(w), w.ndim, _i64(w.shape), len(axes), _i32(axes), _p(out))
+    if r < 0:
+        raise RuntimeError(lib().xtref_last_error().decode())
+    assert r == out.size
+    return out

@@ -46,6 +46,17 @@ def main():
     g["cnz_i32_in"] = i
     for ax in AXES:
         g[f"cnz_i32_ax{''.join(map(str, ax))}"] = refbin.count_nonzero_i32(i, ax)
+    # xt::average: weights along one axis / of the full shape / whole array (integer-valued: exact in any order)
+    a = rng.integers(-5, 6, (4, 6, 5)).astype(np.float64)
+    g["avg_in"] = a
+    for axis in range(3):
+        w = rng.integers(1, 5, a.shape[axis]).astype(np.float64)
+        g[f"avg_w1_ax{axis}"], g[f"avg_out1_ax{axis}"] = w, refbin.average(a, w, [axis])
+    wf = rng.integers(1, 5, a.shape).astype(np.float64)
+    g["avg_wfull"] = wf
+    for ax in ([0], [1, 2], [0, 1, 2]):
+        g[f"avg_outfull_ax{''.join(map(str, ax))}"] = refbin.average(a, wf, ax)
+    g["avg_outfull_all"] = refbin.average(a, wf, [])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_vectors_nan.npz")
     np.savez_compressed(path, **g)
     print(f"wrote {path}: {len(g)} arrays")

@@ -86,6 +86,24 @@ def _check_reference_kats(xt, make):
         assert np.array_equal(got, want, equal_nan=True)
 
 
+def _check_average(xt, make):
+    """xt::average (core/xmath.hpp:1925-2010) against the real reference; sums of small integers are exact, the one
+    division is the same IEEE operation."""
+    a = G["avg_in"]
+    for axis in range(3):
+        got = xt.evaluate(xt.average(make(a), make(G[f"avg_w1_ax{axis}"]), [axis])).numpy()
+        assert_bit_exact(got, G[f"avg_out1_ax{axis}"])
+    for ax in ([0], [1, 2], [0, 1, 2]):
+        got = xt.evaluate(xt.average(make(a), make(G["avg_wfull"]), ax)).numpy()
+        assert_bit_exact(got, G[f"avg_outfull_ax{''.join(map(str, ax))}"])
+    assert_bit_exact(xt.evaluate(xt.average(make(a), make(G["avg_wfull"]))).numpy(), G["avg_outfull_all"])
+    assert_bit_exact(xt.evaluate(xt.average(make(a))).numpy(), np.asarray(a.mean()))
+    with pytest.raises(RuntimeError, match="same shape as expression at axes"):
+        xt.average(make(a), make(np.ones(3)), [1])
+    with pytest.raises(RuntimeError, match="same shape as expression"):
+        xt.average(make(a), make(np.ones((4, 6, 4))), [0])
+
+
 @pytest.fixture(scope="module")
 def H(xt):
     return xt.HostArray.from_numpy
@@ -111,6 +129,10 @@ def test_oracle_reference_kats(xt, H):
     _check_reference_kats(xt, H)
 
 
+def test_oracle_average(xt, H):
+    _check_average(xt, H)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("ax", AXES, ids=lambda a: "ax" + "".join(map(str, a)))
 @pytest.mark.parametrize("tag", ["f32", "f64"])
@@ -127,3 +149,8 @@ def test_gpu_nan_misc(xt, D):
 @pytest.mark.gpu
 def test_gpu_reference_kats(xt, D):
     _check_reference_kats(xt, D)
+
+
+@pytest.mark.gpu
+def test_gpu_average(xt, D):
+    _check_average(xt, D)

@@ -783,6 +783,35 @@ def mean(e, axes=None, dtype=None, ddof=0, keep_dims=False):
     return s / _mean_divisor(e, s.shape, axes, dtype, ddof)
 
 
+def average(e, weights=None, axes=None, dtype=None):
+    """xt::average (core/xmath.hpp:1925-2010): sum<T>(e * w, axes) / sum<T>(w, axes, immediate), `w` 1-d along the
+    first given axis or of e's shape; without weights it is mean<T>(e)."""
+    e = as_expr(e)
+    if weights is None:
+        return mean(e, axes, dtype=dtype)
+    w = weights
+    if axes is None:
+        if tuple(w.shape) != tuple(e.shape):
+            raise RuntimeError("Weights need to have the same shape as expression.")
+        div = _run_reducer(sum(w, dtype=dtype), _leaf_kind(w) or DeviceArray, mode=1)
+        return sum(e * w, dtype=dtype) / div
+    nd = len(e.shape)
+    ax = [axes] if isinstance(axes, (int, np.integer)) else list(axes)
+    ax = [int(a) + nd if int(a) < 0 else int(a) for a in ax]
+    if len(w.shape) == 1:
+        if w.size != e.shape[ax[0]]:
+            raise RuntimeError("Weights need to have the same shape as expression at axes.")
+        bshape = [1] * nd
+        bshape[ax[0]] = w.size
+    else:
+        if tuple(w.shape) != tuple(e.shape):
+            raise RuntimeError("Weights with dim > 1 need to have the same shape as expression.")
+        bshape = list(e.shape)
+    wv = w.reshape_view(bshape)
+    scl = _run_reducer(sum(wv, ax, dtype=dtype), _leaf_kind(w) or DeviceArray, mode=1)
+    return sum(e * wv, ax, dtype=dtype) / scl
+
+
 def variance(e, axes=None, dtype=None, ddof=0):
     """Two-pass, as the reference (core/xmath.hpp:2082-2105): inner_mean =
     eval(mean<T>(e, axes, immediate)) -- the *immediate* evaluation order --, reshaped with
