@@ -357,6 +357,13 @@ def other_configs(lib, xt, capi, world, rank, dist, args):
             xt.assign(o3, e3)
             out["jit_hypot_div_f32_2^26"] = timed(lambda: xt.assign(o3, e3), 16 * n)
             del a3, o3, e3
+        if world == 1 and not args.quick:
+            # context only: xtensor's own CPU evaluation of the other configs on bounded samples (host cores)
+            try:
+                from oracle import refbin
+                out["cpu_reference_context"] = refbin.run_context()
+            except Exception as ex:
+                out["cpu_reference_context"] = {"error": repr(ex)}
         # cfg5: sharded (262144, 8192) fp32: mean / variance over axis 0 (allreduce) + exp(a - mean)
         rows = args.cfg5_rows or 262144 // world
         cols = 8192

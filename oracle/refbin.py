@@ -171,6 +171,39 @@ def run_cfg2(sample_rows: int):
                    "-DXTENSOR_USE_OPENMP, xtl stand-in, no xsimd); this expression runs xtensor's single-threaded stepper_assigner"}
 
 
+def run_context():
+    """Timed context numbers for bench.py (reported next to the device numbers, not a target): xtensor's own CPU
+    evaluation of the other BASELINE configs on bounded samples, libxtref_fast.so (OpenMP build: the linear and
+    strided-loop assigners use all host threads, the stepper assigner and reduce_immediate are single-threaded)."""
+    if not available(fast=True):
+        return None
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    rng = np.random.default_rng(11)
+    res = {"threads": threads, "library": "oracle/_ref/libxtref_fast.so (real xtensor 0.27.1, -O3 -march=x86-64-v3 -fopenmp -DXTENSOR_USE_OPENMP, no xsimd)"}
+
+    def best(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    n = 1 << 24
+    a, b = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    res["cfg1_add_f64_2^24"] = {"GBs": round(3 * n * 8 / best(lambda: cfg1(a, b, fast=True)) / 1e9, 2), "path": "linear_assigner (OpenMP)"}
+    x = rng.uniform(-1, 1, (256, 4096, 16)).astype(np.float32)
+    for axis in (0, 2):
+        dt = best(lambda: reduce(0, x, [axis], mode=1, fast=True), reps=2)
+        res[f"cfg3_sum_axis{axis}_sample_256x4096x16"] = {"GBs": round(x.nbytes / dt / 1e9, 2), "path": "reduce_immediate (1 thread)"}
+    m = 2048
+    a4, b4 = rng.uniform(-1, 1, (m, m)), rng.uniform(-1, 1, (2 * m, m))
+    res["cfg4_transpose_view_f64_sample_2048"] = {"GBs": round(3 * m * m * 8 / best(lambda: cfg4(a4, b4, fast=True), reps=2) / 1e9, 2),
+                                                   "path": "stepper_assigner (1 thread)"}
+    return res
+
+
 def nanfn(name, a, axes):
     """xt::nansum / nanprod / nanmin / nanmax / nanmean / nanvar / nanstd / count_nonzero / count_nonnan over `axes`
     ("nanmean_t" / "nanvar_t": result type = input type)."""
