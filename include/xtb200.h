@@ -243,6 +243,25 @@ int  xtb_reduce(int op, int acc_type, const xtb_program* program,
                 int n_axes, const int32_t* axes, int keep_dims,
                 const void* initial, const xtb_operand* out, int allreduce);
 
+/* xtb_reduce with a finalize step fused into the last store, applied once after every merge (including the
+ * cross-GPU one): the `finalize` of the reference's blockwise reducer functors
+ * (include/xtensor/reducers/xblockwise_reducer_functors.hpp:146-186, 246-258) and the division of
+ * xt::mean / xt::variance (include/xtensor/core/xmath.hpp:1827-1852, 2082-2105).
+ *   out = static_cast<out.dtype>( T(acc) / imm )            XTB_FIN_DIV
+ *   out = static_cast<out.dtype>( sqrt(T(acc) / imm) )      XTB_FIN_DIV_SQRT   (xt::stddev)
+ * with T = `type` (XTB_F32 or XTB_F64) and imm the divisor's bits in T.  fin == NULL: plain xtb_reduce. */
+typedef enum { XTB_FIN_NONE = 0, XTB_FIN_DIV = 1, XTB_FIN_DIV_SQRT = 2 } xtb_finalize_op;
+typedef struct {
+    int32_t  op;     /* xtb_finalize_op */
+    int32_t  type;   /* XTB_F32 / XTB_F64 */
+    uint64_t imm;    /* divisor, raw bits in `type` (f32 in the low 32 bits) */
+} xtb_finalize;
+int  xtb_reduce_fin(int op, int acc_type, const xtb_program* program,
+                    const xtb_operand* leaves, int ndim, const int64_t* shape,
+                    int n_axes, const int32_t* axes, int keep_dims,
+                    const void* initial, const xtb_operand* out, int allreduce,
+                    const xtb_finalize* fin);
+
 /* inclusive scan (cumsum: op = XTB_RED_SUM, cumprod: XTB_RED_PROD) of `in` along
  * `axis`, or over the flattened row-major traversal when axis < 0.  out has the
  * shape of in (or is 1-D of in's size when axis < 0) and dtype = acc_type.      */
@@ -268,7 +287,16 @@ int  xtb_comm_p2p_attach(const void* handles, int world);
 /* in-place allreduce of `count` elements of storage dtype `dtype` on the stream */
 int  xtb_allreduce(void* buf, size_t count, int dtype, int op);
 
+/* ---- process options ------------------------------------------------------- */
+/* The XTB_* environment switches are read once, at first use; afterwards they are changed through this call
+ * (name = the variable without the XTB_ prefix, lower case: "no_static", "no_jit", "no_staged", "no_tma",
+ * "jit_min_elems", "jit_verbose", "scan_variant", "tile_variant").  xtb_get_option returns -1 for unknown names. */
+int  xtb_set_option(const char* name, long long value);
+long long xtb_get_option(const char* name);
+
 /* ---- introspection (tests, bench.py) --------------------------------------- */
+/* kernel nodes of an instantiated graph (each replay counts that many launches) */
+int  xtb_graph_kernel_count(void* graph_exec);
 /* number of kernels launched by this library since the last reset            */
 int64_t xtb_launch_count(int reset);
 /* name of the kernel variant the last xtb_assign/xtb_reduce/xtb_scan selected  */

@@ -12,11 +12,16 @@ pytestmark = pytest.mark.gpu
 F32, F64 = np.float32, np.float64
 
 
+def _set_min(v):
+    from xtensor_b200 import capi
+    capi.check(capi.lib().xtb_set_option(b"jit_min_elems", v))
+
+
 @pytest.fixture(autouse=True)
 def force_jit():
-    os.environ["XTB_JIT_MIN_ELEMS"] = "0"
+    _set_min(0)
     yield
-    del os.environ["XTB_JIT_MIN_ELEMS"]
+    _set_min(1 << 20)
 
 
 def rnd(shape, dtype=F32, lo=-2.0, hi=2.0, seed=0):
@@ -74,7 +79,7 @@ def test_fused_map_reduce_jit(xt, gpu):
 
 
 def test_large_expression_uses_jit_by_default(xt, gpu):
-    del os.environ["XTB_JIT_MIN_ELEMS"]
+    _set_min(1 << 20)
     try:
         a = rnd((1 << 21,), F32, seed=8)
         got, want = run_both(xt, lambda A: xt.sqrt(A * A + F32(1.0)) - xt.abs(A), a)
@@ -84,4 +89,4 @@ def test_large_expression_uses_jit_by_default(xt, gpu):
         run_both(xt, lambda A: xt.sqrt(A * A + F32(1.0)) - xt.abs(A), small)
         assert "jit" not in last_kernel()           # below the threshold: interpreter kernel
     finally:
-        os.environ["XTB_JIT_MIN_ELEMS"] = "0"
+        _set_min(0)

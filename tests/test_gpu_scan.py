@@ -137,3 +137,57 @@ def test_tiled_kernels_fp_tolerance_and_determinism(xt, gpu):
         ref = np.cumsum(a.astype(np.float64), axis=axis).reshape(g1.shape)
         scale = np.cumsum(np.abs(a).astype(np.float64), axis=axis).reshape(g1.shape)
         assert np.all(np.abs(g1 - ref) <= 1e-6 * np.maximum(scale, 1.0))
+
+
+# ---- round 2 kernels: reduce-ahead scan (k_scan_ahead) and column walkers (k_scan_colwalk) --------------
+AHEAD = [
+    ((16384 * 4 + 1,), None), ((4096 * 33 + 7,), None), ((4096 * 1030 + 12,), None),     # 1-, 2- and 3-level aggregate trees
+    ((1 << 24,), None), ((3, 4096 * 70 + 4), 1), ((2, 4096 * 1100), 1), ((5, 16385 * 4), 1),
+]
+
+
+@pytest.mark.parametrize("shape,axis", AHEAD)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+def test_reduce_ahead_scan(xt, gpu, shape, axis, dtype):
+    from util import last_kernel
+    a = np.random.default_rng(21).integers(-3, 4, shape).astype(dtype)
+    got = xt.cumsum(xt.DeviceArray.from_numpy(a), axis).numpy()
+    if np.prod(shape[-1:]) * a.itemsize > 64 * 1024:
+        assert "k_scan_ahead" in last_kernel(), last_kernel()
+    assert_bit_exact(got, np.cumsum(a, axis=axis, dtype=got.dtype).reshape(got.shape))
+
+
+def test_reduce_ahead_scan_views_and_prod(xt, gpu):
+    rng = np.random.default_rng(22)
+    a = rng.integers(-3, 4, (3, 200003)).astype(np.int16)                       # converted input, unaligned rows
+    assert_bit_exact(xt.cumsum(xt.DeviceArray.from_numpy(a), 1).numpy(), np.cumsum(a, axis=1, dtype=np.int32))
+    b = rng.integers(-3, 4, (2, 300000)).astype(np.float32)
+    d = xt.DeviceArray.from_numpy(b)
+    assert_bit_exact(xt.cumsum(d[:, 5:], 1).numpy(), np.cumsum(b[:, 5:], axis=1))                # unaligned view
+    assert_bit_exact(xt.cumsum(d[:, ::2], 1).numpy(), np.cumsum(b[:, ::2], axis=1))              # strided view
+    c = np.ones(1 << 20, np.float64)
+    c[::4099] = 2.0
+    c[1::4099] = 0.5
+    assert_bit_exact(xt.cumprod(xt.DeviceArray.from_numpy(c)).numpy(), np.cumprod(c))
+
+
+WALK = [((300, 4736), 0), ((1000, 9472 + 4), 0), ((2, 257, 8192), 1), ((513, 148 * 128), 0), ((4097, 5000), 0)]
+
+
+@pytest.mark.parametrize("shape,axis", WALK)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+def test_column_walkers(xt, gpu, shape, axis, dtype):
+    from util import last_kernel
+    rng = np.random.default_rng(23)
+    a = rng.integers(-3, 4, shape).astype(dtype)
+    got = xt.cumsum(xt.DeviceArray.from_numpy(a), axis).numpy()
+    assert "k_scan_colwalk" in last_kernel(), last_kernel()
+    assert_bit_exact(got, np.cumsum(a, axis=axis, dtype=got.dtype))
+    if dtype in (np.float32, np.float64):
+        # walkers accumulate every column in the reference's order: random fp data is bit-exact against the oracle too
+        b = rng.uniform(-1, 1, (shape[0] if len(shape) == 2 else shape[0], *shape[1:])).astype(dtype)
+        g, w = both(xt, b, axis)
+        assert_bit_exact(g, w)
+        b[0] = -0.0                                            # out[0] = in[0]: a leading -0.0 survives
+        g, w = both(xt, b, axis)
+        assert_bit_exact(g, w)

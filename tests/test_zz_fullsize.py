@@ -104,17 +104,44 @@ def check_cfg5(xt, kind, blk_rows, reps, cols):
     m32 = (reps * s_blk).astype(F32) / F32(rows)
     assert np.array_equal(m.numpy(), m32)
     v = xt.evaluate(xt.variance(a, [0], dtype=xt.F32)).numpy()
-    v_ref = np.square(blk.astype(np.float64) - m32.astype(np.float64)).mean(axis=0)
-    # against the fp64 value: fp32 accumulation over `rows` positive terms (sequential in the reference, per-split
-    # sequential + merge on the device) is itself only good to a few 1e-6; the 1e-6 parity bound against the
-    # reference's own fp32 order is tested on oracle-sized inputs in test_gpu_reduce.py
-    assert np.allclose(v, v_ref, rtol=2e-5, atol=0)
+    v64 = np.square(blk.astype(np.float64) - m32.astype(np.float64)).mean(axis=0)       # fp64 truth of the same two passes
+    err = np.abs(v.astype(np.float64) - v64) / v64
+    # Contract: every term is positive, so sum|x| / |sum x| = 1 and the north-star bound
+    # "1e-6 relative" applies to the distance from the exact value.  A split reduction is summed in blocks of 32
+    # rows (fp32 chains of <= 32 + ~60 + ~20 terms), so the device must sit within 1e-6 of fp64 truth ...
+    # (the CPU twin of this test evaluates with the oracle = the reference's sequential order: worst case rows * eps / 2)
+    bound = 1e-6 if kind is xt.DeviceArray else max(1e-6, rows * 6e-8)
+    assert float(err.max()) <= bound, f"variance: max relative error vs fp64 {err.max():.3e}"
+    # ... and, measured against the REAL reference on the same rows (its sequential fp32 order drifts by up to
+    # ~1e-3 over 262144 rows), the device must be at least as close to the truth as the reference is.
+    ref_cols = min(cols, 256)
+    v_ref = _reference_variance(xt, kind, blk, reps, ref_cols)
+    if v_ref is not None:
+        err_ref = np.abs(v_ref.astype(np.float64) - v64[:ref_cols]) / v64[:ref_cols]
+        assert float(err[:ref_cols].max()) <= max(float(err_ref.max()), 1e-6), (float(err[:ref_cols].max()), float(err_ref.max()))
+        # both are the same quantity: they agree to the reference's own accuracy
+        assert np.allclose(v[:ref_cols], v_ref, rtol=max(4 * float(err_ref.max()), 1e-6), atol=0)
+        if kind is xt.HostArray:
+            assert np.array_equal(v[:ref_cols], v_ref)     # the oracle IS the reference's order, bit for bit
     out = xt.evaluate(xt.exp(a - m))
     first = _rows(xt, out, 0, blk_rows)
     for r in sorted({1 % reps, reps // 2, reps - 1}):
         assert np.array_equal(_rows(xt, out, r * blk_rows, (r + 1) * blk_rows), first)   # every copy of the block maps alike
     arg32 = blk - m32                                                       # the same fp32 subtraction
     assert float(_ulps(first, np.exp(arg32.astype(np.float64))).max()) <= 2.0
+
+
+def _reference_variance(xt, kind, blk, reps, ncols):
+    """xt::variance<float>(a, {0}) of the REAL reference (oracle/_ref, prebuilt) on the first `ncols` columns of the
+    tiled matrix: columns are independent, so this is the reference's result for those columns of the full array."""
+    try:
+        from oracle import refbin
+        if not refbin.available():
+            return None
+    except Exception:
+        return None
+    sub = np.ascontiguousarray(np.tile(blk[:, :ncols], (reps, 1)))
+    return refbin.variance(sub, [0])
 
 
 def check_cumsum(xt, make, side):

@@ -44,11 +44,12 @@ def assert_bit_exact(got, want):
 @contextmanager
 def interpreter_only():
     """Force the run-time interpreter kernels (no compile-time program match)."""
-    os.environ["XTB_NO_STATIC"] = "1"
+    from xtensor_b200 import capi
+    capi.check(capi.lib().xtb_set_option(b"no_static", 1))
     try:
         yield
     finally:
-        del os.environ["XTB_NO_STATIC"]
+        capi.check(capi.lib().xtb_set_option(b"no_static", 0))
 
 
 def last_kernel():

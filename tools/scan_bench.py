@@ -35,23 +35,30 @@ CASES = [
     ((1 << 20, 64), 1, np.float32), ((1 << 17, 512), 1, np.float32), ((64, 1 << 20), 1, np.float32), ((64, 1 << 20), 0, np.float32),
     ((1 << 20, 64), 0, np.float32), ((256, 512, 512), 1, np.float32), ((1 << 26,), None, np.uint8),
 ]
-only = sys.argv[1:]
-for shape, axis, dt in CASES:
-    tag = f"{'x'.join(map(str, shape))}:{axis}:{np.dtype(dt).name}"
-    if only and not any(o in tag for o in only):
-        continue
-    rng = np.random.default_rng(1)
-    n = int(np.prod(shape))
-    a = rng.integers(-3, 4, n).astype(dt).reshape(shape) if dt != np.uint8 else rng.integers(0, 2, n).astype(dt).reshape(shape)
-    d = xt.DeviceArray.from_numpy(a)
-    res = xt.cumsum(d, axis)
+only = [a for a in sys.argv[1:] if not a.startswith("--")]
+variants = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--variant=")] or [0]
+for a in sys.argv[1:]:
+    if a.startswith("--nv="):
+        capi.check(lib.xtb_set_option(b"scan_nv", int(a.split("=")[1])))
+for variant in variants:
+  capi.check(lib.xtb_set_option(b"scan_variant", variant))
+  print(f"# scan_variant={variant} (>0: look-ahead MB of k_scan_ahead, <0: ring stages of k_scan_colwalk)", flush=True)
+  for shape, axis, dt in CASES:
+      tag = f"{'x'.join(map(str, shape))}:{axis}:{np.dtype(dt).name}"
+      if only and not any(o in tag for o in only):
+          continue
+      rng = np.random.default_rng(1)
+      n = int(np.prod(shape))
+      a = rng.integers(-3, 4, n).astype(dt).reshape(shape) if dt != np.uint8 else rng.integers(0, 2, n).astype(dt).reshape(shape)
+      d = xt.DeviceArray.from_numpy(a)
+      res = xt.cumsum(d, axis)
 
-    def f():
-        xt.cumsum(d, axis, out=res)
+      def f():
+          xt.cumsum(d, axis, out=res)
 
-    ms = timed(f)
-    r = res.numpy()
-    want = np.cumsum(a, axis=axis, dtype=r.dtype)
-    ok = np.array_equal(r, want.reshape(r.shape))
-    nbytes = n * (a.itemsize + r.itemsize)
-    print(f"{tag:32s} {ms:8.4f} ms {nbytes / ms / 1e6:8.1f} GB/s  ok={ok}  {lib.xtb_last_kernel().decode()}", flush=True)
+      ms = timed(f)
+      r = res.numpy()
+      want = np.cumsum(a, axis=axis, dtype=r.dtype)
+      ok = np.array_equal(r, want.reshape(r.shape))
+      nbytes = n * (a.itemsize + r.itemsize)
+      print(f"{tag:32s} {ms:8.4f} ms {nbytes / ms / 1e6:8.1f} GB/s  ok={ok}  {lib.xtb_last_kernel().decode()}", flush=True)

@@ -46,6 +46,14 @@ class Program(C.Structure):
                 ("insns", Insn * MAX_INSNS), ("imms", C.c_uint64 * MAX_IMMS)]
 
 
+class Finalize(C.Structure):
+    """xtb_finalize: the step fused into the last store of a reduction (include/xtb200.h)."""
+    _fields_ = [("op", C.c_int32), ("type", C.c_int32), ("imm", C.c_uint64)]
+
+
+FIN_NONE, FIN_DIV, FIN_DIV_SQRT = 0, 1, 2
+
+
 class XtbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"xtb status {code}: {msg}")
@@ -62,6 +70,7 @@ SYMBOLS = [
     "xtb_graph_begin", "xtb_graph_end", "xtb_graph_launch", "xtb_graph_destroy", "xtb_fork_begin", "xtb_fork_end", "xtb_fork_join",
     "xtb_assign", "xtb_assign_host", "xtb_reduce", "xtb_scan", "xtb_comm_unique_id", "xtb_comm_init", "xtb_comm_destroy",
     "xtb_comm_info", "xtb_comm_p2p_handle", "xtb_comm_p2p_attach", "xtb_allreduce", "xtb_launch_count", "xtb_last_kernel", "xtb_program_result_type",
+    "xtb_reduce_fin", "xtb_set_option", "xtb_get_option", "xtb_graph_kernel_count",
 ]
 
 _LIB = None
@@ -111,6 +120,11 @@ def lib():
         "xtb_assign_host": (i32, [C.POINTER(Program), C.POINTER(Operand), C.POINTER(Operand), i64]),
         "xtb_reduce": (i32, [i32, i32, C.POINTER(Program), C.POINTER(Operand), i32, C.POINTER(i64), i32,
                              C.POINTER(C.c_int32), i32, vp, C.POINTER(Operand), i32]),
+        "xtb_reduce_fin": (i32, [i32, i32, C.POINTER(Program), C.POINTER(Operand), i32, C.POINTER(i64), i32,
+                                 C.POINTER(C.c_int32), i32, vp, C.POINTER(Operand), i32, C.POINTER(Finalize)]),
+        "xtb_set_option": (i32, [C.c_char_p, C.c_longlong]),
+        "xtb_get_option": (C.c_longlong, [C.c_char_p]),
+        "xtb_graph_kernel_count": (i32, [vp]),
         "xtb_scan": (i32, [i32, i32, C.POINTER(Operand), i32, C.POINTER(Operand)]),
         "xtb_comm_unique_id": (i32, [vp]),
         "xtb_comm_init": (i32, [i32, i32, vp]),

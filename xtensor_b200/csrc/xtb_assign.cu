@@ -15,7 +15,7 @@ template <class S, int V> static int launch_interp(const EwParams& p, DeviceCtx*
 static bool ew_nd_ok_rank(int nd) { return nd <= 3; }
 
 static int dispatch_tile(const xtb_program* prog, const EwParams& p, DeviceCtx* ctx, bool w64) {
-    const bool no_static = getenv("XTB_NO_STATIC") != nullptr;
+    const bool no_static = options().no_static != 0;
     if (!no_static) {
         const StaticEntry* e = find_static(prog);
         if (e && sprogs::is64(*e->prog) == w64) return e->launch_tile(p, ctx);
@@ -33,9 +33,10 @@ static int dispatch_tile(const xtb_program* prog, const EwParams& p, DeviceCtx* 
                 if (d != p.tile_i) batch *= p.shape[d];
             const int64_t blocks = batch * p.ntile_i * p.ntile_j;
             if (blocks < 0x7fffffffLL) {
-                XTB_TRY(jit_launch(fn, (unsigned) blocks, 1, 256, 0, ctx->stream, &p));
-                note_launch(w64 ? "k_ew_tile_static<jit,S64>" : "k_ew_tile_static<jit,S32>");
-                return XTB_OK;
+                if (jit_launch(fn, (unsigned) blocks, 1, 256, 0, ctx->stream, &p) == XTB_OK) {
+                    note_launch(w64 ? "k_ew_tile_static<jit,S64>" : "k_ew_tile_static<jit,S32>");
+                    return XTB_OK;
+                }   // a failed launch falls through to the interpreter kernel
             }
         }
     }
@@ -44,7 +45,7 @@ static int dispatch_tile(const xtb_program* prog, const EwParams& p, DeviceCtx* 
 }
 
 static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ctx, bool w64, int V) {
-    const bool no_static = getenv("XTB_NO_STATIC") != nullptr;  // tests toggle this per call
+    const bool no_static = options().no_static != 0;
     if (!no_static && ew_nd_ok(p)) {
         const StaticEntry* e = find_static(prog);
         if (e) {
@@ -69,12 +70,13 @@ static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ct
             q.fast = fast;
             char name[96];
             snprintf(name, sizeof(name), "k_ew<jit,S%d,V%d,ND%d>%s", w64 ? 64 : 32, V, p.ndim, fast ? "[fast]" : "");
-            XTB_TRY(jit_launch(fn, (unsigned) ((p.total_vec + per_block - 1) / per_block), 1, 256, 0, ctx->stream, &q));
-            note_launch(name);
-            return XTB_OK;
+            if (jit_launch(fn, (unsigned) ((p.total_vec + per_block - 1) / per_block), 1, 256, 0, ctx->stream, &q) == XTB_OK) {
+                note_launch(name);
+                return XTB_OK;
+            }   // a failed launch falls through to the interpreter kernel
         }
     }
-    if (p.idx32 && p.total_vec < (int64_t) 0x7fffffff && getenv("XTB_NO_STAGED") == nullptr) {
+    if (p.idx32 && p.total_vec < (int64_t) 0x7fffffff && !options().no_staged) {
         // run-time program with 32-bit offsets: staged interpreter (cp.async operand staging)
         EwParams q = p;
         for (int k = 0; k < q.n_leaves; ++k) if (q.leaf[k].mode == MODE_LINEAR) q.leaf[k].mode = MODE_VEC;

@@ -155,6 +155,8 @@ template <class T> static int launch_p2p(DeviceCtx* ctx, void* buf, size_t count
     return check_launch("k_allreduce_p2p");
 }
 
+int comm_world() { return g_nccl.world; }
+
 int comm_allreduce(DeviceCtx* ctx, void* buf, size_t count, int dtype, int op) {
     if (g_nccl.world <= 1 && !g_nccl.comm) return XTB_OK;  // single rank: nothing to merge
     if (!g_nccl.comm) XTB_FAIL(XTB_ERR_NCCL, "xtb_comm_init has not been called");

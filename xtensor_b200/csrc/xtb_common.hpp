@@ -45,7 +45,26 @@ struct DeviceCtx {
     bool forked = false;
     void* fork_scratch = nullptr;        // calls on the fork stream get their own scratch
     size_t fork_scratch_bytes = 0;
+    // the stream whose work last touched `scratch`: a call on another stream first waits for it
+    cudaStream_t scratch_stream = nullptr;
+    cudaEvent_t scratch_ev = nullptr;
 };
+// ---- process options -----------------------------------------------------------
+// Read from the environment ONCE (first use) and changeable through xtb_set_option; the dispatchers never
+// call getenv.  Names are the environment variables without the XTB_ prefix, lower case.
+struct Options {
+    int no_static = 0;        // XTB_NO_STATIC: skip the ahead-of-time instantiations (tests: evaluators agree)
+    int no_jit = 0;           // XTB_NO_JIT: skip run-time specialisation
+    int no_staged = 0;        // XTB_NO_STAGED: interpreter without cp.async staging
+    int no_tma = 0;           // XTB_NO_TMA: tile kernels fetch with plain / bulk copies
+    int jit_verbose = 0;      // XTB_JIT_VERBOSE
+    long long jit_min_elems = 1 << 20;   // XTB_JIT_MIN_ELEMS: problems below this size use the interpreter
+    int scan_variant = 0;     // XTB_SCAN_VARIANT: development switch of xtb_scan
+    int scan_nv = 0;          // XTB_SCAN_NV: 128-bit vectors per thread of k_scan_ahead (4 or 8)
+    int tile_variant = 0;     // XTB_TILE_VARIANT: development switch of the transposed-leaf kernel
+};
+Options& options();
+
 // Context of the calling thread's device; fails with XTB_ERR_NO_DEVICE when
 // there is no GPU.  (No CPU fallback by design.)
 int get_ctx(DeviceCtx** ctx);

@@ -59,7 +59,6 @@ void* sym(void* h, const char* name) { return h ? dlsym(h, name) : nullptr; }
 bool load_api(const DeviceCtx* ctx) {
     if (g_api.tried) return g_api.ok;
     g_api.tried = true;
-    if (getenv("XTB_NO_JIT")) return false;
     void* rtc = nullptr;
     const char* rtc_names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
     for (const char* n : rtc_names) {
@@ -123,16 +122,17 @@ bool jit_program_ok(const xtb_program* p) { return p->n_insns <= XTB_MAX_INSNS; 
 // A compile costs ~2 s: only worth it when the problem is large (the interpreter kernels finish a
 // small problem in microseconds).  XTB_JIT_MIN_ELEMS overrides the threshold (tests use 0).
 bool jit_worthwhile(int64_t elements) {
-    const char* e = getenv("XTB_JIT_MIN_ELEMS");   // read per call: tests toggle it
-    return elements >= (e ? (int64_t) atoll(e) : (int64_t) 1 << 20);
+    return elements >= (int64_t) options().jit_min_elems;
 }
 
 int jit_get(const DeviceCtx* ctx, const xtb_program* prog, const JitSpec& spec, void** fn) {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (!load_api(ctx)) return XTB_ERR_UNSUPPORTED;
+    if (options().no_jit || !load_api(ctx)) return XTB_ERR_UNSUPPORTED;
     std::string key((const char*) prog->insns, sizeof(xtb_insn) * prog->n_insns);
     char tail[96];
-    snprintf(tail, sizeof(tail), "|%d|%d|%d|%d|%d|%d|%d", spec.kind, spec.w64, spec.V, spec.nd, spec.binop, spec.acc_rt, prog->n_leaves);
+    // the CUfunction belongs to the primary context of the device it was loaded on: the device is part of the key
+    snprintf(tail, sizeof(tail), "|%d|%d|%d|%d|%d|%d|%d|dev%d", spec.kind, spec.w64, spec.V, spec.nd, spec.binop, spec.acc_rt, prog->n_leaves,
+             ctx->device);
     key += tail;
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
@@ -162,7 +162,16 @@ int jit_get(const DeviceCtx* ctx, const xtb_program* prog, const JitSpec& spec, 
     const std::string source = src.str(), expr = name.str();
     if (g_api.create(&prog_h, source.c_str(), "xtb_jit.cu", 0, nullptr, nullptr) != 0) return XTB_ERR_UNSUPPORTED;
     g_api.add_name(prog_h, expr.c_str());
-    const std::string inc1 = "-I" + g_api.csrc_dir, inc2 = "-I" + g_api.cuda_inc, arch = "--gpu-architecture=" + g_api.arch;
+    std::string dev_arch = g_api.arch;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) {
+            char a[32];
+            snprintf(a, sizeof(a), "sm_%d%d%s", prop.major, prop.minor, prop.major >= 9 ? "a" : "");
+            dev_arch = a;
+        }
+    }
+    const std::string inc1 = "-I" + g_api.csrc_dir, inc2 = "-I" + g_api.cuda_inc, arch = "--gpu-architecture=" + dev_arch;
     const char* opts[] = {arch.c_str(), "--std=c++20", inc1.c_str(), inc2.c_str(), "--fmad=false", "-default-device"};
     const int rc = g_api.compile(prog_h, 6, opts);
     ++g_compiles;
@@ -173,7 +182,7 @@ int jit_get(const DeviceCtx* ctx, const xtb_program* prog, const JitSpec& spec, 
             log.resize(n);
             g_api.log(prog_h, log.data());
         }
-        if (getenv("XTB_JIT_VERBOSE")) fprintf(stderr, "[xtb jit] compile failed for %s:\n%s\n", expr.c_str(), log.c_str());
+        if (options().jit_verbose) fprintf(stderr, "[xtb jit] compile failed for %s:\n%s\n", expr.c_str(), log.c_str());
         g_api.destroy(&prog_h);
         return set_error(XTB_ERR_UNSUPPORTED, "jit compile failed: %.300s", log.c_str());
     }
@@ -193,7 +202,7 @@ int jit_get(const DeviceCtx* ctx, const xtb_program* prog, const JitSpec& spec, 
         return set_error(XTB_ERR_UNSUPPORTED, "jit: module load failed");
     }
     g_api.destroy(&prog_h);
-    if (getenv("XTB_JIT_VERBOSE")) fprintf(stderr, "[xtb jit] compiled %s\n", expr.c_str());
+    if (options().jit_verbose) fprintf(stderr, "[xtb jit] compiled %s\n", expr.c_str());
     g_cache[key] = func;
     *fn = func;
     return XTB_OK;

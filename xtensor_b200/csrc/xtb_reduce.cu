@@ -13,6 +13,7 @@
 namespace xtb {
 
 int comm_allreduce(DeviceCtx* ctx, void* buf, size_t count, int dtype, int op);  // xtb_comm.cu
+int comm_world();                                                                 // xtb_comm.cu
 bool comm_p2p_params(DeviceCtx* ctx, P2pParams* w);                               // xtb_comm.cu
 
 static uint64_t identity_bits(int op, int rt) {
@@ -61,7 +62,7 @@ static int binop_of(int op) {
 }
 
 static int run_reduce_kernel(const xtb_program* prog, const RdParams& p, DeviceCtx* ctx, bool inner, bool w64, int V) {
-    const bool no_static = getenv("XTB_NO_STATIC") != nullptr;  // tests toggle this per call
+    const bool no_static = options().no_static != 0;
     if (!no_static && p.in_rt == p.acc_rt && V == (w64 ? 2 : 4) && p.K < 0x7fffffff) {
         const StaticReduceTable t = static_reduce_table();
         for (int i = 0; i < t.n; ++i) {
@@ -84,9 +85,10 @@ static int run_reduce_kernel(const xtb_program* prog, const RdParams& p, DeviceC
         spec.acc_rt = p.acc_rt;
         void* fn = nullptr;
         if (jit_get(ctx, prog, spec, &fn) == XTB_OK) {
-            XTB_TRY(jit_launch(fn, g.gx, g.gy, 256, 0, ctx->stream, &p));
-            note_launch(names[g.kind]);
-            return XTB_OK;
+            if (jit_launch(fn, g.gx, g.gy, 256, 0, ctx->stream, &p) == XTB_OK) {
+                note_launch(names[g.kind]);
+                return XTB_OK;
+            }   // a failed launch falls through to the interpreter kernel
         }
     }
     if (w64) {
@@ -99,23 +101,22 @@ static int run_reduce_kernel(const xtb_program* prog, const RdParams& p, DeviceC
 
 struct ReducePlanIn {
     const xtb_program* prog;
-    xtb_program own_prog;  // storage for the merge pass's program
     bool empty = false;    // a reduced extent is 0: every output is init
     int n_leaves;
     const char* leaf_ptr[XTB_MAX_LEAVES];
     int leaf_dtype[XTB_MAX_LEAVES];
     Space space;       // operands: leaves..., out (index n_leaves); reduced[] flags set
+    int op;            // xtb_reduce_op
     int binop, acc_rt, in_rt;
     bool w64;
     char* out_ptr;
     int out_dtype;
     bool has_initial;
     uint64_t initial_bits, identity;
-    bool want_xchg = false;   // in: the caller asked for the cross-GPU merge of the result
-    bool xchg_done = false;   // out: the merge pass did it (k_reduce_merge<XCHG>); else the caller still has to
+    int fin_op = 0, fin_rt = 0;
+    uint64_t fin_imm = 0;
+    bool want_xchg = false;   // the caller asked for the cross-GPU merge of the result
 };
-
-static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth);
 
 // second pass over partials[nsplit][K]
 template <int BINOP, int ACC_RT>
@@ -141,35 +142,27 @@ static int launch_merge_rt(int acc_rt, const RdParams& fp, DeviceCtx* ctx, bool 
     }
 }
 
-static int merge_partials(ReducePlanIn& first, const RdParams& fp, DeviceCtx* ctx, int depth) {
-    (void) depth;
+// out[k] = finalize(initial (+) partials[0][k] (+) partials[1][k] (+) ...), optionally exchanged across GPUs
+// in the same kernel (xchg)
+static int merge_partials(const RdParams& fp, DeviceCtx* ctx, bool xchg, const P2pParams& xw, const char* what) {
     if (fp.K >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "too many outputs");
-    // fused local + cross-GPU merge: same values as xtb_allreduce on the stored result when the result is
-    // stored in the accumulator type and no initial value is folded in
-    P2pParams xw;
-    memset(&xw, 0, sizeof(xw));
-    const size_t words = (size_t) fp.K * (size_t) (dtype_size(first.acc_rt) / 4);
-    const bool xchg = first.want_xchg && fp.K >= 128 && !first.has_initial && first.out_dtype == first.acc_rt &&
-                      words <= kP2pMaxWords && comm_p2p_params(ctx, &xw) && xw.world > 1;
     // the reported kernel stays the first pass (the one that moves the data), with the merge appended
     char name[128];
-    snprintf(name, sizeof(name), "%.90s + %s", xtb_last_kernel(), xchg ? "k_reduce_merge[+p2p exchange]" : fp.K < 128 ? "k_reduce_merge_few" : "k_reduce_merge");
-    switch (first.binop) {
-        case XTB_OP_ADD: XTB_TRY(launch_merge_rt<XTB_OP_ADD>(first.acc_rt, fp, ctx, xchg, xw)); break;
-        case XTB_OP_MUL: XTB_TRY(launch_merge_rt<XTB_OP_MUL>(first.acc_rt, fp, ctx, xchg, xw)); break;
-        case XTB_OP_MAXIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MAXIMUM>(first.acc_rt, fp, ctx, xchg, xw)); break;
-        case XTB_OP_MINIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MINIMUM>(first.acc_rt, fp, ctx, xchg, xw)); break;
-        default: XTB_FAIL(XTB_ERR_INVALID, "merge: operator %d", first.binop);
+    snprintf(name, sizeof(name), "%.90s + %s", xtb_last_kernel(), what);
+    switch (fp.binop) {
+        case XTB_OP_ADD: XTB_TRY(launch_merge_rt<XTB_OP_ADD>(fp.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_MUL: XTB_TRY(launch_merge_rt<XTB_OP_MUL>(fp.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_MAXIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MAXIMUM>(fp.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_MINIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MINIMUM>(fp.acc_rt, fp, ctx, xchg, xw)); break;
+        default: XTB_FAIL(XTB_ERR_INVALID, "merge: operator %d", fp.binop);
     }
-    if (xchg) first.xchg_done = true;
     note_launch(name);
     return check_launch("k_reduce_merge");
 }
 
-static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
+static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
     Space& s = in.space;
     const int OUT = in.n_leaves;
-    // NOTE: no collapse_space() on the merge pass's kept dims beyond what is exact
     collapse_space(&s);
     RdParams p;
     memset(&p, 0, sizeof(p));
@@ -186,6 +179,9 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
     p.has_initial = in.has_initial;
     p.out_ptr = in.out_ptr;
     p.out_dtype = in.out_dtype;
+    p.fin_op = in.fin_op;
+    p.fin_rt = in.fin_rt;
+    p.fin_imm = in.fin_imm;
 
     // split dims into kept / reduced lists (order preserved)
     int kd[XTB_MAX_DIM], rd[XTB_MAX_DIM];
@@ -240,13 +236,6 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
         any_vec |= L.mode == MODE_VEC;
     }
     if (!any_vec) V = 1;
-    p.out_vec_ok = 0;
-    if (!inner && V > 1) {
-        const int osz = dtype_size(p.out_dtype);
-        bool ok = p.out_kstride[p.nk - 1] == 1 && ((uintptr_t) p.out_ptr) % ((int64_t) V * osz) == 0;
-        for (int d = 0; d < p.nk - 1 && ok; ++d) ok = (p.out_kstride[d] * osz) % ((int64_t) V * osz) == 0;
-        p.out_vec_ok = ok;
-    }
 
     if (in.empty) p.R = 0;
     // parallelisation
@@ -265,7 +254,7 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
         if (p.rvec_total > 32 * 8 && p.K * 32 < target_threads) G = 256;
         p.G = G;
         p.chunk = p.rvec_total;
-        if (G == 256 && depth == 0 && p.K * 256 < target_threads && p.rvec_total > 256 * 16) {
+        if (G == 256 && p.K * 256 < target_threads && p.rvec_total > 256 * 16) {
             int64_t want = target_threads / (p.K * 256);
             int64_t maxsplit = p.rvec_total / (256 * 8);
             int64_t ns = std::max<int64_t>(1, std::min(want, maxsplit));
@@ -287,25 +276,72 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
         p.kvec_total = (p.K / KL) * kvpr;
         if (p.kvec_total >= 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "too many outputs");
         p.chunk = p.R;
-        if (depth == 0 && p.kvec_total < target_threads && p.R > 32) {
+        if (p.kvec_total < target_threads && p.R > 32) {
             int64_t want = target_threads / std::max<int64_t>(p.kvec_total, 1);
             int64_t maxsplit = p.R / 16;
             int64_t ns = std::max<int64_t>(1, std::min(want, maxsplit));
             ns = std::min<int64_t>(ns, 4096);
             if (ns > 1) {
                 p.chunk = (p.R + ns - 1) / ns;
+                p.chunk = (p.chunk + kRdFlush - 1) / kRdFlush * kRdFlush;   // whole summation blocks per split
                 p.nsplit = (int) ((p.R + p.chunk - 1) / p.chunk);
-                // the merge pass reads partials[K][nsplit] with 128-bit loads: keep rows 16-byte multiples
+                // the merge pass reads partials[nsplit][K] with 128-bit loads: keep rows 16-byte multiples
                 // (trailing empty splits write the identity)
                 const int q = 16 / dtype_size(p.acc_rt);
                 p.nsplit = (p.nsplit + q - 1) / q * q;
             }
         }
+        // Split rows are already summed out of the reference's order: use blocked summation there, which keeps
+        // every fp32 chain short (<= kRdFlush terms per level).  Unsplit, the kernel adds row after row exactly
+        // like reduce_immediate (xreducer.hpp:512-551) and stays bit-identical to it.
+        p.two_level = p.nsplit > 1 ? 1 : 0;
+    }
+
+    // ---- cross-GPU merge of the result (the reduced axis is the sharded one) ----
+    //   fused   : k_reduce_merge<XCHG> exchanges each merged output over NVLink peer memory before the one store
+    //   staged  : local result -> dense accumulator-typed staging buffer -> collective -> final store.
+    // Either way xt::initial and the finalize step are applied ONCE, after the cross-GPU merge.
+    const int asz = dtype_size(p.acc_rt);
+    P2pParams xw;
+    memset(&xw, 0, sizeof(xw));
+    bool fused = false, staged = false;
+    if (in.want_xchg && comm_world() > 1) {
+        const size_t words = (size_t) p.K * (size_t) (asz / 4);
+        fused = p.nsplit > 1 && p.K >= 128 && words <= kP2pMaxWords && comm_p2p_params(ctx, &xw) && xw.world > 1;
+        staged = !fused;
+    }
+    const size_t part_bytes = p.nsplit > 1 ? ((size_t) p.nsplit * (size_t) p.K * asz + 255) / 256 * 256 : 0;
+    const size_t stage_bytes = staged ? (size_t) p.K * asz : 0;
+    char* scratch = nullptr;
+    if (part_bytes + stage_bytes > 0) {
+        void* sp = nullptr;
+        XTB_TRY(ensure_scratch(ctx, part_bytes + stage_bytes, &sp));
+        scratch = (char*) sp;
+    }
+    if (p.nsplit > 1) p.part_ptr = scratch;
+    const RdParams final_view = p;      // the caller's output, initial and finalize step
+    if (staged) {
+        p.out_ptr = scratch + part_bytes;
+        p.out_dtype = p.acc_rt;
+        int64_t st = 1;
+        for (int d = p.nk - 1; d >= 0; --d) {
+            p.out_kstride[d] = st;
+            st *= p.kshape[d];
+        }
+        p.has_initial = 0;
+        p.fin_op = 0;
+    }
+    p.out_vec_ok = 0;
+    if (!inner && V > 1) {
+        const int osz = dtype_size(p.out_dtype);
+        bool ok = p.out_kstride[p.nk - 1] == 1 && ((uintptr_t) p.out_ptr) % ((int64_t) V * osz) == 0;
+        for (int d = 0; d < p.nk - 1 && ok; ++d) ok = (p.out_kstride[d] * osz) % ((int64_t) V * osz) == 0;
+        p.out_vec_ok = ok;
     }
     // preconditions of k_reduce_rows_exact
     p.exact_rows = 0;
     if (inner && p.nk == 1 && p.nr == 1 && p.G <= 32 && p.nsplit == 1 && V > 1 && p.rshape[0] % V == 0 &&
-        p.rvec_total == p.G && !p.has_initial && p.out_dtype == p.acc_rt && p.in_rt == p.acc_rt &&
+        p.rvec_total == p.G && !p.has_initial && (p.out_dtype == p.acc_rt || p.fin_op != 0) && p.in_rt == p.acc_rt &&
         (p.kshape[0] == 1 || p.out_kstride[0] == 1) && p.K < 0x7fffffffLL) {
         bool ok = true;
         for (int k = 0; k < in.n_leaves; ++k) {
@@ -316,14 +352,16 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx, int depth) {
         }
         p.exact_rows = ok;
     }
-    if (p.nsplit > 1) {
-        void* scratch = nullptr;
-        const size_t bytes = (size_t) p.nsplit * (size_t) p.K * dtype_size(p.acc_rt);
-        XTB_TRY(ensure_scratch(ctx, bytes, &scratch));
-        p.part_ptr = (char*) scratch;
-    }
     XTB_TRY(run_reduce_kernel(in.prog, p, ctx, inner, in.w64, V));
-    if (p.nsplit > 1) return merge_partials(in, p, ctx, depth);
+    if (p.nsplit > 1)
+        XTB_TRY(merge_partials(p, ctx, fused, xw, fused ? "k_reduce_merge[+p2p exchange]" : p.K < 128 ? "k_reduce_merge_few" : "k_reduce_merge"));
+    if (staged) {
+        XTB_TRY(comm_allreduce(ctx, p.out_ptr, (size_t) p.K, p.acc_rt, in.op));
+        RdParams f = final_view;
+        f.nsplit = 1;
+        f.part_ptr = p.out_ptr;
+        XTB_TRY(merge_partials(f, ctx, false, xw, "allreduce + k_reduce_merge[final store]"));
+    }
     return XTB_OK;
 }
 
@@ -334,6 +372,12 @@ using namespace xtb;
 extern "C" int xtb_reduce(int op, int acc_type, const xtb_program* prog, const xtb_operand* leaves, int ndim,
                           const int64_t* shape, int n_axes, const int32_t* axes, int keep_dims, const void* initial,
                           const xtb_operand* out, int allreduce) {
+    return xtb_reduce_fin(op, acc_type, prog, leaves, ndim, shape, n_axes, axes, keep_dims, initial, out, allreduce, nullptr);
+}
+
+extern "C" int xtb_reduce_fin(int op, int acc_type, const xtb_program* prog, const xtb_operand* leaves, int ndim,
+                              const int64_t* shape, int n_axes, const int32_t* axes, int keep_dims, const void* initial,
+                              const xtb_operand* out, int allreduce, const xtb_finalize* fin) {
     if (!prog || !out || (ndim > 0 && !shape)) XTB_FAIL(XTB_ERR_INVALID, "null argument");
     if (ndim < 0 || ndim > XTB_MAX_DIM) XTB_FAIL(XTB_ERR_INVALID, "rank %d out of range", ndim);
     if (n_axes < 0 || n_axes > ndim) XTB_FAIL(XTB_ERR_AXIS, "%d axes for rank %d", n_axes, ndim);
@@ -353,8 +397,15 @@ extern "C" int xtb_reduce(int op, int acc_type, const xtb_program* prog, const x
     int rt = 0;
     bool w64 = false;
     XTB_TRY(validate_program(prog, leaf_dt, &rt, &w64));
-    if (dtype_size(acc_type) == 8 || dtype_size(out->dtype) == 8) w64 = true;
     if (out->dtype < 0 || out->dtype >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "bad out dtype");
+    if (fin && fin->op != XTB_FIN_NONE) {
+        if (fin->op != XTB_FIN_DIV && fin->op != XTB_FIN_DIV_SQRT) XTB_FAIL(XTB_ERR_INVALID, "unknown finalize step %d", fin->op);
+        if (fin->type != XTB_F32 && fin->type != XTB_F64) XTB_FAIL(XTB_ERR_INVALID, "finalize runs in f32 or f64");
+        // the finalize step converts by itself: a 32-bit accumulator keeps 32-bit slots whatever the output dtype
+        if (dtype_size(acc_type) == 8) w64 = true;
+    } else if (dtype_size(acc_type) == 8 || dtype_size(out->dtype) == 8) {
+        w64 = true;
+    }
 
     ReducePlanIn in;
     in.prog = prog;
@@ -400,6 +451,12 @@ extern "C" int xtb_reduce(int op, int acc_type, const xtb_program* prog, const x
     if (K == 0) return XTB_OK;
     DeviceCtx* ctx;
     XTB_TRY(get_ctx(&ctx));
+    in.op = op;
+    if (fin && fin->op != XTB_FIN_NONE) {
+        in.fin_op = fin->op;
+        in.fin_rt = fin->type;
+        in.fin_imm = fin->imm;
+    }
     in.binop = binop;
     in.acc_rt = acc_type;
     in.in_rt = rt;
@@ -418,10 +475,5 @@ extern "C" int xtb_reduce(int op, int acc_type, const xtb_program* prog, const x
         in.empty = true;
     }
     in.want_xchg = allreduce != 0;
-    XTB_TRY(plan_and_launch(in, ctx, 0));
-    if (allreduce && !in.xchg_done) {
-        // out must be dense for the in-place collective
-        XTB_TRY(comm_allreduce(ctx, in.out_ptr, (size_t) K, out->dtype, op));
-    }
-    return XTB_OK;
+    return plan_and_launch(in, ctx);
 }

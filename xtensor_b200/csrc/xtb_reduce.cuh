@@ -61,7 +61,20 @@ struct RdParams {
     uint32_t kvpr;          // vectors per innermost kept row
     FastDiv kvpr_div;
     int64_t kvec_total;
+    // accuracy: blocked summation.  The running accumulator is flushed into a second-level total after every
+    // block of kRdFlush rows (outer kernel) / kRdInnerFlush vectors per lane (inner kernels); for fp32 sums the
+    // second level is fp64 (RdTotal), so the only fp32 chains are the <= 8-term blocks and the merge trees.
+    // Set whenever the result is not the reference's sequential order anyway (split rows, lanes sharing an
+    // output); an unsplit strided-axis reduction keeps the reference's order bit for bit.
+    int32_t two_level;
+    // finalize step fused into the last store (mean_functor::finalize, xblockwise_reducer_functors.hpp:146-186):
+    //   0 none, 1: out = T(acc) / imm, 2: out = sqrt(T(acc) / imm), T = fin_rt (XTB_F32 / XTB_F64)
+    int32_t fin_op;
+    int32_t fin_rt;
+    uint64_t fin_imm;
 };
+constexpr int kRdFlush = 8;        // = the staged batch of the outer kernel
+constexpr int kRdInnerFlush = 4;   // = the staged batch of the inner kernels
 
 // Leaf access of one thread.  The kept part of every leaf's offset is folded into a
 // per-leaf base pointer once per output (or once per thread in the outer kernel); the
@@ -120,11 +133,49 @@ struct DynAcc {
     template <class S, int V> static XTB_DEV void step(const RdParams& p, S (&acc)[V], const S (&x)[V]) {
         exec_binary<S, V, false>(p.binop, p.acc_rt, acc, x);
     }
+    static XTB_DEV bool wide(const RdParams& p) { return p.binop == XTB_OP_ADD && p.acc_rt == XTB_F32; }
 };
 template <int BINOP, int ACC_RT> struct StaticAcc {
     template <class S, int V> static XTB_DEV void cast_in(const RdParams&, S (&)[V]) {}
     template <class S, int V> static XTB_DEV void step(const RdParams&, S (&acc)[V], const S (&x)[V]) {
         exec_binary_c<BINOP, ACC_RT, S, V>(acc, x);
+    }
+    static XTB_DEV constexpr bool wide(const RdParams&) { return BINOP == XTB_OP_ADD && ACC_RT == XTB_F32; }
+};
+
+// second level of the blocked summation: block results are merged into `tot` in the accumulator type, except
+// for fp32 sums, whose blocks are added in fp64 (one conversion + one add per block) and rounded once at the end
+template <class Acc, class S, int V> struct RdTotal {
+    S tot[V];
+    double totd[V];
+    XTB_DEV void init(const RdParams& p) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            tot[v] = (S) p.identity_bits;
+            totd[v] = 0.0;
+        }
+    }
+    // tot (+)= acc; acc = identity
+    XTB_DEV void flush(const RdParams& p, S (&acc)[V]) {
+        if (Acc::wide(p)) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) totd[v] += (double) get<float>(acc[v]);
+        } else {
+            Acc::template step<S, V>(p, tot, acc);
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = (S) p.identity_bits;
+    }
+    // acc = tot (+) acc
+    XTB_DEV void finish(const RdParams& p, S (&acc)[V]) {
+        if (Acc::wide(p)) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = put<S>((float) (totd[v] + (double) get<float>(acc[v])));
+        } else {
+            Acc::template step<S, V>(p, tot, acc);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = tot[v];
+        }
     }
 };
 
@@ -133,14 +184,32 @@ template <class S> XTB_DEV S shfl_xor(S v, int o) {
     else return (S) __shfl_xor_sync(0xffffffffu, v, o);
 }
 
-// final value -> (merge initial) -> cast -> store
+// accumulator value -> finalize (mean: / count, stddev: sqrt) -> cast -> store
+template <class T> XTB_DEV void rd_store_final_t(const RdParams& p, char* dst, T v) {
+    if (p.fin_op == 0) {
+        store_as<T>(dst, p.out_dtype, v);
+    } else if (p.fin_rt == XTB_F32) {
+        float x = (float) v / __uint_as_float((uint32_t) p.fin_imm);
+        if (p.fin_op == 2) x = sqrtf(x);
+        store_as<float>(dst, p.out_dtype, x);
+    } else {
+        double x = (double) v / __longlong_as_double((long long) p.fin_imm);
+        if (p.fin_op == 2) x = sqrt(x);
+        store_as<double>(dst, p.out_dtype, x);
+    }
+}
+template <class S> XTB_DEV void rd_store_final(const RdParams& p, char* dst, S v) {
+    XTB_TYPE_SWITCH(p.acc_rt, S, { rd_store_final_t<T>(p, dst, get<T>(v)); })
+}
+
+// final value -> (merge initial) -> finalize -> cast -> store
 template <class S> XTB_DEV void rd_finish_store(const RdParams& p, char* dst, S v) {
     S a[1] = {v};
     if (p.has_initial) {
         S b[1] = {(S) p.initial_bits};
         exec_binary<S, 1, false>(p.binop, p.acc_rt, a, b);
     }
-    store_elem<S>(dst, p.out_dtype, p.acc_rt, a[0]);
+    rd_store_final<S>(p, dst, a[0]);
 }
 
 // final value of a typed merge -> (merge initial) -> cast -> store
@@ -151,7 +220,7 @@ template <int BINOP, int ACC_RT, class S> XTB_DEV void rd_finish_store_c(const R
         exec_binary_c<BINOP, ACC_RT, S, 1>(a, b);
     }
     using T = reg_t<ACC_RT>;
-    store_as<T>(dst, p.out_dtype, get<T>(a[0]));
+    rd_store_final_t<T>(p, dst, get<T>(a[0]));
 }
 
 // Second pass of a split reduction: out[k] = partials[0][k] (+) partials[1][k] (+) ... over part[nsplit][K].
@@ -199,9 +268,19 @@ __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_
                     for (int i = 0; i < 4; ++i) x[u][i] = (sp < p.nsplit && k0 + i < p.K) ? load_elem<S>(src + i * asz, ACC_RT) : (S) p.identity_bits;
                 }
             }
+            // pairwise tree over the batch (absent splits hold the identity), then one add into the running value
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (s0 + kMergeWarps * u < p.nsplit) exec_binary_c<BINOP, ACC_RT, S, 4>(acc, x[u]);
+            for (int u = 0; u < U; ++u) {
+                if (!(s0 + kMergeWarps * u < p.nsplit)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[u][i] = (S) p.identity_bits;
+                }
+            }
+#pragma unroll
+            for (int st = 1; st < U; st <<= 1)
+#pragma unroll
+                for (int u = 0; u + st < U; u += 2 * st) exec_binary_c<BINOP, ACC_RT, S, 4>(x[u], x[u + st]);
+            exec_binary_c<BINOP, ACC_RT, S, 4>(acc, x[0]);
         }
     }
 #pragma unroll
@@ -212,12 +291,15 @@ __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_
         const int64_t k = (int64_t) blockIdx.x * 128 + warp * 32 + lane;
         if (k < p.K) {
             const int c = warp * 32 + lane;
-            S r[1] = {sm[0][c]};
+            // the warps' values are combined in a fixed pairwise tree
+            S t[kMergeWarps][1];
 #pragma unroll
-            for (int w = 1; w < kMergeWarps; ++w) {
-                S y[1] = {sm[w][c]};
-                exec_binary_c<BINOP, ACC_RT, S, 1>(r, y);
-            }
+            for (int w = 0; w < kMergeWarps; ++w) t[w][0] = sm[w][c];
+#pragma unroll
+            for (int st = 1; st < kMergeWarps; st <<= 1)
+#pragma unroll
+                for (int w = 0; w + st < kMergeWarps; w += 2 * st) exec_binary_c<BINOP, ACC_RT, S, 1>(t[w], t[w + st]);
+            S r[1] = {t[0][0]};
             if constexpr (XCHG) {
                 constexpr int W = sizeof(S) / 4;
                 const S mine = r[0];
@@ -361,6 +443,10 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
             // U vectors of every leaf in flight before any arithmetic
             constexpr int U = 4;
             PreFetch<NL, U, S, V> pf;
+            // blocked summation: lanes interleave, so the order is never the reference's; keep chains short
+            static_assert(U == kRdInnerFlush, "one block per staged batch");
+            RdTotal<Acc, S, V> total;
+            total.init(p);
             for (int64_t j = jbeg + lane; j < jend; j += (int64_t) stride * U) {
                 int nvalid[U];
 #pragma unroll
@@ -389,7 +475,9 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
                         Acc::template step<S, V>(p, acc, x);
                     }
                 }
+                total.flush(p, acc);
             }
+            total.finish(p, acc);
             S r0[1] = {acc[0]};
 #pragma unroll
             for (int v = 1; v < V; ++v) {
@@ -399,6 +487,9 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
             return r0[0];
         }
     }
+    RdTotal<Acc, S, V> total2;
+    total2.init(p);
+    int in_block2 = 0;
     for (int64_t j = jbeg + lane; j < jend; j += stride) {
         int64_t cv = j;
         if (p.nr > 1) {
@@ -424,7 +515,12 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
                 if (v >= f.nvalid) x[v] = (S) p.identity_bits;
         }
         Acc::template step<S, V>(p, acc, x);
+        if (++in_block2 >= kRdInnerFlush) {     // same block boundaries as the staged loop above
+            total2.flush(p, acc);
+            in_block2 = 0;
+        }
     }
+    total2.finish(p, acc);
     S r[1] = {acc[0]};
 #pragma unroll
     for (int v = 1; v < V; ++v) {
@@ -585,7 +681,10 @@ __global__ void __launch_bounds__(256) k_reduce_rows_exact(const __grid_constant
             }
         }
         const uint32_t ko = out_base + lane;
-        if (ko < K) store_elem<S>(p.out_ptr + (int64_t) ko * osz, RT, RT, keep);
+        if (ko < K) {
+            if (p.fin_op == 0) store_elem<S>(p.out_ptr + (int64_t) ko * osz, RT, RT, keep);
+            else rd_store_final<S>(p, p.out_ptr + (int64_t) ko * dtype_size(p.out_dtype), keep);
+        }
     }
 }
 
@@ -626,7 +725,7 @@ __global__ void __launch_bounds__(256) k_reduce_inner_block(const __grid_constan
 }
 
 // ---- innermost dim kept --------------------------------------------------------------------
-// INV: bit mask of leaves the host found invariant along the reduced dim (k_reduce_outer_inv, opt-in)
+// INV: bit mask of leaves the host found invariant along the reduced dim (k_reduce_outer_inv)
 template <class Eval, class Acc, class S, int V, int INV>
 XTB_DEV void reduce_outer_body(const RdParams& p) {
     constexpr int NL = Eval::kLeaves;
@@ -662,6 +761,10 @@ XTB_DEV void reduce_outer_body(const RdParams& p) {
                 // the reference's order (row r before row r + 1)
                 constexpr int U = 8;
                 std::conditional_t<INV != 0, PreFetchInv<NL, U, S, V, INV>, PreFetch<NL, U, S, V>> pf;
+                // blocked summation (two_level): `acc` holds one batch of kRdFlush rows, `total` the flushed blocks
+                static_assert(U == kRdFlush, "one block per staged batch");
+                RdTotal<Acc, S, V> total;
+                total.init(p);
                 for (int64_t r = rbeg; r < rend; r += U) {
                     int nvalid[U];
 #pragma unroll
@@ -683,29 +786,33 @@ XTB_DEV void reduce_outer_body(const RdParams& p) {
                             Acc::template step<S, V>(p, acc, x);
                         }
                     }
+                    if (p.two_level) total.flush(p, acc);
                 }
-            }
-        } else if (p.nr == 1) {
-            for (int64_t r = rbeg; r < rend; ++r) {
-#pragma unroll
-                for (int k = 0; k < NL; ++k)
-                    if (k < p.n_leaves) f.cur[k] = base[k] + r * rstep[k];
-                S x[V];
-                Eval::template run<S, V>(p.prog, f, x);
-                Acc::template cast_in<S, V>(p, x);
-                Acc::template step<S, V>(p, acc, x);
+                if (p.two_level) total.finish(p, acc);
             }
         } else {
+            // same block boundaries as the staged loop above (results do not depend on the evaluator)
+            RdTotal<Acc, S, V> total;
+            total.init(p);
+            int in_block = 0;
             for (int64_t r = rbeg; r < rend; ++r) {
 #pragma unroll
-                for (int k = 0; k < NL; ++k)
-                    if (k < p.n_leaves)
-                        f.cur[k] = base[k] + rd_reduced_offset(p, (uint32_t) r, p.nr, p.leaf[k].rstride) * dtype_size(p.leaf[k].dtype);
+                for (int k = 0; k < NL; ++k) {
+                    if (k < p.n_leaves) {
+                        if (p.nr == 1) f.cur[k] = base[k] + r * rstep[k];
+                        else f.cur[k] = base[k] + rd_reduced_offset(p, (uint32_t) r, p.nr, p.leaf[k].rstride) * dtype_size(p.leaf[k].dtype);
+                    }
+                }
                 S x[V];
                 Eval::template run<S, V>(p.prog, f, x);
                 Acc::template cast_in<S, V>(p, x);
                 Acc::template step<S, V>(p, acc, x);
+                if (p.two_level && ++in_block >= kRdFlush) {
+                    total.flush(p, acc);
+                    in_block = 0;
+                }
             }
+            if (p.two_level) total.finish(p, acc);
         }
         if (p.nsplit > 1) {
             // partials[nsplit][K]: k_reduce_merge streams them with coalesced 128-bit loads
@@ -723,23 +830,24 @@ XTB_DEV void reduce_outer_body(const RdParams& p) {
                 for (int v = 0; v < V; ++v) b[v] = (S) p.initial_bits;
                 Acc::template step<S, V>(p, acc, b);
             }
-            if (p.out_vec_ok && f.nvalid == V) {
+            if (p.out_vec_ok && f.nvalid == V && p.fin_op == 0) {
                 store_vec<S, V>(dst, p.out_dtype, p.acc_rt, acc);
             } else {
                 const int64_t step = p.out_kstride[p.nk - 1] * osz;
 #pragma unroll
                 for (int v = 0; v < V; ++v)
-                    if (v < f.nvalid) store_elem<S>(dst + v * step, p.out_dtype, p.acc_rt, acc[v]);
+                    if (v < f.nvalid) rd_store_final<S>(p, dst + v * step, acc[v]);
             }
         }
     }
 }
 
+// compile-time one-leaf programs: 3 CTAs per SM (<= 80 registers) keep 96 KB of rows in flight per SM
 template <class Eval, class Acc, class S, int V>
-__global__ void __launch_bounds__(256) k_reduce_outer(const __grid_constant__ RdParams p) {
+__global__ void __launch_bounds__(256, Eval::kPrefetch ? (Eval::kLeaves >= 2 ? 2 : 3) : 1) k_reduce_outer(const __grid_constant__ RdParams p) {
     reduce_outer_body<Eval, Acc, S, V, 0>(p);
 }
-// opt-in (XTB_REDUCE_INV=1): invariant leaves staged once; 80 registers -> 3 CTAs per SM
+// invariant leaves (the mean in square(a - mean)) staged once; 80 registers -> 3 CTAs per SM
 template <class Eval, class Acc, class S, int V, int INV>
 __global__ void __launch_bounds__(256, 3) k_reduce_outer_inv(const __grid_constant__ RdParams p) {
     reduce_outer_body<Eval, Acc, S, V, INV>(p);
@@ -801,9 +909,9 @@ static int launch_reduce(const RdParams& p, DeviceCtx* ctx, bool inner, const ch
         snprintf(name, sizeof(name), "k_reduce_outer<%s,S%d,V%d>[split=%d]", evname, (int) sizeof(S) * 8, V, p.nsplit);
         bool inv1 = false;
         if constexpr (Eval::kPrefetch && Eval::kLeaves == 2 && V > 1) {
-            // opt-in: leaf 1 staged once when it does not move along the reduced dim and every thread owns whole vectors
+            // leaf 1 staged once when it does not move along the reduced dim and every thread owns whole vectors
             const RdLeaf& L = p.leaf[1];
-            inv1 = getenv("XTB_REDUCE_INV") != nullptr && p.nr == 1 && p.n_leaves == 2 && L.rstride[0] == 0 && L.mode == MODE_VEC &&
+            inv1 = p.nr == 1 && p.n_leaves == 2 && L.rstride[0] == 0 && L.mode == MODE_VEC &&
                    p.leaf[0].rstride[0] != 0 && p.kshape[p.nk - 1] % V == 0;
             if (inv1) {
                 snprintf(name, sizeof(name), "k_reduce_outer<%s,S%d,V%d,inv1>[split=%d]", evname, (int) sizeof(S) * 8, V, p.nsplit);

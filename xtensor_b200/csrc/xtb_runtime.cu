@@ -5,7 +5,10 @@
 // operand canonicaliser used by every compute entry point.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
 
@@ -36,6 +39,25 @@ int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(XTB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return XTB_OK;
+}
+
+// ---- process options -----------------------------------------------------------
+static Options g_options;
+static std::once_flag g_options_once;
+Options& options() {
+    std::call_once(g_options_once, [] {
+        auto flag = [](const char* n) { const char* e = getenv(n); return e != nullptr && e[0] != 0 && strcmp(e, "0") != 0; };
+        g_options.no_static = flag("XTB_NO_STATIC");
+        g_options.no_jit = flag("XTB_NO_JIT");
+        g_options.no_staged = flag("XTB_NO_STAGED");
+        g_options.no_tma = flag("XTB_NO_TMA");
+        g_options.jit_verbose = flag("XTB_JIT_VERBOSE");
+        if (const char* e = getenv("XTB_JIT_MIN_ELEMS")) g_options.jit_min_elems = atoll(e);
+        if (const char* e = getenv("XTB_SCAN_VARIANT")) g_options.scan_variant = atoi(e);
+        if (const char* e = getenv("XTB_TILE_VARIANT")) g_options.tile_variant = atoi(e);
+        if (const char* e = getenv("XTB_SCAN_NV")) g_options.scan_nv = atoi(e);
+    });
+    return g_options;
 }
 
 // ---- device contexts ---------------------------------------------------------
@@ -109,6 +131,20 @@ int get_ctx(DeviceCtx** ctx) {
 int ensure_scratch(DeviceCtx* ctx, size_t bytes, void** ptr) {
     void*& buf = ctx->forked ? ctx->fork_scratch : ctx->scratch;
     size_t& have = ctx->forked ? ctx->fork_scratch_bytes : ctx->scratch_bytes;
+    if (!ctx->forked) {
+        // the buffer is reused call after call: stream order protects it on one stream; after xtb_set_stream
+        // moved the library to another stream, the new stream first waits for the old one's last user
+        if (ctx->scratch_stream && ctx->scratch_stream != ctx->stream) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(ctx->stream, &cs);
+            if (cs == cudaStreamCaptureStatusNone) {
+                if (!ctx->scratch_ev) XTB_CUDA(cudaEventCreateWithFlags(&ctx->scratch_ev, cudaEventDisableTiming));
+                XTB_CUDA(cudaEventRecord(ctx->scratch_ev, ctx->scratch_stream));
+                XTB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->scratch_ev, 0));
+            }
+        }
+        ctx->scratch_stream = ctx->stream;
+    }
     if (bytes > have) {
         if (buf) XTB_CUDA(cudaFreeAsync(buf, ctx->stream));
         size_t want = std::max(bytes, (size_t) 1 << 20);
@@ -459,31 +495,100 @@ int xtb_graph_begin(void) {
     return XTB_OK;
 }
 
+static std::mutex g_graph_mutex;
+static std::unordered_map<void*, int> g_graph_kernels;   // kernel nodes per instantiated graph (launch accounting)
+
 int xtb_graph_end(void** graph_exec) {
     if (!graph_exec) XTB_FAIL(XTB_ERR_INVALID, "null graph");
     DeviceCtx* c;
     XTB_TRY(get_ctx(&c));
     cudaGraph_t graph = nullptr;
     XTB_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    int kernels = 0;
+    {
+        size_t n = 0;
+        if (cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n > 0) {
+            std::vector<cudaGraphNode_t> nodes(n);
+            if (cudaGraphGetNodes(graph, nodes.data(), &n) == cudaSuccess) {
+                for (size_t i = 0; i < n; ++i) {
+                    cudaGraphNodeType t;
+                    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++kernels;
+                }
+            }
+        }
+    }
     cudaGraphExec_t exec = nullptr;
     cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) XTB_FAIL(XTB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    {
+        std::lock_guard<std::mutex> lock(g_graph_mutex);
+        g_graph_kernels[(void*) exec] = kernels;
+    }
     *graph_exec = (void*) exec;
     return XTB_OK;
+}
+
+int xtb_graph_kernel_count(void* graph_exec) {
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    auto it = g_graph_kernels.find(graph_exec);
+    return it == g_graph_kernels.end() ? -1 : it->second;
 }
 
 int xtb_graph_launch(void* graph_exec) {
     DeviceCtx* c;
     XTB_TRY(get_ctx(&c));
     XTB_CUDA(cudaGraphLaunch((cudaGraphExec_t) graph_exec, c->stream));
-    note_launch("cudaGraphLaunch");
+    int kernels = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_graph_mutex);
+        auto it = g_graph_kernels.find(graph_exec);
+        if (it != g_graph_kernels.end()) kernels = it->second;
+    }
+    note_launch(nullptr, kernels);       // every kernel node of the graph is one launch of ours
     return XTB_OK;
 }
 
 int xtb_graph_destroy(void* graph_exec) {
-    if (graph_exec) XTB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t) graph_exec));
+    if (graph_exec) {
+        {
+            std::lock_guard<std::mutex> lock(g_graph_mutex);
+            g_graph_kernels.erase(graph_exec);
+        }
+        XTB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t) graph_exec));
+    }
     return XTB_OK;
+}
+
+int xtb_set_option(const char* name, long long value) {
+    if (!name) XTB_FAIL(XTB_ERR_INVALID, "null option name");
+    Options& o = options();
+    if (!strcmp(name, "no_static")) o.no_static = (int) value;
+    else if (!strcmp(name, "no_jit")) o.no_jit = (int) value;
+    else if (!strcmp(name, "no_staged")) o.no_staged = (int) value;
+    else if (!strcmp(name, "no_tma")) o.no_tma = (int) value;
+    else if (!strcmp(name, "jit_verbose")) o.jit_verbose = (int) value;
+    else if (!strcmp(name, "jit_min_elems")) o.jit_min_elems = value;
+    else if (!strcmp(name, "scan_variant")) o.scan_variant = (int) value;
+    else if (!strcmp(name, "tile_variant")) o.tile_variant = (int) value;
+    else if (!strcmp(name, "scan_nv")) o.scan_nv = (int) value;
+    else XTB_FAIL(XTB_ERR_INVALID, "unknown option '%s'", name);
+    return XTB_OK;
+}
+
+long long xtb_get_option(const char* name) {
+    if (!name) return -1;
+    const Options& o = options();
+    if (!strcmp(name, "no_static")) return o.no_static;
+    if (!strcmp(name, "no_jit")) return o.no_jit;
+    if (!strcmp(name, "no_staged")) return o.no_staged;
+    if (!strcmp(name, "no_tma")) return o.no_tma;
+    if (!strcmp(name, "jit_verbose")) return o.jit_verbose;
+    if (!strcmp(name, "jit_min_elems")) return o.jit_min_elems;
+    if (!strcmp(name, "scan_variant")) return o.scan_variant;
+    if (!strcmp(name, "tile_variant")) return o.tile_variant;
+    if (!strcmp(name, "scan_nv")) return o.scan_nv;
+    return -1;
 }
 
 int64_t xtb_launch_count(int reset) {

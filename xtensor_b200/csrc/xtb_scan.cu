@@ -72,6 +72,18 @@ template <class T> XTB_DEV T load_cast(const char* p, int dt) {
 
 template <class T> XTB_DEV T scan_op(int op, T a, T b) { return op == XTB_RED_PROD ? (T) (a * b) : (T) (a + b); }
 template <class T> XTB_DEV T scan_identity(int op) { return op == XTB_RED_PROD ? T(1) : T(0); }
+template <class T> XTB_DEV T shfl_xor_t(T v, int m);
+// compile-time operator (the bandwidth-critical kernels are instantiated per operator: no select per element)
+template <int OP, class T> XTB_DEV T sop(T a, T b) {
+    if constexpr (OP == XTB_RED_PROD) return (T) (a * b);
+    else return (T) (a + b);
+}
+template <int OP, class T> XTB_DEV constexpr T sident() { return OP == XTB_RED_PROD ? T(1) : T(0); }
+template <int OP, class T> XTB_DEV T warp_total_c(T v) {
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) v = sop<OP, T>(v, shfl_xor_t<T>(v, m));
+    return v;
+}
 
 XTB_DEV int64_t scan_offset(uint32_t lin, int n, const int64_t* shape, const int64_t* stride, const FastDiv* div) {
     int64_t off = 0;
@@ -98,6 +110,25 @@ template <class T> XTB_DEV T shfl_up_t(T v, int d) {
         T r;
         memcpy(&r, &u, 4);
         return r;
+    }
+}
+
+// streaming store of N bytes (4 / 8 / 16) from registers.  No "memory" clobber: the kernels that use it never
+// read back what they store, and the compiler stays free to hoist the next loads above the store.
+template <int N> XTB_DEV void memcpy_stream(void* dst, const void* src) {
+    if constexpr (N == 16) {
+        uint4 v;
+        memcpy(&v, src, 16);
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+    } else if constexpr (N == 8) {
+        uint2 v;
+        memcpy(&v, src, 8);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(v.x), "r"(v.y));
+    } else {
+        static_assert(N == 4, "");
+        uint32_t v;
+        memcpy(&v, src, 4);
+        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(dst), "r"(v));
     }
 }
 
@@ -432,6 +463,290 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_tiles(const __grid_con
     }
 }
 
+// ---- contiguous scan, rows longer than one tile: reduce ahead, scan from L2 --------------------------
+// A single-pass look-back scan (Merrill & Garland; CUB's DeviceScan) retires tiles in order: a tile cannot
+// store before every older tile has LOADED, so under HBM3e latencies its registers / shared memory idle while
+// the slowest older load completes (measured on this B200: CUB InclusiveSum and the round-1 staged look-back
+// kernel both stop at 0.58 of the copy bandwidth).  Here no tile ever waits for another one:
+//   CTA k  (1) loads tile k from HBM, reduces it and publishes its aggregate            ("reduce ahead"),
+//          (2) loads tile k - D, which CTA k - D pulled through the 126 MB L2 a few microseconds ago, scans it
+//              with the prefix gathered from aggregates that were published D tiles earlier, and stores it,
+//          (3) (one warp) folds complete groups of 32 units of the aggregate tree that finished D / 2 tiles ago.
+// Both tile loads are issued before anything is consumed.  HBM traffic stays one read + one write per element
+// (D x tile = 24 MB of look-ahead lives in L2); the L2 serves one extra read.  Tiles are taken in launch order.
+// Across tiles a fan-32 tree: level 0 holds every tile's aggregate, a unit of level l + 1 the total of 32 units
+// of level l.  The exclusive prefix of tile t is
+//        part[L-1] (+) ... (+) part[1] (+) part[0],   part[l] = butterfly(totals of the siblings before t's unit at level l)
+// which depends only on t's position: floating-point results are run-to-run deterministic.
+// Every slot is one {flag, value} word (one 64- / 128-bit access: no fences); a reader still checks the flag.
+constexpr int kLbFan = 32;
+constexpr int kLbMaxLevels = 5;
+
+struct LbTree {
+    int32_t levels;
+    uint32_t ahead;                     // D: tiles between the reduce visit and the scan visit (multiple of 64)
+    uint32_t units[kLbMaxLevels];       // units per row at each level = ceil(tiles_per_row / 32^l)
+    uint32_t level_off[kLbMaxLevels];   // first slot of each level; slot = level_off[l] + row * units[l] + unit
+    char* slots;                        // zeroed before the launch
+};
+
+XTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+XTB_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+template <class T> XTB_DEV T slot_wait(const char* slots, uint32_t i) {
+    T v;
+    while (!slot_try<T>(slots, i, v)) __nanosleep(20);
+    return v;
+}
+
+template <class T, int NV, int OP>
+__global__ void __launch_bounds__(kScanThreads, NV <= 4 ? 5 : 3) k_scan_ahead(const __grid_constant__ ScanParams p, const __grid_constant__ LbTree tr) {
+    constexpr int VEC = 16 / (int) sizeof(T);
+    constexpr int WARP_ELEMS = 32 * NV * VEC;
+    constexpr int TILE = kScanThreads * NV * VEC;
+    constexpr T ident = sident<OP, T>();
+    __shared__ __align__(128) T s_tile[TILE];              // the reduce-visit tile lands here (bulk copy: no registers in flight)
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ T s_red[kScanWarpsPerTile];
+    __shared__ T s_warp[kScanWarpsPerTile];
+    __shared__ T s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t k = blockIdx.x;
+    const bool do_red = k < p.total_tiles;                 // visit 1: reduce tile k
+    const bool do_scan = k >= tr.ahead;                    // visit 2: scan tile k - D
+    const uint32_t j = k - tr.ahead;
+    const int isz = dtype_size(p.in_dtype);
+    const bool one_row = p.rows == 1;                      // the flat scan: no row arithmetic at all
+
+    auto tile_pos = [&](uint32_t tile, uint32_t& row, uint32_t& trow) {
+        if (one_row) {
+            row = 0;
+            trow = tile;
+        } else {
+            row = tile / p.tiles_per_row;
+            trow = tile - row * p.tiles_per_row;
+        }
+    };
+    auto row_ptr = [&](uint32_t row) -> const char* {
+        return one_row ? p.in : p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz;
+    };
+    auto load_tile = [&](const char* in_row, uint32_t trow, T (&x)[NV][VEC]) {
+        const int64_t wbase = (int64_t) trow * TILE + (int64_t) (warp * WARP_ELEMS);
+        if (p.vec_io) {
+            const char* src = in_row + (wbase + lane * VEC) * (int64_t) sizeof(T);
+            if (wbase + WARP_ELEMS <= p.n) {               // whole warp chunk inside the row: no per-vector checks
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const uint4 r = ldg_stream_16(src + q * 512);
+                    memcpy(&x[q][0], &r, 16);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int64_t j0 = wbase + (int64_t) (q * 32 + lane) * VEC;
+                    if (j0 + VEC <= p.n) {
+                        const uint4 r = ldg_stream_16(src + q * 512);
+                        memcpy(&x[q][0], &r, 16);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) x[q][i] = j0 + i < p.n ? ((const T*) in_row)[j0 + i] : ident;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const int64_t e = wbase + (int64_t) (q * 32 + lane) * VEC + i;
+                    x[q][i] = e < p.n ? load_cast<T>(in_row + e * p.in_axis_stride * isz, p.in_dtype) : ident;
+                }
+            }
+        }
+    };
+
+    // ---- (1a) request tile k: one bulk copy HBM -> shared memory when the tile is whole and copyable ----
+    uint32_t krow = 0, ktrow = 0, jrow = 0, jtrow = 0;
+    bool red_bulk = false;
+    const char* krow_ptr = nullptr;
+    if (do_red) {
+        tile_pos(k, krow, ktrow);
+        krow_ptr = row_ptr(krow);
+        red_bulk = p.vec_io && (int64_t) (ktrow + 1) * TILE <= p.n;
+        if (red_bulk && tid == 0) {
+            const uint32_t bar = smem_u32(&s_bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (TILE * sizeof(T))) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(s_tile)), "l"(krow_ptr + (int64_t) ktrow * TILE * (int64_t) sizeof(T)), "r"((uint32_t) (TILE * sizeof(T))), "r"(bar)
+                         : "memory");
+        }
+    }
+    // ---- (2) tile j = k - D: requested from L2 into registers ----
+    T x[NV][VEC];
+    if (do_scan) {
+        tile_pos(j, jrow, jtrow);
+        load_tile(row_ptr(jrow), jtrow, x);
+    }
+    // ---- (3) tree maintenance for tile m = k - D / 2: everything it reads was published D / 2 tiles ago ----
+    if (warp == kScanWarpsPerTile - 1 && k >= tr.ahead / 2 && k - tr.ahead / 2 < p.total_tiles) {
+        uint32_t row, trow;
+        tile_pos(k - tr.ahead / 2, row, trow);
+        if ((trow + 1) % kLbFan == 0) {                    // (most tiles stop here)
+            uint32_t span = kLbFan;
+            for (int l = 0; l + 1 < tr.levels; ++l) {
+                // m closes a complete level-(l+1) unit that is not the last one of its row?
+                if ((trow + 1) % span != 0 || trow + 1 >= p.tiles_per_row) break;
+                const uint32_t unit = trow / span;                               // index of that unit at level l + 1
+                const T v = slot_wait<T>(tr.slots, tr.level_off[l] + row * tr.units[l] + unit * kLbFan + lane);
+                const T total = warp_total_c<OP, T>(v);
+                if (lane == 0) slot_publish<T>(tr.slots, tr.level_off[l + 1] + row * tr.units[l + 1] + unit, total);
+                __syncwarp();
+                span *= kLbFan;
+            }
+        }
+    }
+    // ---- (2a) prefix of tile j, gathered by warp 0 while the tile loads are in flight: the slots of all levels are
+    //      requested together (one L2 round trip), then combined from the highest level down ----
+    if (warp == 0 && do_scan && jtrow > 0) {
+        T v[kLbMaxLevels];
+        bool need[kLbMaxLevels], ok[kLbMaxLevels];
+        uint32_t idx[kLbMaxLevels];
+        uint32_t u = jtrow;
+#pragma unroll
+        for (int l = 0; l < kLbMaxLevels; ++l) {
+            const uint32_t cnt = u % kLbFan;
+            need[l] = l < tr.levels && (uint32_t) lane < cnt;
+            idx[l] = l < tr.levels ? tr.level_off[l] + jrow * tr.units[l] + (u - cnt) + lane : 0u;
+            v[l] = ident;
+            ok[l] = !need[l] || slot_try<T>(tr.slots, idx[l], v[l]);
+            u /= kLbFan;
+        }
+        T acc = ident;
+#pragma unroll
+        for (int l = kLbMaxLevels - 1; l >= 0; --l) {
+            if (l < tr.levels) {                           // warp-uniform
+                while (!ok[l]) {
+                    __nanosleep(20);
+                    ok[l] = slot_try<T>(tr.slots, idx[l], v[l]);
+                }
+                const T part = warp_total_c<OP, T>(need[l] ? v[l] : ident);
+                acc = sop<OP, T>(acc, part);               // higher levels lie before lower ones; ident (+) x == x
+            }
+        }
+        if (lane == 0) s_prefix = acc;
+    }
+    // ---- (2b) warp-level scan of tile j on the striped arrangement ----
+    T off[NV];
+    if (do_scan) {
+        T inc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+#pragma unroll
+            for (int i = 1; i < VEC; ++i) x[q][i] = sop<OP, T>(x[q][i - 1], x[q][i]);
+            inc[q] = x[q][VEC - 1];
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const T y = shfl_up_t<T>(inc[q], d);
+                if (lane >= d) inc[q] = sop<OP, T>(y, inc[q]);
+            }
+        }
+        T carry = ident;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const T ex = shfl_up_t<T>(inc[q], 1);
+            const T rowtot = shfl_idx_t<T>(inc[q], 31);
+            off[q] = lane == 0 ? carry : sop<OP, T>(carry, ex);
+            carry = q == 0 ? rowtot : sop<OP, T>(carry, rowtot);
+        }
+        if (lane == 0) s_warp[warp] = carry;
+    }
+    __syncthreads();                                       // s_warp, s_prefix; also: the mbarrier is initialised
+    if (do_scan) {
+        // ---- (2c) offsets of the warps, apply, store (striped): leaves before tile k has even arrived ----
+        T wv = lane < kScanWarpsPerTile ? s_warp[lane] : ident;
+#pragma unroll
+        for (int d = 1; d < kScanWarpsPerTile; d <<= 1) {
+            const T y = shfl_up_t<T>(wv, d);
+            if (lane >= d) wv = sop<OP, T>(y, wv);
+        }
+        const T warp_off = shfl_idx_t<T>(wv, warp > 0 ? warp - 1 : 0);
+        T base_off = warp > 0 ? warp_off : ident;
+        bool have_base = warp > 0;
+        if (jtrow > 0) {
+            const T e = s_prefix;
+            base_off = warp > 0 ? sop<OP, T>(e, warp_off) : e;
+            have_base = true;
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const bool first_vec = !have_base && q == 0 && lane == 0;       // the very first vector of a row keeps its values
+            if (!first_vec) {
+                const T o = have_base ? ((q == 0 && lane == 0) ? base_off : sop<OP, T>(base_off, off[q])) : off[q];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) x[q][i] = sop<OP, T>(o, x[q][i]);
+            }
+        }
+        const int64_t wbase = (int64_t) jtrow * TILE + (int64_t) (warp * WARP_ELEMS);
+        T* out_row = (T*) p.out + (int64_t) jrow * p.n;
+        if (p.vec_io && wbase + WARP_ELEMS <= p.n) {
+            char* dst = (char*) (out_row + wbase + lane * VEC);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) memcpy_stream<16>(dst + q * 512, &x[q][0]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const int64_t e = wbase + (int64_t) (q * 32 + lane) * VEC + i;
+                    if (e < p.n) out_row[e] = x[q][i];
+                }
+            }
+        }
+    }
+    if (!do_red) return;
+    // ---- (1b) reduce tile k: fixed order inside the thread, butterfly over the warp, fixed tree over the warps ----
+    T xa[NV][VEC];
+    if (red_bulk) {
+        mbar_wait(smem_u32(&s_bar), 0);
+        const T* mine = s_tile + warp * WARP_ELEMS + lane * VEC;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const uint4 r = *(const uint4*) (mine + q * 32 * VEC);
+            memcpy(&xa[q][0], &r, 16);
+        }
+    } else {
+        load_tile(krow_ptr, ktrow, xa);
+    }
+    T t = ident;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        T v = xa[q][0];
+#pragma unroll
+        for (int i = 1; i < VEC; ++i) v = sop<OP, T>(v, xa[q][i]);
+        t = q == 0 ? v : sop<OP, T>(t, v);
+    }
+    t = warp_total_c<OP, T>(t);
+    if (lane == 0) s_red[warp] = t;
+    __syncthreads();
+    if (warp == 0) {
+        T v = lane < kScanWarpsPerTile ? s_red[lane] : ident;
+#pragma unroll
+        for (int mk = 1; mk < kScanWarpsPerTile; mk <<= 1) v = sop<OP, T>(v, shfl_xor_t<T>(v, mk));
+        if (lane == 0 && ktrow + 1 < p.tiles_per_row) slot_publish<T>(tr.slots, tr.level_off[0] + krow * tr.units[0] + ktrow, v);
+    }
+}
+
 // ---- contiguous scan, long rows: shared-memory staged super-tiles -------------------------------
 // At HBM3e latencies the bytes a register-resident tile keeps in flight (64 B per thread) cannot cover
 // the look-back wait.  Here a CTA owns a super-tile of up to 64 KB: each warp fetches its slice with one
@@ -441,7 +756,6 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan_tiles(const __grid_con
 // be bulk-copied (other dtype, strided, unaligned) are read through registers into the same pipeline.
 constexpr int kStMaxBytesLimit = 64 * 1024;
 
-XTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
 template <class T, int kStThreads, int kStCtas, bool CHAINED>
 __global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_scan_stile(const __grid_constant__ ScanParams p) {
@@ -617,360 +931,6 @@ __global__ void __launch_bounds__(kStThreads + (CHAINED ? 32 : 0), kStCtas) k_sc
                     if (e0 + i < cvalid) dst[e0 + i] = v[i];
             }
         }
-    }
-}
-
-// ---- contiguous scan, chained rows: persistent CTAs over a ring of tiles (opt-in: XTB_SCAN_RING=1) ----
-// k_scan_stile holds a 64 KB super-tile in shared memory from its load until the look-back of the tile has
-// finished; a tile cannot finish before EVERY older tile has published its aggregate, and under bandwidth
-// saturation those loads complete with a spread of several microseconds -- the shared memory (and with it
-// the bytes in flight) idles meanwhile: 0.59 of the copy peak on the flat scan.
-// Here one CTA per SM stays resident and cycles 16 KB tiles through a ring of kRgStages shared-memory
-// slots; every hand-over is an mbarrier, so no warp ever waits for a warp doing something else:
-//   producer warp : next tile of this CTA (tiles are dealt round robin over the resident CTAs), waits for
-//                   its slot to be free, issues ONE bulk copy -> full[s]
-//   scan warps    : 2 groups x 8 warps, group g owns the CTA's tiles g, g+2, ..: wait full[s], scan the
-//                   warp's 128 vectors in place, hand the warp total over (agg[s]); phase B (add the tile's
-//                   base, stream out, empty[s]) runs kRgSkew tiles of the group later, so a look-back has
-//                   several tile times to complete before anybody has to wait for it
-//   totals warp   : agg[s] -> warp offsets + tile total, publishes the aggregate at once (tot[s])
-//   look-back warps (4, round robin): tile_lookback as in the other kernels (same fixed-shape trees: the
-//                   result depends only on the tile's position), then pre[s]
-// Reads and writes of the data: one each.
-constexpr int kRgTileBytes = 16 * 1024;
-constexpr int kRgStages = 13;
-constexpr int kRgGroupWarps = 8;
-constexpr int kRgAheadWarps = 8;
-// LOOKW look-back warps, SKEW = tiles of one group between a tile's phase A and its phase B.
-// AHEAD = 0: two scan groups.  AHEAD > 0 ("reduce ahead"): one scan group plus kRgAheadWarps warps that
-// reduce the CTA's tiles AHEAD positions before they are scanned and publish the aggregates then: by the
-// time a tile is scanned everything its look-back needs was published long ago (no waiting), and its data
-// is re-read from the L2 (AHEAD x grid x 16 KB in between must stay L2-resident), so HBM still sees one
-// read and one write.  The published aggregate comes from the reduce pass (per-lane ascending sums, then a
-// butterfly: fixed shape), the tile's own elements from the scan pass.
-template <int AHEAD> constexpr int rg_groups() { return AHEAD > 0 ? 1 : 2; }
-template <int LOOKW, int AHEAD> constexpr int rg_threads() {
-    return (rg_groups<AHEAD>() * kRgGroupWarps + 2 + LOOKW + (AHEAD > 0 ? kRgAheadWarps : 0)) * 32;
-}
-
-XTB_DEV void mbar_init(unsigned long long* b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-XTB_DEV void mbar_arrive(unsigned long long* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-XTB_DEV void mbar_wait(unsigned long long* b, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    }
-}
-
-template <class T, int LOOKW, int SKEW, int AHEAD>
-__global__ void __launch_bounds__(rg_threads<LOOKW, AHEAD>(), 1) k_scan_ring(const __grid_constant__ ScanParams p) {
-    constexpr int kRgLookWarps = LOOKW, kRgSkew = SKEW;
-    constexpr int kRgGroups = rg_groups<AHEAD>();
-    constexpr int kRgScanWarps = kRgGroups * kRgGroupWarps;
-    constexpr int kRgWarpP = kRgScanWarps, kRgWarpT = kRgScanWarps + 1, kRgWarpL0 = kRgScanWarps + 2;
-    constexpr int kRgWarpR0 = kRgWarpL0 + LOOKW;
-    constexpr int kRgSentinels = LOOKW > kRgGroups ? LOOKW : kRgGroups;
-    constexpr int VEC = 16 / (int) sizeof(T), NV = 4;
-    constexpr int TE = kRgTileBytes / (int) sizeof(T);           // elements per tile
-    constexpr int WE = TE / kRgGroupWarps;                       // elements per scan warp = 128 vectors
-    static_assert(WE == 32 * NV * VEC, "a scan warp owns NV vectors per lane");
-    extern __shared__ __align__(128) unsigned char rg_smem[];
-    __shared__ __align__(8) unsigned long long b_full[kRgStages], b_agg[kRgStages], b_tot[kRgStages], b_pre[kRgStages], b_empty[kRgStages];
-    __shared__ int32_t s_tile[kRgStages];
-    __shared__ int32_t s_valid[kRgStages];
-    __shared__ T s_wtot[kRgStages][kRgGroupWarps];
-    __shared__ T s_woff[kRgStages][kRgGroupWarps];
-    __shared__ T s_total[kRgStages];
-    __shared__ T s_prefix[kRgStages];
-    __shared__ int s_done;                                       // tiles of this CTA whose phase B has run (reduce-ahead throttle)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int op = p.op;
-    const T ident = scan_identity<T>(op);
-    if (tid == 0) {
-        s_done = 0;
-        for (int s = 0; s < kRgStages; ++s) {
-            mbar_init(&b_full[s], 1);
-            mbar_init(&b_agg[s], kRgGroupWarps);
-            mbar_init(&b_tot[s], 1);
-            mbar_init(&b_pre[s], 1);
-            mbar_init(&b_empty[s], kRgGroupWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int isz = (int) sizeof(T);
-
-    if (warp == kRgWarpP) {
-        // ---- producer ----
-        if (lane == 0) {
-            int posted = 0;   // sentinels posted after the CTA's last tile (every consumer role sees one)
-            for (int n = 0;; ++n) {
-                const int s = n % kRgStages, r = n / kRgStages;
-                if (r > 0) {
-                    mbar_wait(&b_empty[s], (uint32_t) ((r - 1) & 1));
-                    // the scan warps' generic-proxy accesses to the slot (observed through the barrier) are
-                    // ordered before the bulk copy that overwrites it
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                }
-                // CTA c owns tiles c, c + grid, ..: every CTA is resident (grid <= SM count, one CTA per SM), so
-                // all predecessors of a tile are in flight at about the same ring position of their CTAs
-                const uint64_t tile64 = (uint64_t) blockIdx.x + (uint64_t) n * gridDim.x;
-                const uint32_t tile = tile64 < p.total_tiles ? (uint32_t) tile64 : 0xffffffffu;
-                if (tile >= p.total_tiles) {
-                    s_tile[s] = -1;
-                    mbar_arrive(&b_full[s]);
-                    if (++posted == kRgSentinels) break;
-                    continue;
-                }
-                const uint32_t row = tile / p.tiles_per_row;
-                const uint32_t trow = tile - row * p.tiles_per_row;
-                const int64_t tbase = (int64_t) trow * TE;
-                const int64_t left = p.n - tbase;
-                const int valid = left < TE ? (int) left : TE;
-                s_tile[s] = (int32_t) tile;
-                s_valid[s] = valid;
-                const char* src = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz + tbase * isz;
-                const uint32_t bytes = (uint32_t) valid * (uint32_t) sizeof(T);
-                const uint32_t bar = smem_u32(&b_full[s]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(rg_smem + (size_t) s * kRgTileBytes)), "l"(src), "r"(bytes), "r"(bar) : "memory");
-            }
-        }
-        return;
-    }
-    if (warp == kRgWarpT) {
-        // ---- totals: warp offsets, tile total, aggregate published at once ----
-        for (int n = 0;; ++n) {
-            const int s = n % kRgStages;
-            const uint32_t par = (uint32_t) ((n / kRgStages) & 1);
-            mbar_wait(&b_full[s], par);
-            const int32_t tile = s_tile[s];
-            if (tile < 0) break;
-            mbar_wait(&b_agg[s], par);
-            T wv = lane < kRgGroupWarps ? s_wtot[s][lane] : ident;
-#pragma unroll
-            for (int d = 1; d < kRgGroupWarps; d <<= 1) {
-                const T y = shfl_up_t<T>(wv, d);
-                if (lane >= d) wv = scan_op<T>(op, y, wv);
-            }
-            const T total = shfl_idx_t<T>(wv, kRgGroupWarps - 1);
-            const T excl = shfl_up_t<T>(wv, 1);
-            if (lane < kRgGroupWarps) s_woff[s][lane] = lane == 0 ? ident : excl;
-            if (lane == 0) {
-                const uint32_t row = (uint32_t) tile / p.tiles_per_row;
-                const uint32_t trow = (uint32_t) tile - row * p.tiles_per_row;
-                s_total[s] = total;
-                if constexpr (AHEAD == 0) {
-                    if (trow + 1 < p.tiles_per_row) slot_publish<T>(p.aggregate, (uint32_t) tile, total);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b_tot[s]);
-        }
-        return;
-    }
-    if (warp >= kRgWarpL0) {
-        // ---- look-back: tiles l, l + kRgLookWarps, .. of this CTA ----
-        for (int n = warp - kRgWarpL0;; n += kRgLookWarps) {
-            const int s = n % kRgStages;
-            const uint32_t par = (uint32_t) ((n / kRgStages) & 1);
-            mbar_wait(&b_full[s], par);
-            const int32_t tile = s_tile[s];
-            if (tile < 0) break;
-            const uint32_t row = (uint32_t) tile / p.tiles_per_row;
-            const uint32_t trow = (uint32_t) tile - row * p.tiles_per_row;
-            T part;
-            const T e = tile_lookback<T>(p, op, row, trow, lane, &part);
-            mbar_wait(&b_tot[s], par);
-            if (lane == 0) {
-                if constexpr (AHEAD == 0) {
-                    const uint32_t kb = trow / kScanWindow;
-                    if (trow - kb * kScanWindow == kScanWindow - 1 && trow + 1 < p.tiles_per_row) {
-                        const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
-                        slot_publish<T>(p.prefix, row * blocks_per_row + kb, scan_op<T>(op, part, *(volatile T*) &s_total[s]));
-                    }
-                }
-                s_prefix[s] = e;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b_pre[s]);
-        }
-        return;
-    }
-    if constexpr (AHEAD > 0) {
-        if (warp >= kRgWarpR0) {
-            // ---- reduce ahead: tiles r, r + kRgAheadWarps, .. of this CTA, at most AHEAD tiles before their scan ----
-            constexpr int NB = 16;                                   // 128-bit loads in flight per lane
-            for (int m = warp - kRgWarpR0;; m += kRgAheadWarps) {
-                const uint64_t tile64 = (uint64_t) blockIdx.x + (uint64_t) m * gridDim.x;
-                if (tile64 >= p.total_tiles) break;
-                const uint32_t tile = (uint32_t) tile64;
-                while (m > *(volatile int*) &s_done + AHEAD) __nanosleep(200);
-                const uint32_t row = tile / p.tiles_per_row;
-                const uint32_t trow = tile - row * p.tiles_per_row;
-                if (trow + 1 >= p.tiles_per_row) continue;           // the last tile of a row has no successor
-                const int64_t tbase = (int64_t) trow * TE;
-                const int64_t left = p.n - tbase;
-                const int nvec = (int) (left < TE ? left : TE) / VEC;
-                const char* src = p.in + scan_offset(row, p.n_outer, p.outer_shape, p.outer_stride, p.outer_div) * isz + tbase * isz;
-                T acc = ident;
-                for (int v0 = 0; v0 < TE / VEC; v0 += 32 * NB) {
-                    if (v0 >= nvec) break;                           // warp-uniform
-                    uint4 raw[NB];
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const int vi = v0 + b * 32 + lane;
-                        raw[b] = vi < nvec ? ldg_stream_16(src + (size_t) vi * 16) : make_uint4(0, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const int vi = v0 + b * 32 + lane;
-                        if (vi < nvec) {
-                            T e[VEC];
-                            memcpy(&e[0], &raw[b], 16);
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) acc = scan_op<T>(op, acc, e[i]);
-                        }
-                    }
-                }
-                acc = warp_total<T>(op, acc);
-                if (lane == 0) slot_publish<T>(p.aggregate, tile, acc);
-                // the last tile of a window also publishes the window's total (needed by every later window) now,
-                // not when it is scanned: it waits only for the aggregates of its own window, which are being
-                // published by the other CTAs' reduce-ahead warps at this very moment
-                const uint32_t kb = trow / kScanWindow;
-                if (trow - kb * kScanWindow == kScanWindow - 1) {
-                    const T part = window_part<T>(p, op, row, trow, lane);
-                    if (lane == 0) {
-                        const uint32_t blocks_per_row = (p.tiles_per_row + kScanWindow - 1) / kScanWindow;
-                        slot_publish<T>(p.prefix, row * blocks_per_row + kb, scan_op<T>(op, part, acc));
-                    }
-                }
-            }
-            return;
-        }
-    }
-    // ---- scan warps ----
-    const int g = warp / kRgGroupWarps, wl = warp % kRgGroupWarps;
-    bool ended = false;
-    int jend = 0;
-    for (int j = 0;; ++j) {
-        if (!ended) {
-            const int n = g + j * kRgGroups;
-            const int s = n % kRgStages;
-            mbar_wait(&b_full[s], (uint32_t) ((n / kRgStages) & 1));
-            const int32_t tile = s_tile[s];
-            if (tile < 0) {
-                ended = true;
-                jend = j;
-            } else {
-                // phase A: scan my 128 vectors in place, striped over the lanes
-                int myvalid = s_valid[s] - wl * WE;
-                myvalid = myvalid < 0 ? 0 : (myvalid > WE ? WE : myvalid);
-                T* my = (T*) (rg_smem + (size_t) s * kRgTileBytes) + wl * WE;
-                T x[NV][VEC];
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const int e0 = (q * 32 + lane) * VEC;
-                    if (e0 + VEC <= myvalid) {
-                        const uint4 rr = *(const uint4*) (my + e0);
-                        memcpy(&x[q][0], &rr, 16);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) x[q][i] = ident;   // valid counts are multiples of VEC
-                    }
-                }
-                T inc[NV];
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-#pragma unroll
-                    for (int i = 1; i < VEC; ++i) x[q][i] = scan_op<T>(op, x[q][i - 1], x[q][i]);
-                    inc[q] = x[q][VEC - 1];
-                }
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-                    for (int q = 0; q < NV; ++q) {
-                        const T y = shfl_up_t<T>(inc[q], d);
-                        if (lane >= d) inc[q] = scan_op<T>(op, y, inc[q]);
-                    }
-                }
-                T carry = ident;
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const T ex = shfl_up_t<T>(inc[q], 1);
-                    const T rowtot = shfl_idx_t<T>(inc[q], 31);
-                    if (q == 0) {
-                        if (lane > 0) {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) x[q][i] = scan_op<T>(op, ex, x[q][i]);
-                        }
-                        carry = rowtot;
-                    } else {
-                        const T o = lane == 0 ? carry : scan_op<T>(op, carry, ex);
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) x[q][i] = scan_op<T>(op, o, x[q][i]);
-                        carry = scan_op<T>(op, carry, rowtot);
-                    }
-                    uint4 rr;
-                    memcpy(&rr, &x[q][0], 16);
-                    *(uint4*) (my + (q * 32 + lane) * VEC) = rr;
-                }
-                if (lane == 0) s_wtot[s][wl] = carry;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&b_agg[s]);
-            }
-        }
-        const int jb = j - kRgSkew;
-        if (jb >= 0 && (!ended || jb < jend)) {
-            // phase B of an earlier tile of my group: add its base, stream out, free the slot
-            const int n = g + jb * kRgGroups;
-            const int s = n % kRgStages;
-            mbar_wait(&b_pre[s], (uint32_t) ((n / kRgStages) & 1));
-            const uint32_t tile = (uint32_t) s_tile[s];
-            const uint32_t row = tile / p.tiles_per_row;
-            const uint32_t trow = tile - row * p.tiles_per_row;
-            int myvalid = s_valid[s] - wl * WE;
-            myvalid = myvalid < 0 ? 0 : (myvalid > WE ? WE : myvalid);
-            const T woff = s_woff[s][wl];
-            T base = woff;
-            bool have = wl > 0;
-            if (trow > 0) {
-                const T e = s_prefix[s];
-                base = wl > 0 ? scan_op<T>(op, e, woff) : e;
-                have = true;
-            }
-            const T* my = (const T*) (rg_smem + (size_t) s * kRgTileBytes) + wl * WE;
-            T* dst = (T*) p.out + (int64_t) row * p.n + (int64_t) trow * TE + wl * WE;
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                const int e0 = (q * 32 + lane) * VEC;
-                if (e0 + VEC <= myvalid) {
-                    T v[VEC];
-                    const uint4 rr = *(const uint4*) (my + e0);
-                    memcpy(&v[0], &rr, 16);
-                    if (have) {
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) v[i] = scan_op<T>(op, base, v[i]);
-                    }
-                    uint4 w;
-                    memcpy(&w, &v[0], 16);
-                    stg_stream_16(dst + e0, w);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b_empty[s]);
-            if constexpr (AHEAD > 0) {
-                if (wl == 0 && lane == 0) *(volatile int*) &s_done = n + 1;
-            }
-        }
-        if (ended && jb >= jend - 1) break;
     }
 }
 
@@ -1248,6 +1208,114 @@ __global__ void __launch_bounds__(kCtThreads, 3) k_scan_coltile(const __grid_con
     }
 }
 
+// ---- strided axis, many columns: column walkers over a TMA ring ---------------------------------------
+// With at least ~one strip of 32 columns per SM there is enough parallelism ACROSS the columns, so nothing
+// has to be chained along the axis: a walker (one CTA: a producer warp and a consumer warp) owns a strip of
+// 32 x CV columns and walks the whole axis top to bottom.  The producer keeps `stages` TMA boxes of R rows
+// in flight in a shared-memory ring (cp.async.bulk.tensor -> mbarrier); the consumer adds row after row into
+// the running column totals it holds in registers and stores each row as it goes.  No look-back, no second
+// pass, and every column is accumulated in exactly the reference's order (accumulator_impl,
+// xaccumulator.hpp:282-294): bit-exact for floating point too.  One read + one write of the data.
+constexpr int kCwRows = 64;          // rows per TMA box
+
+struct ColWalkParams {
+    int32_t W;           // columns per walker (32 * CV)
+    int32_t strips;      // walkers across the columns
+    int32_t stages;      // ring depth
+    int32_t chunks;      // boxes along the axis = ceil(n / kCwRows)
+};
+
+
+template <int N> struct VecOf;
+template <> struct VecOf<4> { using type = uint32_t; };
+template <> struct VecOf<8> { using type = uint2; };
+template <> struct VecOf<16> { using type = uint4; };
+
+template <class T, int CV, int OP>
+__global__ void __launch_bounds__(64) k_scan_colwalk(const __grid_constant__ ScanParams p, const __grid_constant__ ColWalkParams c,
+                                                      const __grid_constant__ CUtensorMap tmap) {
+    using Vec = typename VecOf<(int) sizeof(T) * CV>::type;
+    extern __shared__ __align__(128) unsigned char cw_smem[];
+    __shared__ __align__(8) unsigned long long s_full[16], s_empty[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int W = 32 * CV;
+    constexpr uint32_t stage_bytes = (uint32_t) (kCwRows * W * (int) sizeof(T));
+    const uint32_t walker = blockIdx.x;
+    const uint32_t o = walker / (uint32_t) c.strips;
+    const uint32_t strip = walker - o * (uint32_t) c.strips;
+    const int64_t col0 = (int64_t) strip * W;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < c.stages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_empty[s])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        // ---- producer: one elected lane keeps the ring full ----
+        if (lane == 0) {
+            for (int it = 0; it < c.chunks; ++it) {
+                const int s = it % c.stages;
+                if (it >= c.stages) mbar_wait(smem_u32(&s_empty[s]), (uint32_t) ((it / c.stages) + 1) & 1u);
+                const uint32_t bar = smem_u32(&s_full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(smem_u32(cw_smem + (size_t) s * stage_bytes)), "l"(&tmap), "r"((int) col0), "r"(it * kCwRows), "r"((int) o), "r"(bar)
+                             : "memory");
+            }
+        }
+        return;
+    }
+    // ---- consumer: lane owns CV adjacent columns; one shared-memory vector load and one store per row ----
+    const int64_t col = col0 + (int64_t) lane * CV;
+    const bool active = col < p.inner;                     // inner is a multiple of CV (host-checked)
+    T acc[CV];
+#pragma unroll
+    for (int k = 0; k < CV; ++k) acc[k] = sident<OP, T>();
+    char* d = (char*) ((T*) p.out + (int64_t) o * p.n * p.inner + col);
+    const int64_t row_bytes = p.inner * (int64_t) sizeof(T);
+    for (int it = 0; it < c.chunks; ++it) {
+        const int s = it % c.stages;
+        mbar_wait(smem_u32(&s_full[s]), (uint32_t) (it / c.stages) & 1u);
+        const Vec* q = (const Vec*) (cw_smem + (size_t) s * stage_bytes) + lane;      // row r: q[r * 32]
+        const int64_t r0 = (int64_t) it * kCwRows;
+        const int rv = (int) (p.n - r0 < kCwRows ? p.n - r0 : kCwRows);
+        if (rv == kCwRows && it > 0) {
+            // batches of kB rows: all shared-memory loads of a batch first, then the dependent chain of adds and stores
+            constexpr int kB = 16;
+#pragma unroll 1
+            for (int rb = 0; rb < kCwRows; rb += kB) {
+                Vec xv[kB];
+#pragma unroll
+                for (int u = 0; u < kB; ++u) xv[u] = q[(rb + u) * 32];
+                asm volatile("" ::: "memory");         // keep all kB loads in flight: the chain below runs at one row per add latency
+#pragma unroll
+                for (int u = 0; u < kB; ++u) {
+                    T x[CV];
+                    memcpy(&x[0], &xv[u], sizeof(Vec));
+#pragma unroll
+                    for (int k = 0; k < CV; ++k) acc[k] = sop<OP, T>(acc[k], x[k]);
+                    if (active) memcpy_stream<sizeof(Vec)>(d, &acc[0]);
+                    d += row_bytes;
+                }
+            }
+        } else {
+            for (int r = 0; r < rv; ++r) {
+                T x[CV];
+                const Vec xv = q[r * 32];
+                memcpy(&x[0], &xv, sizeof(Vec));
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[k] = (it == 0 && r == 0) ? x[k] : sop<OP, T>(acc[k], x[k]);   // out[0] = in[0]
+                if (active) memcpy_stream<sizeof(Vec)>(d, &acc[0]);
+                d += row_bytes;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[s])) : "memory");
+    }
+}
+
 template <class T> static int scan_coltile(ScanParams p, DeviceCtx* ctx) {
     ColTileParams c;
     memset(&c, 0, sizeof(c));
@@ -1300,7 +1368,7 @@ template <class T> static int scan_coltile(ScanParams p, DeviceCtx* ctx) {
     const unsigned threads = kCtThreads;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    if (bulk && p.n_outer <= 1 && c.R <= 256 && getenv("XTB_NO_TMA") == nullptr) {
+    if (bulk && p.n_outer <= 1 && c.R <= 256 && !options().no_tma) {
         // 3-D view (inner, axis, outer) of the input; box = (W, R, 1)
         static PFN_cuTensorMapEncodeTiled encode = nullptr;
         if (!encode) {
@@ -1332,6 +1400,89 @@ template <class T> static int scan_coltile(ScanParams p, DeviceCtx* ctx) {
     }
     note_launch(c.chunks > 1 ? (c.tma ? "k_scan_coltile[TMA, look-back]" : "k_scan_coltile[look-back]") : (c.tma ? "k_scan_coltile[TMA]" : "k_scan_coltile"));
     return check_launch("k_scan_coltile");
+}
+
+// Column walkers apply when the tile rows can be fetched by TMA (dense inner dims of the accumulator dtype,
+// 16-byte aligned) and there are enough strips to occupy the GPU.  Returns 1 when they do not apply.
+template <class T> static int scan_colwalk(const ScanParams& p, DeviceCtx* ctx) {
+    const int64_t asz = sizeof(T);
+    bool ok = std::is_same<T, float>::value ? p.in_dtype == XTB_F32
+            : std::is_same<T, double>::value ? p.in_dtype == XTB_F64
+            : sizeof(T) == 4 ? (p.in_dtype == XTB_I32 || p.in_dtype == XTB_U32)
+                             : (p.in_dtype == XTB_I64 || p.in_dtype == XTB_U64);
+    ok = ok && !options().no_tma && (uintptr_t) p.in % 16 == 0 && (uintptr_t) p.out % 16 == 0 && (p.inner * asz) % 16 == 0 &&
+         (p.in_axis_stride * asz) % 16 == 0 && p.in_axis_stride > 0 && p.n_outer <= 1 && p.n >= 4 * kCwRows;
+    int64_t expect = 1;
+    for (int d = p.n_inner - 1; d >= 0 && ok; --d) {
+        if (p.inner_shape[d] != 1 && p.inner_stride[d] != expect) ok = false;
+        expect *= p.inner_shape[d];
+    }
+    const int64_t outer_stride = p.n_outer == 1 && p.outer_shape[0] > 1 ? p.outer_stride[0] : p.n * p.in_axis_stride;
+    ok = ok && (outer_stride * asz) % 16 == 0 && outer_stride > 0;
+    if (!ok) return 1;
+    // Strip width: the widest (32 lanes x 16 bytes: one LDS.128 + one STG.128 per row, fewest instructions per
+    // element) unless that leaves fewer than ~a third of the SMs with a walker; then narrower strips.
+    const int cv_max = 16 / (int) asz;
+    int cv = cv_max;
+    while (cv > 1 && ((p.inner + 32 * cv - 1) / (32 * cv)) * p.rows < (int64_t) ctx->sm_count / 3) cv >>= 1;
+    ColWalkParams c;
+    c.W = 32 * cv;
+    c.strips = (int32_t) ((p.inner + c.W - 1) / c.W);
+    const int64_t walkers = (int64_t) c.strips * p.rows;
+    if (walkers < ctx->sm_count / 3 || walkers >= 0x7fffffffLL || p.inner % cv != 0) return 1;
+    c.chunks = (int32_t) ((p.n + kCwRows - 1) / kCwRows);
+    // ring depth: ~20 MB of boxes in flight over the whole GPU; up to 3 walkers share an SM's 200 KB of rings
+    const int64_t stage_bytes = (int64_t) kCwRows * c.W * asz;
+    const int64_t per_sm = std::min<int64_t>(3, (walkers + ctx->sm_count - 1) / ctx->sm_count);
+    const int64_t ring_cap = (200 * 1024) / per_sm;
+    const int64_t ring_need = ((int64_t) 20 << 20) / std::min<int64_t>(walkers, per_sm * ctx->sm_count);
+    int64_t stages = std::min(ring_cap, std::max(ring_need, 2 * stage_bytes)) / stage_bytes;
+    stages = std::max<int64_t>(2, std::min<int64_t>(stages, 16));
+    if (options().scan_variant < 0) stages = std::max<int64_t>(2, std::min<int64_t>(-options().scan_variant, 16));
+    stages = std::min<int64_t>(stages, std::max<int64_t>(2, c.chunks));
+    c.stages = (int32_t) stages;
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = (PFN_cuTensorMapEncodeTiled) fn;
+    }
+    if (!encode) return 1;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const CUtensorMapDataType dt = std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : std::is_same<T, double>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+                                 : sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+    const cuuint64_t gdim[3] = {(cuuint64_t) p.inner, (cuuint64_t) p.n, (cuuint64_t) p.rows};
+    const cuuint64_t gstr[2] = {(cuuint64_t) (p.in_axis_stride * asz), (cuuint64_t) (outer_stride * asz)};
+    const cuuint32_t box[3] = {(cuuint32_t) c.W, (cuuint32_t) kCwRows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (encode(&tmap, dt, 3, (void*) p.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    const size_t smem = (size_t) stages * (size_t) stage_bytes;
+#define XTB_CW_LAUNCH(CVV)                                                                                                       \
+    do {                                                                                                                         \
+        if (p.op == XTB_RED_PROD) {                                                                                              \
+            XTB_CUDA(cudaFuncSetAttribute(k_scan_colwalk<T, CVV, XTB_RED_PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); \
+            k_scan_colwalk<T, CVV, XTB_RED_PROD><<<(unsigned) walkers, 64, smem, ctx->stream>>>(p, c, tmap);                     \
+        } else {                                                                                                                 \
+            XTB_CUDA(cudaFuncSetAttribute(k_scan_colwalk<T, CVV, XTB_RED_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));  \
+            k_scan_colwalk<T, CVV, XTB_RED_SUM><<<(unsigned) walkers, 64, smem, ctx->stream>>>(p, c, tmap);                      \
+        }                                                                                                                        \
+    } while (0)
+    if constexpr (sizeof(T) == 4) {
+        if (cv == 4) XTB_CW_LAUNCH(4);
+        else if (cv == 2) XTB_CW_LAUNCH(2);
+        else XTB_CW_LAUNCH(1);
+    } else {
+        if (cv == 2) XTB_CW_LAUNCH(2);
+        else XTB_CW_LAUNCH(1);
+    }
+#undef XTB_CW_LAUNCH
+    note_launch("k_scan_colwalk[TMA ring, reference order]");
+    return check_launch("k_scan_colwalk");
 }
 
 // ---- strided axis: one thread per column ------------------------------------------------------
@@ -1366,6 +1517,46 @@ __global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ Sc
     }
 }
 
+// rows longer than one staged tile: reduce ahead, scan from L2 (k_scan_ahead)
+template <class T, int NV> static int launch_scan_ahead(ScanParams q, DeviceCtx* ctx) {
+    using C = ScanTile<T>;
+    const int64_t te = (int64_t) kScanThreads * NV * (16 / (int64_t) sizeof(T));       // 16 KB tiles
+    const int64_t tpr = (q.n + te - 1) / te;
+    const int64_t tiles = tpr * q.rows;
+    LbTree tr;
+    memset(&tr, 0, sizeof(tr));
+    // look-ahead distance: 24 MB = 1536 tiles -- more than twice the ~740 CTAs in flight, so that a tile's scan visit
+    // never meets aggregates that are still being computed; it has to stay in the 126 MB L2 next to as many
+    // bytes of stores.  At most half the work.
+    int64_t ahead_mb = options().scan_variant > 0 ? options().scan_variant : 24;
+    int64_t ahead = std::min<int64_t>((ahead_mb << 20) / (te * (int64_t) sizeof(T)), std::max<int64_t>(64, tiles / 2)) / 64 * 64;
+    if (ahead < 64) ahead = 64;
+    tr.ahead = (uint32_t) ahead;
+    if (tiles + ahead >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
+    q.tiles_per_row = (uint32_t) tpr;
+    q.total_tiles = (uint32_t) tiles;
+    int64_t slots = 0, units = tpr;
+    while (true) {
+        if (tr.levels >= kLbMaxLevels) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: row too long");
+        tr.units[tr.levels] = (uint32_t) units;
+        tr.level_off[tr.levels] = (uint32_t) slots;
+        slots += units * q.rows;
+        ++tr.levels;
+        if (units <= kLbFan) break;
+        units = (units + kLbFan - 1) / kLbFan;
+    }
+    if (slots >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
+    const size_t bytes = ((size_t) slots * C::SLOT + 255) / 256 * 256;
+    void* scratch = nullptr;
+    XTB_TRY(ensure_scratch(ctx, bytes, &scratch));
+    tr.slots = (char*) scratch;
+    XTB_CUDA(cudaMemsetAsync(scratch, 0, bytes, ctx->stream));
+    if (q.op == XTB_RED_PROD) k_scan_ahead<T, NV, XTB_RED_PROD><<<(unsigned) (tiles + ahead), kScanThreads, 0, ctx->stream>>>(q, tr);
+    else k_scan_ahead<T, NV, XTB_RED_SUM><<<(unsigned) (tiles + ahead), kScanThreads, 0, ctx->stream>>>(q, tr);
+    note_launch("k_scan_ahead[reduce ahead, scan from L2]");
+    return check_launch("k_scan_ahead");
+}
+
 template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, bool columns) {
     if (columns) {
         const int64_t cols = p.rows * p.inner;
@@ -1398,45 +1589,9 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
         return check_launch("k_scan_tiles");
     }
     const int64_t row_bytes = q.n * (int64_t) sizeof(T);
-    if (getenv("XTB_SCAN_RING") && q.vec_io && row_bytes >= 16 * (int64_t) kRgTileBytes && q.n % C::VEC == 0) {
-        // opt-in: persistent CTAs over a ring of 16 KB tiles (k_scan_ring)
-        const int64_t te = kRgTileBytes / (int64_t) sizeof(T);
-        const int64_t tpr = (q.n + te - 1) / te;
-        const int64_t tiles = tpr * q.rows;
-        if (tiles >= 0x7fffffffLL) XTB_FAIL(XTB_ERR_UNSUPPORTED, "scan: too many tiles");
-        q.tiles_per_row = (uint32_t) tpr;
-        q.total_tiles = (uint32_t) tiles;
-        q.st_elems = (int32_t) te;
-        const int64_t bpr = (tpr + kScanWindow - 1) / kScanWindow;
-        const size_t agg_bytes = ((size_t) tiles * C::SLOT + 255) / 256 * 256;
-        const size_t blk_bytes = ((size_t) (bpr * q.rows) * C::SLOT + 255) / 256 * 256;
-        void* scratch = nullptr;
-        XTB_TRY(ensure_scratch(ctx, agg_bytes + blk_bytes, &scratch));
-        char* s = (char*) scratch;
-        q.aggregate = s;
-        q.prefix = s + agg_bytes;
-        XTB_CUDA(cudaMemsetAsync(s, 0, agg_bytes + blk_bytes, ctx->stream));
-        const size_t smem = (size_t) kRgStages * kRgTileBytes;
-        const unsigned grid = (unsigned) std::min<int64_t>(tiles, (int64_t) ctx->sm_count);
-        const int variant = atoi(getenv("XTB_SCAN_RING"));
-#define XTB_RING_LAUNCH(LW, SK, AH)                                                                                          \
-    do {                                                                                                                     \
-        XTB_CUDA(cudaFuncSetAttribute(k_scan_ring<T, LW, SK, AH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-        k_scan_ring<T, LW, SK, AH><<<grid, rg_threads<LW, AH>(), smem, ctx->stream>>>(q);                                    \
-    } while (0)
-        switch (variant) {   // measured on flat 2^26 fp32: 1 -> 0.193 ms, 2 -> 0.217, 3 -> 0.158, 4 -> 0.297 (k_scan_stile: 0.142)
-            case 2: XTB_RING_LAUNCH(8, 2, 0); break;
-            case 3: XTB_RING_LAUNCH(4, 3, 0); break;
-            case 4: XTB_RING_LAUNCH(4, 1, 0); break;
-            case 5: XTB_RING_LAUNCH(4, 2, 8); break;     // reduce ahead (not yet run on the device)
-            case 6: XTB_RING_LAUNCH(4, 2, 16); break;
-            case 7: XTB_RING_LAUNCH(4, 2, 32); break;
-            default: XTB_RING_LAUNCH(4, 2, 0); break;
-        }
-#undef XTB_RING_LAUNCH
-        note_launch(variant >= 5 ? "k_scan_ring[reduce-ahead]" : "k_scan_ring[look-back]");
-        return check_launch("k_scan_ring");
-    }
+    // rows longer than one staged tile: reduce ahead, scan from L2 (k_scan_ahead)
+    // rows longer than one staged tile: reduce ahead, scan from L2 (k_scan_ahead)
+    if (q.n * (int64_t) sizeof(T) > 64 * 1024) return options().scan_nv == 8 ? launch_scan_ahead<T, 8>(q, ctx) : launch_scan_ahead<T, 4>(q, ctx);
     // staged super-tile configuration: threads per CTA / CTAs per SM / super-tile bytes
     // staged super-tiles: long rows (several tiles, look-back) use 8 scan warps + the look-back warp on 64 KB,
     // 3 CTAs per SM; rows of one tile use 4 warps on up to 32 KB, 6 CTAs per SM
@@ -1576,6 +1731,14 @@ extern "C" int xtb_scan(int op, int acc_type, const xtb_operand* in, int axis, c
         // thread-per-column walk (exactly the reference's order, enough parallelism from the columns).
         if (p.n >= 128 && p.inner < 0x7fffffffLL - 256) {
             int r;
+            // enough column strips to fill the GPU: walkers (no chaining along the axis, reference order)
+            switch (acc_type) {
+                case XTB_I32: case XTB_U32: r = scan_colwalk<uint32_t>(p, ctx); break;
+                case XTB_I64: case XTB_U64: r = scan_colwalk<unsigned long long>(p, ctx); break;
+                case XTB_F32: r = scan_colwalk<float>(p, ctx); break;
+                default: r = scan_colwalk<double>(p, ctx); break;
+            }
+            if (r <= 0) return r;
             switch (acc_type) {
                 case XTB_I32: case XTB_U32: r = scan_coltile<uint32_t>(p, ctx); break;
                 case XTB_I64: case XTB_U64: r = scan_coltile<unsigned long long>(p, ctx); break;

@@ -629,6 +629,11 @@ def assign(out: Array, e) -> Array:
     shp = broadcast_shape([e.shape])
     if broadcast_shape([shp, out.shape]) != out.shape:
         raise BroadcastError(f"cannot assign shape {shp} into {out.shape}")
+    fr = _finalized_reducer(e)
+    if fr is not None and isinstance(out, DeviceArray) and (_leaf_kind(e) or DeviceArray) is DeviceArray and out.shape == fr[0].shape:
+        # device: the division is the reduction kernel's epilogue (one launch fewer, same arithmetic)
+        _run_reducer(fr[0], DeviceArray, out=out, fin=fr[1])
+        return out
     lw = lower(e)
     kind = _kind(lw.leaves, out)
     be, pre = _backend_for(kind)
@@ -667,6 +672,22 @@ def _leaf_kind(e: Expr):
     return None
 
 
+def _finalized_reducer(e: Expr):
+    """`sum(...) / scalar` (xt::mean, xt::variance: core/xmath.hpp:1827-1852, 2082-2105) and sqrt of it (xt::stddev):
+    returns (reducer, capi.Finalize) when the division can be fused into the reduction's last store, else None.
+    The fused step computes exactly what the separate kernel would: T(sum) / T(divisor) in the node's value type."""
+    fin_op = capi.FIN_DIV
+    if isinstance(e, Func) and e.op == "SQRT" and isinstance(e.args[0], Func) and e.dtype == e.args[0].dtype:
+        e, fin_op = e.args[0], capi.FIN_DIV_SQRT
+    if not (isinstance(e, Func) and e.op == "DIV" and isinstance(e.args[0], Reducer) and isinstance(e.args[1], Scalar)):
+        return None
+    r, t = e.args[0], e.dtype
+    if t not in (F32, F64) or r.op != capi.RED_SUM or r.acc < I32:
+        return None
+    fin = capi.Finalize(fin_op, t, _imm_bits(e.args[1].value, t))
+    return r, fin
+
+
 def evaluate(e, dtype: Optional[int] = None) -> Array:
     """xt::eval / container construction from an expression: allocate + assign."""
     e = as_expr(e)
@@ -680,7 +701,7 @@ def evaluate(e, dtype: Optional[int] = None) -> Array:
 
 
 def _run_reducer(r: Reducer, kind, out_dtype: Optional[int] = None, allreduce: bool = False, mode: int = 0,
-                 out: Optional[Array] = None) -> Array:
+                 out: Optional[Array] = None, fin=None) -> Array:
     inner = _materialise(r.e)
     lw = Lowered()
     _emit_value(lw, inner, None)
@@ -696,6 +717,11 @@ def _run_reducer(r: Reducer, kind, out_dtype: Optional[int] = None, allreduce: b
         init_p = C.cast(C.create_string_buffer(buf, len(buf)), C.c_void_p)
     be, pre = _backend_for(kind)
     last = int(allreduce) if kind is DeviceArray else int(mode)
+    if fin is not None:
+        assert kind is DeviceArray
+        _check(kind, be.xtb_reduce_fin(r.op, r.acc, C.byref(prog), ops, nd, shape, len(r.axes), axes,
+                                       int(r.keep_dims), init_p, C.byref(oop), last, C.byref(fin)))
+        return out
     _check(kind, getattr(be, pre + "reduce")(r.op, r.acc, C.byref(prog), ops, nd, shape, len(r.axes), axes,
                                              int(r.keep_dims), init_p, C.byref(oop), last))
     return out

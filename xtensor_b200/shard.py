@@ -98,10 +98,18 @@ def sharded_reduce(op: int, local: xt.Expr, axes: Sequence[int], global_rows: in
 def sharded_mean(local: xt.Expr, axes: Sequence[int], global_rows: int, world: int,
                  host_allreduce: Optional[HostAllreduce] = None, dtype=None) -> xt.Array:
     """mean over `axes` of a row-sharded expression: merged sum / GLOBAL count."""
-    s = sharded_reduce(capi.RED_SUM, local, axes, global_rows, world, host_allreduce, dtype)
     full_shape = (global_rows,) + tuple(local.shape[1:])
     n = int(np.prod([full_shape[a] for a in axes], dtype=np.int64))
     vt = xt.F64 if dtype is None else dtype
+    kind = xt._leaf_kind(local) or xt.DeviceArray
+    if kind is xt.DeviceArray:
+        # device: local partial, cross-GPU merge and the division by the GLOBAL count are one call -- the
+        # division is the epilogue of the merge kernel (xtb_reduce_fin), applied once after the exchange
+        r = xt.Reducer(capi.RED_SUM, local, list(axes), acc_dtype=dtype)
+        out = xt.DeviceArray.empty(r.shape, vt)
+        fin = capi.Finalize(capi.FIN_DIV, vt, xt._imm_bits(xt.NP_OF[vt](n), vt))
+        return xt._run_reducer(r, kind, allreduce=(0 in r.axes and world > 1), out=out, fin=fin)
+    s = sharded_reduce(capi.RED_SUM, local, axes, global_rows, world, host_allreduce, dtype)
     return xt.evaluate(s / xt.Scalar(xt.NP_OF[vt](n), vt))
 
 
