@@ -38,6 +38,8 @@ CASES = [
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
 variants = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--variant=")] or [0]
 for a in sys.argv[1:]:
+    if a.startswith("--cv="):
+        capi.check(lib.xtb_set_option(b"tile_variant", int(a.split("=")[1])))
     if a.startswith("--nv="):
         capi.check(lib.xtb_set_option(b"scan_nv", int(a.split("=")[1])))
 for variant in variants:

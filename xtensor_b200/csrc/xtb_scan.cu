@@ -1209,31 +1209,34 @@ __global__ void __launch_bounds__(kCtThreads, 3) k_scan_coltile(const __grid_con
 }
 
 // ---- strided axis, many columns: column walkers over a TMA ring ---------------------------------------
-// With at least ~one strip of 32 columns per SM there is enough parallelism ACROSS the columns, so nothing
-// has to be chained along the axis: a walker (one CTA: a producer warp and a consumer warp) owns a strip of
-// 32 x CV columns and walks the whole axis top to bottom.  The producer keeps `stages` TMA boxes of R rows
-// in flight in a shared-memory ring (cp.async.bulk.tensor -> mbarrier); the consumer adds row after row into
-// the running column totals it holds in registers and stores each row as it goes.  No look-back, no second
-// pass, and every column is accumulated in exactly the reference's order (accumulator_impl,
+// With about one strip of columns per SM there is enough parallelism ACROSS the columns, so nothing has to be
+// chained along the axis: a walker (one CTA: a producer warp and a consumer warp) owns a strip of 32 x CV
+// columns and walks the whole axis top to bottom.  The producer keeps `stages` TMA boxes of 64 rows in flight
+// in a shared-memory ring (cp.async.bulk.tensor -> mbarrier).  The consumer scans a box IN PLACE in shared
+// memory -- per row one LDS, CV adds into the running column totals it holds in registers, one STS, all with
+// immediate offsets -- and hands the box back to the TMA unit, which writes it to the output
+// (cp.async.bulk.tensor global <- shared): no global address arithmetic and no per-row global stores in the
+// instruction stream, rows and columns outside the array are clipped by the tensor maps.  No look-back, no
+// second pass, and every column is accumulated in exactly the reference's order (accumulator_impl,
 // xaccumulator.hpp:282-294): bit-exact for floating point too.  One read + one write of the data.
-constexpr int kCwRows = 64;          // rows per TMA box
+constexpr int kCwRowsMax = 64;       // rows per TMA box: 32 (64 is kept for experiments)
 
 struct ColWalkParams {
     int32_t W;           // columns per walker (32 * CV)
     int32_t strips;      // walkers across the columns
     int32_t stages;      // ring depth
-    int32_t chunks;      // boxes along the axis = ceil(n / kCwRows)
+    int32_t chunks;      // boxes along the axis = ceil(n / box rows)
+    int32_t box_rows;
 };
-
 
 template <int N> struct VecOf;
 template <> struct VecOf<4> { using type = uint32_t; };
 template <> struct VecOf<8> { using type = uint2; };
 template <> struct VecOf<16> { using type = uint4; };
 
-template <class T, int CV, int OP>
+template <class T, int CV, int OP, int kCwRows>
 __global__ void __launch_bounds__(64) k_scan_colwalk(const __grid_constant__ ScanParams p, const __grid_constant__ ColWalkParams c,
-                                                      const __grid_constant__ CUtensorMap tmap) {
+                                                      const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out) {
     using Vec = typename VecOf<(int) sizeof(T) * CV>::type;
     extern __shared__ __align__(128) unsigned char cw_smem[];
     __shared__ __align__(8) unsigned long long s_full[16], s_empty[16];
@@ -1243,7 +1246,7 @@ __global__ void __launch_bounds__(64) k_scan_colwalk(const __grid_constant__ Sca
     const uint32_t walker = blockIdx.x;
     const uint32_t o = walker / (uint32_t) c.strips;
     const uint32_t strip = walker - o * (uint32_t) c.strips;
-    const int64_t col0 = (int64_t) strip * W;
+    const int col0 = (int) (strip * W);
     if (threadIdx.x == 0) {
         for (int s = 0; s < c.stages; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[s])));
@@ -1255,65 +1258,86 @@ __global__ void __launch_bounds__(64) k_scan_colwalk(const __grid_constant__ Sca
     if (warp == 1) {
         // ---- producer: one elected lane keeps the ring full ----
         if (lane == 0) {
+            int s = 0;
+            uint32_t round = 0;
             for (int it = 0; it < c.chunks; ++it) {
-                const int s = it % c.stages;
-                if (it >= c.stages) mbar_wait(smem_u32(&s_empty[s]), (uint32_t) ((it / c.stages) + 1) & 1u);
+                if (round > 0) mbar_wait(smem_u32(&s_empty[s]), (round + 1) & 1u);
                 const uint32_t bar = smem_u32(&s_full[s]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                             ::"r"(smem_u32(cw_smem + (size_t) s * stage_bytes)), "l"(&tmap), "r"((int) col0), "r"(it * kCwRows), "r"((int) o), "r"(bar)
+                             ::"r"(smem_u32(cw_smem + (size_t) s * stage_bytes)), "l"(&tmap_in), "r"(col0), "r"(it * kCwRows), "r"((int) o), "r"(bar)
                              : "memory");
+                if (++s == c.stages) {
+                    s = 0;
+                    ++round;
+                }
             }
         }
         return;
     }
-    // ---- consumer: lane owns CV adjacent columns; one shared-memory vector load and one store per row ----
-    const int64_t col = col0 + (int64_t) lane * CV;
-    const bool active = col < p.inner;                     // inner is a multiple of CV (host-checked)
+    // ---- consumer: lane owns CV adjacent columns of the box ----
     T acc[CV];
 #pragma unroll
     for (int k = 0; k < CV; ++k) acc[k] = sident<OP, T>();
-    char* d = (char*) ((T*) p.out + (int64_t) o * p.n * p.inner + col);
-    const int64_t row_bytes = p.inner * (int64_t) sizeof(T);
+    constexpr int kLag = 2;          // boxes a stage stays with its TMA store before it is handed back
+    int s = 0;
+    uint32_t round = 0;
     for (int it = 0; it < c.chunks; ++it) {
-        const int s = it % c.stages;
-        mbar_wait(smem_u32(&s_full[s]), (uint32_t) (it / c.stages) & 1u);
-        const Vec* q = (const Vec*) (cw_smem + (size_t) s * stage_bytes) + lane;      // row r: q[r * 32]
-        const int64_t r0 = (int64_t) it * kCwRows;
-        const int rv = (int) (p.n - r0 < kCwRows ? p.n - r0 : kCwRows);
-        if (rv == kCwRows && it > 0) {
-            // batches of kB rows: all shared-memory loads of a batch first, then the dependent chain of adds and stores
-            constexpr int kB = 16;
-#pragma unroll 1
-            for (int rb = 0; rb < kCwRows; rb += kB) {
-                Vec xv[kB];
+        mbar_wait(smem_u32(&s_full[s]), round & 1u);
+        Vec* q = (Vec*) (cw_smem + (size_t) s * stage_bytes) + lane;      // row r: q[r * 32]
+        if (it > 0) {
+            // rows past the end of the axis were zero-filled by the load and are clipped by the store
 #pragma unroll
-                for (int u = 0; u < kB; ++u) xv[u] = q[(rb + u) * 32];
-                asm volatile("" ::: "memory");         // keep all kB loads in flight: the chain below runs at one row per add latency
-#pragma unroll
-                for (int u = 0; u < kB; ++u) {
-                    T x[CV];
-                    memcpy(&x[0], &xv[u], sizeof(Vec));
-#pragma unroll
-                    for (int k = 0; k < CV; ++k) acc[k] = sop<OP, T>(acc[k], x[k]);
-                    if (active) memcpy_stream<sizeof(Vec)>(d, &acc[0]);
-                    d += row_bytes;
-                }
-            }
-        } else {
-            for (int r = 0; r < rv; ++r) {
+            for (int r = 0; r < kCwRows; ++r) {
                 T x[CV];
                 const Vec xv = q[r * 32];
                 memcpy(&x[0], &xv, sizeof(Vec));
 #pragma unroll
-                for (int k = 0; k < CV; ++k) acc[k] = (it == 0 && r == 0) ? x[k] : sop<OP, T>(acc[k], x[k]);   // out[0] = in[0]
-                if (active) memcpy_stream<sizeof(Vec)>(d, &acc[0]);
-                d += row_bytes;
+                for (int k = 0; k < CV; ++k) acc[k] = sop<OP, T>(acc[k], x[k]);
+                Vec ov;
+                memcpy(&ov, &acc[0], sizeof(Vec));
+                q[r * 32] = ov;
+            }
+        } else {
+            {   // out[0] = in[0] (a leading -0.0 survives), and the row stays as it is
+                const Vec xv = q[0];
+                memcpy(&acc[0], &xv, sizeof(Vec));
+            }
+#pragma unroll
+            for (int r = 1; r < kCwRows; ++r) {
+                T x[CV];
+                const Vec xv = q[r * 32];
+                memcpy(&x[0], &xv, sizeof(Vec));
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[k] = sop<OP, T>(acc[k], x[k]);
+                Vec ov;
+                memcpy(&ov, &acc[0], sizeof(Vec));
+                q[r * 32] = ov;
             }
         }
+        // the box goes back to the TMA unit: writes of all lanes -> async proxy, then one lane issues the store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[s])) : "memory");
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(&tmap_out), "r"(col0), "r"(it * kCwRows), "r"((int) o), "r"(smem_u32(cw_smem + (size_t) s * stage_bytes))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the store issued kLag boxes ago has read its shared memory by now (no stall in the common case):
+            // that stage may be refilled
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kLag) : "memory");
+            if (it >= kLag) {
+                int sr = s - kLag;
+                if (sr < 0) sr += c.stages;
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[sr])) : "memory");
+            }
+        }
+        if (++s == c.stages) {
+            s = 0;
+            ++round;
+        }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <class T> static int scan_coltile(ScanParams p, DeviceCtx* ctx) {
@@ -1411,7 +1435,7 @@ template <class T> static int scan_colwalk(const ScanParams& p, DeviceCtx* ctx) 
             : sizeof(T) == 4 ? (p.in_dtype == XTB_I32 || p.in_dtype == XTB_U32)
                              : (p.in_dtype == XTB_I64 || p.in_dtype == XTB_U64);
     ok = ok && !options().no_tma && (uintptr_t) p.in % 16 == 0 && (uintptr_t) p.out % 16 == 0 && (p.inner * asz) % 16 == 0 &&
-         (p.in_axis_stride * asz) % 16 == 0 && p.in_axis_stride > 0 && p.n_outer <= 1 && p.n >= 4 * kCwRows;
+         (p.in_axis_stride * asz) % 16 == 0 && p.in_axis_stride > 0 && p.n_outer <= 1 && p.n >= 4 * kCwRowsMax;
     int64_t expect = 1;
     for (int d = p.n_inner - 1; d >= 0 && ok; --d) {
         if (p.inner_shape[d] != 1 && p.inner_stride[d] != expect) ok = false;
@@ -1420,26 +1444,28 @@ template <class T> static int scan_colwalk(const ScanParams& p, DeviceCtx* ctx) 
     const int64_t outer_stride = p.n_outer == 1 && p.outer_shape[0] > 1 ? p.outer_stride[0] : p.n * p.in_axis_stride;
     ok = ok && (outer_stride * asz) % 16 == 0 && outer_stride > 0;
     if (!ok) return 1;
-    // Strip width: the widest (32 lanes x 16 bytes: one LDS.128 + one STG.128 per row, fewest instructions per
-    // element) unless that leaves fewer than ~a third of the SMs with a walker; then narrower strips.
+    // Strip width: the widest box (32 lanes x 16 bytes = 512-byte rows: best use of the DRAM pages) that still gives
+    // ~85 % of the SMs a walker -- a walker's throughput is bounded by its SM's TMA / L2 ports -- else narrower.
     const int cv_max = 16 / (int) asz;
     int cv = cv_max;
-    while (cv > 1 && ((p.inner + 32 * cv - 1) / (32 * cv)) * p.rows < (int64_t) ctx->sm_count / 3) cv >>= 1;
+    while (cv > 1 && ((p.inner + 32 * cv - 1) / (32 * cv)) * p.rows < (int64_t) ctx->sm_count * 85 / 100) cv >>= 1;
+    if (options().tile_variant > 0 && options().tile_variant <= cv_max) cv = options().tile_variant;     // development: forced strip width
     ColWalkParams c;
     c.W = 32 * cv;
     c.strips = (int32_t) ((p.inner + c.W - 1) / c.W);
     const int64_t walkers = (int64_t) c.strips * p.rows;
-    if (walkers < ctx->sm_count / 3 || walkers >= 0x7fffffffLL || p.inner % cv != 0) return 1;
-    c.chunks = (int32_t) ((p.n + kCwRows - 1) / kCwRows);
-    // ring depth: ~20 MB of boxes in flight over the whole GPU; up to 3 walkers share an SM's 200 KB of rings
-    const int64_t stage_bytes = (int64_t) kCwRows * c.W * asz;
-    const int64_t per_sm = std::min<int64_t>(3, (walkers + ctx->sm_count - 1) / ctx->sm_count);
-    const int64_t ring_cap = (200 * 1024) / per_sm;
-    const int64_t ring_need = ((int64_t) 20 << 20) / std::min<int64_t>(walkers, per_sm * ctx->sm_count);
-    int64_t stages = std::min(ring_cap, std::max(ring_need, 2 * stage_bytes)) / stage_bytes;
-    stages = std::max<int64_t>(2, std::min<int64_t>(stages, 16));
-    if (options().scan_variant < 0) stages = std::max<int64_t>(2, std::min<int64_t>(-options().scan_variant, 16));
-    stages = std::min<int64_t>(stages, std::max<int64_t>(2, c.chunks));
+    if (walkers < ctx->sm_count / 3 || walkers >= 0x7fffffffLL || p.inner >= 0x7fffffffLL || p.n >= 0x7fffffffLL) return 1;
+    int box_rows = 32;
+    if (options().scan_nv == 32 || options().scan_nv == 64) box_rows = options().scan_nv;      // development
+    c.box_rows = box_rows;
+    c.chunks = (int32_t) ((p.n + box_rows - 1) / box_rows);
+    // ring: ~96 KB per walker in boxes of 32 rows (measured on (8192, 8192): fp32 0.96 / fp64 0.94 of the copy peak;
+    // deeper rings were SLOWER -- more boxes in flight spread the DRAM accesses over more rows at once)
+    const int64_t stage_bytes = (int64_t) box_rows * c.W * asz;
+    int64_t stages = (96 * 1024) / stage_bytes;
+    stages = std::max<int64_t>(4, std::min<int64_t>(stages, 12));      // a stage is handed back two boxes late (its TMA store must have read it)
+    if (options().scan_variant < 0) stages = std::max<int64_t>(4, std::min<int64_t>(-options().scan_variant, 16));
+    stages = std::min<int64_t>(stages, std::max<int64_t>(4, c.chunks));
     c.stages = (int32_t) stages;
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
@@ -1449,27 +1475,36 @@ template <class T> static int scan_colwalk(const ScanParams& p, DeviceCtx* ctx) 
             encode = (PFN_cuTensorMapEncodeTiled) fn;
     }
     if (!encode) return 1;
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap_out;
     memset(&tmap, 0, sizeof(tmap));
-    const CUtensorMapDataType dt = std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                 : std::is_same<T, double>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
-                                 : sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+    memset(&tmap_out, 0, sizeof(tmap_out));
+    // integer data goes through the maps as raw 32- / 64-bit words; floating-point maps must not flush or canonicalise
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
     const cuuint64_t gdim[3] = {(cuuint64_t) p.inner, (cuuint64_t) p.n, (cuuint64_t) p.rows};
     const cuuint64_t gstr[2] = {(cuuint64_t) (p.in_axis_stride * asz), (cuuint64_t) (outer_stride * asz)};
-    const cuuint32_t box[3] = {(cuuint32_t) c.W, (cuuint32_t) kCwRows, 1u};
+    const cuuint64_t ostr[2] = {(cuuint64_t) (p.inner * asz), (cuuint64_t) (p.n * p.inner * asz)};     // the result is dense
+    const cuuint32_t box[3] = {(cuuint32_t) c.W, (cuuint32_t) box_rows, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (encode(&tmap, dt, 3, (void*) p.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return 1;
+    if (encode(&tmap_out, dt, 3, (void*) p.out, gdim, ostr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
     const size_t smem = (size_t) stages * (size_t) stage_bytes;
+#define XTB_CW_LAUNCH2(CVV, OPP, RR)                                                                                             \
+    do {                                                                                                                         \
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_colwalk<T, CVV, OPP, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); \
+        k_scan_colwalk<T, CVV, OPP, RR><<<(unsigned) walkers, 64, smem, ctx->stream>>>(p, c, tmap, tmap_out);                    \
+    } while (0)
 #define XTB_CW_LAUNCH(CVV)                                                                                                       \
     do {                                                                                                                         \
         if (p.op == XTB_RED_PROD) {                                                                                              \
-            XTB_CUDA(cudaFuncSetAttribute(k_scan_colwalk<T, CVV, XTB_RED_PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); \
-            k_scan_colwalk<T, CVV, XTB_RED_PROD><<<(unsigned) walkers, 64, smem, ctx->stream>>>(p, c, tmap);                     \
+            if (box_rows == 32) XTB_CW_LAUNCH2(CVV, XTB_RED_PROD, 32);                                                           \
+            else XTB_CW_LAUNCH2(CVV, XTB_RED_PROD, 64);                                                                          \
         } else {                                                                                                                 \
-            XTB_CUDA(cudaFuncSetAttribute(k_scan_colwalk<T, CVV, XTB_RED_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));  \
-            k_scan_colwalk<T, CVV, XTB_RED_SUM><<<(unsigned) walkers, 64, smem, ctx->stream>>>(p, c, tmap);                      \
+            if (box_rows == 32) XTB_CW_LAUNCH2(CVV, XTB_RED_SUM, 32);                                                            \
+            else XTB_CW_LAUNCH2(CVV, XTB_RED_SUM, 64);                                                                           \
         }                                                                                                                        \
     } while (0)
     if constexpr (sizeof(T) == 4) {
@@ -1481,6 +1516,7 @@ template <class T> static int scan_colwalk(const ScanParams& p, DeviceCtx* ctx) 
         else XTB_CW_LAUNCH(1);
     }
 #undef XTB_CW_LAUNCH
+#undef XTB_CW_LAUNCH2
     note_launch("k_scan_colwalk[TMA ring, reference order]");
     return check_launch("k_scan_colwalk");
 }
