@@ -17,6 +17,7 @@
  *   xtb_reduce   <- reduce_immediate  include/xtensor/reducers/xreducer.hpp:289-565
  *                   and xreducer_stepper::aggregate_impl :1778-1868 (lazy reducers)
  *   xtb_scan     <- detail::accumulator_impl include/xtensor/reducers/xaccumulator.hpp:215-341
+ *   xtb_argreduce <- argmin / argmax, detail::arg_func_impl include/xtensor/misc/xsort.hpp:1150-1300
  *   xtb_malloc/xtb_free/xtb_memcpy
  *                <- uvector<T,A> storage   include/xtensor/containers/xstorage.hpp:33-345
  *   xtb_allreduce / reduce(..., allreduce=1)
@@ -126,6 +127,8 @@ typedef enum {
     XTB_OP_POW = 87, XTB_OP_HYPOT = 88, XTB_OP_ATAN2 = 89,
     /* select based, math::maximum / math::minimum xmath.hpp:570-602: (a>b)?a:b / (a<b)?a:b */
     XTB_OP_MAXIMUM = 90, XTB_OP_MINIMUM = 91,
+    /* detail::nan_min / nan_max xmath.hpp:2333-2363: isnan(a) ? b : (isnan(b) ? a : minimum/maximum(a, b)) */
+    XTB_OP_NANMIN = 92, XTB_OP_NANMAX = 93,
     /* ternary: stack [x, y, z] -> one value */
     XTB_OP_WHERE = 112,    /* x ? y : z      detail::conditional_ternary xoperation.hpp:126-143 */
     XTB_OP_FMA = 113,      /* std::fma(x,y,z) math::fma_fun */
@@ -163,7 +166,9 @@ typedef enum {
     XTB_RED_SUM = 0,       /* detail::plus, init 0            xmath.hpp:1803        */
     XTB_RED_PROD = 1,      /* detail::multiplies, init 1      xmath.hpp:1823        */
     XTB_RED_MAX = 2,       /* math::maximum, init lowest()    xmath.hpp:777-782     */
-    XTB_RED_MIN = 3        /* math::minimum, init max()       xmath.hpp:795-800     */
+    XTB_RED_MIN = 3,       /* math::minimum, init max()       xmath.hpp:795-800     */
+    XTB_RED_NANMIN = 4,    /* detail::nan_min, init NaN       xmath.hpp:2333-2346, 2427 (integers: = MIN) */
+    XTB_RED_NANMAX = 5     /* detail::nan_max, init NaN       xmath.hpp:2348-2363, 2442 (integers: = MAX) */
 } xtb_reduce_op;
 
 /* ---- runtime --------------------------------------------------------------- */
@@ -267,6 +272,13 @@ int  xtb_reduce_fin(int op, int acc_type, const xtb_program* program,
  * shape of in (or is 1-D of in's size when axis < 0) and dtype = acc_type.      */
 int  xtb_scan(int op, int acc_type, const xtb_operand* in, int axis,
               const xtb_operand* out);
+
+/* Index of the first minimum (op = XTB_RED_MIN) / maximum (XTB_RED_MAX) of `in` along `axis`, or over the
+ * flattened row-major traversal when axis < 0 (then `in` must be dense row-major): xt::argmin / xt::argmax and
+ * detail::arg_func_impl, include/xtensor/misc/xsort.hpp:1150-1300.  Sequential semantics of the reference:
+ * ties keep the first index, a NaN never wins unless it is element 0 of its lane.  out: std::size_t (XTB_U64)
+ * indices, rank in.ndim - 1 (0-d when flat). */
+int  xtb_argreduce(int op, const xtb_operand* in, int axis, const xtb_operand* out);
 
 /* ---- multi-GPU: one process per GPU ---------------------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and handed to all ranks by the host

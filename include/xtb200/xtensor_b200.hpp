@@ -29,8 +29,11 @@
 #define XTB200_XTENSOR_B200_HPP
 
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iterator>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -46,8 +49,11 @@
 #include <xtensor/core/xmath.hpp>
 #include <xtensor/core/xnoalias.hpp>
 #include <xtensor/core/xoperation.hpp>
+#include <xtensor/generators/xgenerator.hpp>
+#include <xtensor/misc/xsort.hpp>
 #include <xtensor/misc/xmanipulation.hpp>
 #include <xtensor/reducers/xaccumulator.hpp>
+#include <xtensor/reducers/xnorm.hpp>
 #include <xtensor/reducers/xreducer.hpp>
 #include <xtensor/views/xbroadcast.hpp>
 #include <xtensor/views/xstrided_view.hpp>
@@ -120,11 +126,58 @@ namespace xtb
         return dt < XTB_I32 ? int(XTB_I32) : dt;
     }
 
+    // ---------------------------------------------------------------- device iterators
+    // Iterator over device memory: position arithmetic and comparison only.  Dereferencing is deleted, so host
+    // code that would walk a device container element by element (a(i, j), fill, nested initializer lists,
+    // std::copy into it, a host stepper loop) fails to COMPILE instead of faulting on a device address.
+    template <class T>
+    class device_iterator
+    {
+    public:
+
+        using iterator_category = std::random_access_iterator_tag;
+        using value_type = std::remove_cv_t<T>;
+        using difference_type = std::ptrdiff_t;
+        using pointer = T*;
+        using reference = T&;
+
+        constexpr device_iterator() noexcept = default;
+        constexpr explicit device_iterator(T* p) noexcept : m_p(p) {}
+        template <class U, std::enable_if_t<std::is_same<const U, T>::value, int> = 0>
+        constexpr device_iterator(const device_iterator<U>& rhs) noexcept : m_p(rhs.get()) {}
+
+        constexpr T* get() const noexcept { return m_p; }
+
+        reference operator*() const = delete;      // device memory is not addressable from the host
+        pointer operator->() const = delete;
+        reference operator[](difference_type) const = delete;
+
+        constexpr device_iterator& operator++() noexcept { ++m_p; return *this; }
+        constexpr device_iterator operator++(int) noexcept { device_iterator t(*this); ++m_p; return t; }
+        constexpr device_iterator& operator--() noexcept { --m_p; return *this; }
+        constexpr device_iterator operator--(int) noexcept { device_iterator t(*this); --m_p; return t; }
+        constexpr device_iterator& operator+=(difference_type n) noexcept { m_p += n; return *this; }
+        constexpr device_iterator& operator-=(difference_type n) noexcept { m_p -= n; return *this; }
+        friend constexpr device_iterator operator+(device_iterator a, difference_type n) noexcept { return device_iterator(a.m_p + n); }
+        friend constexpr device_iterator operator+(difference_type n, device_iterator a) noexcept { return device_iterator(a.m_p + n); }
+        friend constexpr device_iterator operator-(device_iterator a, difference_type n) noexcept { return device_iterator(a.m_p - n); }
+        friend constexpr difference_type operator-(device_iterator a, device_iterator b) noexcept { return a.m_p - b.m_p; }
+        friend constexpr bool operator==(device_iterator a, device_iterator b) noexcept { return a.m_p == b.m_p; }
+        friend constexpr bool operator!=(device_iterator a, device_iterator b) noexcept { return a.m_p != b.m_p; }
+        friend constexpr bool operator<(device_iterator a, device_iterator b) noexcept { return a.m_p < b.m_p; }
+        friend constexpr bool operator>(device_iterator a, device_iterator b) noexcept { return a.m_p > b.m_p; }
+        friend constexpr bool operator<=(device_iterator a, device_iterator b) noexcept { return a.m_p <= b.m_p; }
+        friend constexpr bool operator>=(device_iterator a, device_iterator b) noexcept { return a.m_p >= b.m_p; }
+
+    private:
+
+        T* m_p = nullptr;
+    };
+
     // ---------------------------------------------------------------- storage
     // uvector-shaped owner of device memory.  Contents are uninitialised; resize discards
     // (uvector::resize_impl, containers/xstorage.hpp:217-228); copy = device-to-device copy.
-    // Iterators are raw device pointers: they are only meaningful to libxtb200; host code
-    // must not dereference them (use xtb::to_host).
+    // Iterators are device_iterator<T>: positions only, dereferencing does not compile (use xtb::to_host).
     template <class T>
     class device_uvector
     {
@@ -138,8 +191,8 @@ namespace xtb
         using const_pointer = const T*;
         using size_type = std::size_t;
         using difference_type = std::ptrdiff_t;
-        using iterator = pointer;
-        using const_iterator = const_pointer;
+        using iterator = device_iterator<T>;
+        using const_iterator = device_iterator<const T>;
         using reverse_iterator = std::reverse_iterator<iterator>;
         using const_reverse_iterator = std::reverse_iterator<const_iterator>;
 
@@ -225,12 +278,12 @@ namespace xtb
 
         pointer data() noexcept { return m_ptr; }
         const_pointer data() const noexcept { return m_ptr; }
-        iterator begin() noexcept { return m_ptr; }
-        iterator end() noexcept { return m_ptr + m_size; }
-        const_iterator begin() const noexcept { return m_ptr; }
-        const_iterator end() const noexcept { return m_ptr + m_size; }
-        const_iterator cbegin() const noexcept { return m_ptr; }
-        const_iterator cend() const noexcept { return m_ptr + m_size; }
+        iterator begin() noexcept { return iterator(m_ptr); }
+        iterator end() noexcept { return iterator(m_ptr + m_size); }
+        const_iterator begin() const noexcept { return const_iterator(m_ptr); }
+        const_iterator end() const noexcept { return const_iterator(m_ptr + m_size); }
+        const_iterator cbegin() const noexcept { return const_iterator(m_ptr); }
+        const_iterator cend() const noexcept { return const_iterator(m_ptr + m_size); }
         reverse_iterator rbegin() noexcept { return reverse_iterator(end()); }
         reverse_iterator rend() noexcept { return reverse_iterator(begin()); }
         const_reverse_iterator rbegin() const noexcept { return const_reverse_iterator(end()); }
@@ -238,13 +291,13 @@ namespace xtb
         const_reverse_iterator crbegin() const noexcept { return rbegin(); }
         const_reverse_iterator crend() const noexcept { return rend(); }
 
-        // device addresses -- never dereference on the host
-        reference operator[](size_type i) { return m_ptr[i]; }
-        const_reference operator[](size_type i) const { return m_ptr[i]; }
-        reference front() { return m_ptr[0]; }
-        const_reference front() const { return m_ptr[0]; }
-        reference back() { return m_ptr[m_size - 1]; }
-        const_reference back() const { return m_ptr[m_size - 1]; }
+        // element access from the host is a compile-time error (use xtb::to_host)
+        reference operator[](size_type i) = delete;
+        const_reference operator[](size_type i) const = delete;
+        reference front() = delete;
+        const_reference front() const = delete;
+        reference back() = delete;
+        const_reference back() const = delete;
 
         void swap(device_uvector& rhs) noexcept
         {
@@ -305,8 +358,8 @@ namespace xtb
         using const_pointer = const T*;
         using size_type = std::size_t;
         using difference_type = std::ptrdiff_t;
-        using iterator = pointer;
-        using const_iterator = const_pointer;
+        using iterator = device_iterator<T>;
+        using const_iterator = device_iterator<const T>;
         using reverse_iterator = std::reverse_iterator<iterator>;
         using const_reverse_iterator = std::reverse_iterator<const_iterator>;
         using temporary_type = device_uvector<T>;
@@ -344,25 +397,25 @@ namespace xtb
         size_type size() const noexcept { return m_size; }
         pointer data() noexcept { return m_ptr; }
         const_pointer data() const noexcept { return m_ptr; }
-        // device addresses: valid for pointer arithmetic only (same contract as device_uvector)
-        iterator begin() noexcept { return m_ptr; }
-        iterator end() noexcept { return m_ptr + m_size; }
-        const_iterator begin() const noexcept { return m_ptr; }
-        const_iterator end() const noexcept { return m_ptr + m_size; }
-        const_iterator cbegin() const noexcept { return m_ptr; }
-        const_iterator cend() const noexcept { return m_ptr + m_size; }
+        iterator begin() noexcept { return iterator(m_ptr); }
+        iterator end() noexcept { return iterator(m_ptr + m_size); }
+        const_iterator begin() const noexcept { return const_iterator(m_ptr); }
+        const_iterator end() const noexcept { return const_iterator(m_ptr + m_size); }
+        const_iterator cbegin() const noexcept { return const_iterator(m_ptr); }
+        const_iterator cend() const noexcept { return const_iterator(m_ptr + m_size); }
         reverse_iterator rbegin() noexcept { return reverse_iterator(end()); }
         reverse_iterator rend() noexcept { return reverse_iterator(begin()); }
         const_reverse_iterator rbegin() const noexcept { return const_reverse_iterator(end()); }
         const_reverse_iterator rend() const noexcept { return const_reverse_iterator(begin()); }
         const_reverse_iterator crbegin() const noexcept { return const_reverse_iterator(end()); }
         const_reverse_iterator crend() const noexcept { return const_reverse_iterator(begin()); }
-        reference operator[](size_type i) { return m_ptr[i]; }
-        const_reference operator[](size_type i) const { return m_ptr[i]; }
-        reference front() { return m_ptr[0]; }
-        const_reference front() const { return m_ptr[0]; }
-        reference back() { return m_ptr[m_size - 1]; }
-        const_reference back() const { return m_ptr[m_size - 1]; }
+        // element access from the host is a compile-time error (use xtb::to_host)
+        reference operator[](size_type i) = delete;
+        const_reference operator[](size_type i) const = delete;
+        reference front() = delete;
+        const_reference front() const = delete;
+        reference back() = delete;
+        const_reference back() const = delete;
 
         void swap(device_span& rhs) noexcept
         {
@@ -506,6 +559,16 @@ namespace xt
         };
     }
 
+    namespace extension
+    {
+        // xshared_expression<E> (core/xexpression.hpp:510-735; what detail::shared_forward wraps rvalue operands of
+        // nanmean / nanvar / variance in) publishes no expression_tag of its own: it has its operand's
+        template <class E>
+        struct get_expression_tag<xshared_expression<E>> : get_expression_tag<E>
+        {
+        };
+    }
+
     namespace detail
     {
         template <class F, class... E>
@@ -520,6 +583,17 @@ namespace xt
     struct temporary_container<xtb::device_span<T>>
     {
         using type = xtb::device_uvector<T>;
+    };
+
+    // xt::eval of a VIEW picks the view's own temporary_type typedef, which the reference hard-wires to a host
+    // container (views/xview.hpp:304, views/xstrided_view.hpp:80).  For device-tagged views the temporary must
+    // live on the device: this constrained specialisation is preferred over the generic one
+    // (core/xexpression_traits.hpp:150-154) for them.
+    template <class T>
+        requires(std::is_same<xexpression_tag_t<std::decay_t<T>>, xtb::b200_expression_tag>::value)
+    struct temporary_type<T, void_t<typename std::decay_t<T>::temporary_type>>
+    {
+        using type = typename temporary_type_from_tag<xtb::b200_expression_tag, T>::type;
     };
 
     // temporaries of device expressions are device containers of the same rank / value type
@@ -797,28 +871,15 @@ namespace xtb
         {
         };
 
-        // a node a binary instruction can fetch by itself: a scalar, or a strided leaf whose
-        // storage dtype already is the operand register type
         template <class E>
-        constexpr bool is_simple(int t)
+        struct is_generator_node : std::false_type
         {
-            using D = std::decay_t<E>;
-            if constexpr (is_scalar_node<D>::value)
-            {
-                return true;
-            }
-            else if constexpr (is_function_node<D>::value || is_reducer_node<D>::value || is_broadcast_node<D>::value)
-            {
-                return false;
-            }
-            else
-            {
-                return dtype_v<typename D::value_type> == t && t >= XTB_I32;
-            }
-        }
+        };
 
-        template <class E>
-        int emit_value(context& c, const E& e, int want);
+        template <class F, class R, class S>
+        struct is_generator_node<xt::xgenerator<F, R, S>> : std::true_type
+        {
+        };
 
         template <class E>
         struct is_strided_view_node : std::false_type
@@ -829,6 +890,47 @@ namespace xtb
         struct is_strided_view_node<xt::xstrided_view<CT, S, L, FST>> : std::true_type
         {
         };
+
+        // a strided view whose operand is a lazy expression (no data interface anywhere): materialised on use
+        template <class E>
+        struct is_lazy_view_node : std::false_type
+        {
+        };
+
+        template <class CT, class S, xt::layout_type L, class FST>
+        struct is_lazy_view_node<xt::xstrided_view<CT, S, L, FST>>
+            : std::bool_constant<!xt::has_data_interface<xt::xstrided_view<CT, S, L, FST>>::value
+                                 && !xt::has_data_interface<std::decay_t<CT>>::value>
+        {
+        };
+
+        // a node a binary instruction can fetch by itself: a scalar, or a strided leaf whose
+        // storage dtype already is the operand register type
+        template <class E>
+        constexpr bool is_simple(int t)
+        {
+            using D = std::decay_t<E>;
+            if constexpr (is_scalar_node<D>::value)
+            {
+                return true;
+            }
+            else if constexpr (is_function_node<D>::value || is_reducer_node<D>::value || is_broadcast_node<D>::value
+                               || is_generator_node<D>::value)
+            {
+                return false;
+            }
+            else if constexpr (is_lazy_view_node<D>::value)
+            {
+                return false;   // a view over a lazy expression is materialised first
+            }
+            else
+            {
+                return dtype_v<typename D::value_type> == t && t >= XTB_I32;
+            }
+        }
+
+        template <class E>
+        int emit_value(context& c, const E& e, int want);
 
         // reshape_view(container, shape) (views/xstrided_view.hpp:850-878, used by xt::variance) is an
         // xstrided_view over a *flat adaptor*: it has shape / strides / offset but no data().  Over a
@@ -881,7 +983,7 @@ namespace xtb
         template <class E>
         struct is_leaf_node
             : std::bool_constant<!is_scalar_node<E>::value && !is_function_node<E>::value && !is_reducer_node<E>::value
-                                 && !is_broadcast_node<E>::value>
+                                 && !is_broadcast_node<E>::value && !is_generator_node<E>::value>
         {
         };
 
@@ -1043,6 +1145,51 @@ namespace xtb
                 c.emit(XTB_OP_PUSH, dtype_v<typename D::value_type>, XTB_SRC_LEAF, c.leaf(tmp.get(), describe(*tmp)));
                 rt = regtype(dtype_v<typename D::value_type>);
             }
+            else if constexpr (is_generator_node<D>::value)
+            {
+                // generators (arange, linspace, eye, random: generators/xgenerator.hpp, xbuilder.hpp) are host fills:
+                // xtensor's own code produces the values once, the result is uploaded and becomes an ordinary leaf
+                using T = typename D::value_type;
+                xt::xarray<T> host = e;
+                auto tmp = std::make_shared<xtb::xarray<T>>();
+                std::vector<std::size_t> shp(host.shape().begin(), host.shape().end());
+                tmp->resize(shp);
+                if (host.size())
+                {
+                    check(xtb_memcpy(tmp->data(), host.data(), host.size() * sizeof(T), XTB_H2D));
+                    check(xtb_sync());   // `host` dies at the end of this scope
+                }
+                c.keepalive.push_back(tmp);
+                c.emit(XTB_OP_PUSH, dtype_v<T>, XTB_SRC_LEAF, c.leaf(tmp.get(), describe(*tmp)));
+                rt = regtype(dtype_v<T>);
+            }
+            else if constexpr (is_lazy_view_node<D>::value)
+            {
+                // reshape_view / strided_view over a LAZY expression (xt::nanvar reshapes the un-evaluated inner mean,
+                // core/xmath.hpp:2785-2808): evaluate the operand into a device temporary (what the flat adaptor would
+                // walk element by element), then the view is an affine leaf over that dense buffer
+                using T = typename D::value_type;
+                auto tmp = std::make_shared<xtb::xarray<T>>();
+                *tmp = e.expression();
+                c.keepalive.push_back(tmp);
+                xtb_operand op{};
+                op.base = static_cast<void*>(tmp->data());
+                op.offset = static_cast<std::int64_t>(e.data_offset());
+                op.dtype = dtype_v<T>;
+                op.ndim = static_cast<std::int32_t>(e.dimension());
+                std::size_t d = 0;
+                for (auto it = e.shape().begin(); it != e.shape().end(); ++it, ++d)
+                {
+                    op.shape[d] = static_cast<std::int64_t>(*it);
+                }
+                d = 0;
+                for (auto it = e.strides().begin(); it != e.strides().end(); ++it, ++d)
+                {
+                    op.stride[d] = static_cast<std::int64_t>(*it);
+                }
+                c.emit(XTB_OP_PUSH, dtype_v<T>, XTB_SRC_LEAF, c.leaf(tmp.get(), op));
+                rt = regtype(dtype_v<T>);
+            }
             else
             {
                 c.emit(XTB_OP_PUSH, dtype_v<typename D::value_type>, XTB_SRC_LEAF, c.leaf(std::addressof(e), describe_leaf(e)));
@@ -1102,6 +1249,19 @@ namespace xtb
             static constexpr int value = XTB_RED_PROD;
         };
 
+        // nan_min / nan_max (core/xmath.hpp:2333-2363) are native merges of the reduction kernels
+        template <>
+        struct reduce_op_of<xt::detail::nan_min>
+        {
+            static constexpr int value = XTB_RED_NANMIN;
+        };
+
+        template <>
+        struct reduce_op_of<xt::detail::nan_max>
+        {
+            static constexpr int value = XTB_RED_NANMAX;
+        };
+
         template <class F>
         struct nan_fill_of
         {
@@ -1155,7 +1315,8 @@ namespace xtb
             static constexpr std::size_t primes[XTB_MAX_DIM] = {2, 3, 5, 7, 11, 13, 17, 19};
             const std::size_t nd = r.expression().dimension();
             std::vector<std::size_t> probe_shape(primes, primes + nd);
-            auto probe = r.build_reducer(xt::broadcast(char(0), probe_shape));
+            using probe_value_type = typename std::decay_t<decltype(r.expression())>::value_type;
+            auto probe = r.build_reducer(xt::broadcast(probe_value_type(0), probe_shape));
             const auto& rs = probe.shape();
             int na = 0;
             for (std::size_t d = 0; d < nd; ++d)
@@ -1173,37 +1334,366 @@ namespace xtb
             return na;
         }
 
-        // run xreducer<F, CT, X, O> into `out` (any container with the strided data interface)
-        template <class R, class OUT>
-        void run_reducer(const R& r, OUT& out, bool allreduce = false)
+        // ---- reducers whose reduce functor is an opaque lambda ------------------------------------
+        // count_nonzero (core/xmath.hpp:2478-2541), the norms (reducers/xnorm.hpp:369-433, 493-506) and minmax
+        // (core/xmath.hpp:2195-2228) build their reduce functor from a lambda; its type says nothing.  Every one
+        // of them has the form  f(r, v) = r (+) g(v)  with (+) given by the merge functor (std::plus / detail::plus
+        // -> sum, math::maximum -> max) and g one of {v != 0, |v|, v * v, |v|^p}.  The lambda is called on the
+        // host with a few probe values to find out which g it is; anything else is rejected (no CPU fallback).
+        enum map_kind
         {
-            using functors = typename R::reduce_functor_type;
-            constexpr int op = reduce_op_of<std::decay_t<functors>>::value;
-            static_assert(op >= 0, "xtb200: only sum / prod / amax / amin (and nansum / nanprod) reducers can be lowered");
-            using acc_t = typename R::value_type;
-            context c;
-            emit_reducer_operand<std::decay_t<functors>>(c, r.expression());
-            const auto& sh = r.expression().shape();
+            MAP_NONE = 0,
+            MAP_COUNT = 1,   // g(v) = (v != 0)                 count_nonzero, norm_l0
+            MAP_ABS = 2,     // g(v) = std::abs(v)              norm_l1, norm_linf
+            MAP_SQ = 3,      // g(v) = v * v                    norm_sq
+            MAP_POWABS = 4   // g(v) = pow(rt(std::abs(v)), p)  norm_lp_to_p
+        };
+
+        struct reducer_plan
+        {
+            int op = -1;          // xtb_reduce_op
+            int map = MAP_NONE;
+            double p = 0.0;       // MAP_POWABS exponent
+            bool zero_init = false;   // merge the reducer's own init (0) once at the end (max-type norms)
+        };
+
+        template <class T>
+        struct is_array2 : std::false_type
+        {
+        };
+
+        template <class T>
+        struct is_array2<std::array<T, 2>> : std::true_type
+        {
+            using element_type = T;
+        };
+
+        template <class M>
+        struct merge_is_plus : std::false_type
+        {
+        };
+
+        template <>
+        struct merge_is_plus<xt::detail::plus> : std::true_type
+        {
+        };
+
+        template <class T>
+        struct merge_is_plus<std::plus<T>> : std::true_type
+        {
+        };
+
+        template <class M>
+        struct merge_is_max : std::false_type
+        {
+        };
+
+        template <class T>
+        struct merge_is_max<xt::math::maximum<T>> : std::true_type
+        {
+        };
+
+        template <class RF, class MF, class R, class V>
+        inline reducer_plan probe_reducer(const RF& f)
+        {
+            reducer_plan pl;
+            if constexpr (std::is_arithmetic<R>::value && std::is_arithmetic<V>::value && std::is_invocable<const RF&, R, V>::value)
+            {
+                auto g = [&f](double r, double v) { return static_cast<double>(f(static_cast<R>(r), static_cast<V>(v))); };
+                const bool is_signed = std::is_signed<V>::value && !std::is_same<V, bool>::value;
+                if constexpr (merge_is_plus<MF>::value)
+                {
+                    const double z = g(7, 0) - 7, a = g(7, 2) - 7, b = g(7, 3) - 7;
+                    const double n = is_signed ? g(7, -3) - 7 : b;
+                    if (z != 0)
+                    {
+                        return pl;
+                    }
+                    pl.op = XTB_RED_SUM;
+                    if (std::is_same<V, bool>::value ? (a == 1) : (a == 1 && b == 1 && n == 1))
+                    {
+                        pl.map = MAP_COUNT;
+                    }
+                    else if (a == 2 && b == 3 && n == 3)
+                    {
+                        pl.map = MAP_ABS;
+                    }
+                    else if (a == 4 && b == 9 && n == 9)
+                    {
+                        pl.map = MAP_SQ;
+                    }
+                    else if (a > 0 && b > 0 && n == b)
+                    {
+                        // |v|^p: p from the value at 2, confirmed at 3 (the probe runs in V's real type: float
+                        // operands give p to ~1e-7 only).  norm_lp_to_p's lambda captures p by value and nothing
+                        // else (xnorm.hpp:563-566): when the closure is exactly one double that agrees with the
+                        // estimate, that double IS p, bit for bit.
+                        double pw = std::log2(a);
+                        const double tol = std::is_same<V, float>::value ? 1e-5 : 1e-9;
+                        if (std::fabs(std::pow(3.0, pw) - b) <= tol * b)
+                        {
+                            if constexpr (sizeof(RF) == sizeof(double) && std::is_trivially_copyable<RF>::value)
+                            {
+                                double captured = 0.0;
+                                std::memcpy(&captured, &f, sizeof(double));
+                                if (std::fabs(captured - pw) <= tol * std::fabs(pw))
+                                {
+                                    pw = captured;
+                                }
+                            }
+                            pl.map = MAP_POWABS;
+                            pl.p = pw;
+                        }
+                        else
+                        {
+                            pl.op = -1;
+                        }
+                    }
+                    else
+                    {
+                        pl.op = -1;
+                    }
+                }
+                else if constexpr (merge_is_max<MF>::value)
+                {
+                    // norm_linf: std::max<result_type>(r, std::abs(v)); a NaN never replaces r
+                    const double n = is_signed ? g(1, -3) : 3;
+                    if (g(7, 2) == 7 && g(1, 2) == 2 && n == 3 && g(0, 0) == 0)
+                    {
+                        pl.op = XTB_RED_NANMAX;
+                        pl.map = MAP_ABS;
+                        pl.zero_init = true;
+                    }
+                }
+            }
+            return pl;
+        }
+
+        template <class FS, class V>
+        inline reducer_plan plan_reducer(const FS& functors)
+        {
+            using RF = std::decay_t<typename FS::reduce_functor_type>;
+            using MF = std::decay_t<typename FS::merge_functor_type>;
+            using IF = std::decay_t<typename FS::init_functor_type>;
+            using R = std::decay_t<decltype(std::declval<RF>()(std::declval<IF>()(), std::declval<V>()))>;
+            reducer_plan pl;
+            if constexpr (reduce_op_of<RF>::value >= 0)
+            {
+                pl.op = reduce_op_of<RF>::value;
+            }
+            else
+            {
+                pl = probe_reducer<RF, MF, R, V>(std::get<0>(functors));
+                if (pl.op < 0)
+                {
+                    XTENSOR_THROW(std::runtime_error,
+                                  "xtb200: this reducer's functor cannot be lowered to a device reduction (supported: sum, prod, "
+                                  "amax, amin, nan-variants, count_nonzero, minmax and the norms); there is no CPU fallback");
+                }
+            }
+            return pl;
+        }
+
+        // program + leaves of a reducer's operand with the plan's map applied; result in the accumulator type R
+        template <class RF, class R, class E>
+        inline void emit_planned_operand(context& c, const reducer_plan& pl, const E& e)
+        {
+            using V = typename std::decay_t<E>::value_type;
+            if (pl.map == MAP_NONE)
+            {
+                emit_reducer_operand<RF>(c, e);
+                return;
+            }
+            const int acc = regtype(dtype_v<R>);
+            int rt = emit_value(c, e, -1);
+            switch (pl.map)
+            {
+                case MAP_COUNT:
+                    c.emit(XTB_OP_NE, rt, XTB_SRC_IMM, c.imm(0, rt));
+                    rt = XTB_I32;
+                    break;
+                case MAP_ABS:
+                    c.emit(XTB_OP_ABS, rt);
+                    break;
+                case MAP_SQ:
+                    c.emit(XTB_OP_SQUARE, rt);
+                    break;
+                default:
+                {
+                    // norm_lp_to_p(v, p) = pow(rt(std::abs(v)), rt(p)) with rt = real_promote_type_t<V> (xnorm.hpp:185-190)
+                    using PT = std::decay_t<decltype(xt::norm_lp_to_p(std::declval<V>(), 0.0))>;
+                    const int prt = regtype(dtype_v<PT>);
+                    c.emit(XTB_OP_ABS, rt);
+                    if (rt != prt)
+                    {
+                        c.emit(XTB_OP_CAST, rt, 0, prt);
+                    }
+                    c.emit(XTB_OP_POW, prt, XTB_SRC_IMM, c.imm(pl.p, prt));
+                    rt = prt;
+                    break;
+                }
+            }
+            if (rt != acc)
+            {
+                c.emit(XTB_OP_CAST, rt, 0, dtype_v<R>);
+            }
+        }
+
+        // descriptor of a container of std::array<T, 2> seen as T elements: component `which` of every pair
+        template <class T, class OUT>
+        inline xtb_operand describe_component(OUT& out, int which)
+        {
+            xtb_operand op{};
+            op.base = static_cast<void*>(out.data());
+            op.offset = 2 * static_cast<std::int64_t>(out.data_offset()) + which;
+            op.dtype = dtype_v<T>;
+            op.ndim = static_cast<std::int32_t>(out.dimension());
+            std::size_t d = 0;
+            for (auto it = out.shape().begin(); it != out.shape().end(); ++it, ++d)
+            {
+                op.shape[d] = static_cast<std::int64_t>(*it);
+            }
+            d = 0;
+            for (auto it = out.strides().begin(); it != out.strides().end(); ++it, ++d)
+            {
+                op.stride[d] = 2 * static_cast<std::int64_t>(*it);
+            }
+            return op;
+        }
+
+        // the one place a reduction is launched from: reduce `e` over axes[na] with the functor triple `functors`
+        // into `out`.  IV: type of xt::initial's value (void: none)
+        template <class FS, class E, class OUT, class IV>
+        void launch_reducer(const FS& functors, const E& e, const std::int32_t* axes, int na, bool keep, const IV* initial_value,
+                            OUT& out, bool allreduce, const xtb_finalize* fin = nullptr)
+        {
+            using RF = std::decay_t<typename FS::reduce_functor_type>;
+            using IF = std::decay_t<typename FS::init_functor_type>;
+            using V = typename std::decay_t<E>::value_type;
+            using R = std::decay_t<decltype(std::declval<RF>()(std::declval<IF>()(), std::declval<V>()))>;
+            const auto& sh = e.shape();
             std::int64_t shape[XTB_MAX_DIM] = {0};
             int nd = 0;
             for (auto it = sh.begin(); it != sh.end(); ++it)
             {
                 shape[nd++] = static_cast<std::int64_t>(*it);
             }
+            auto run = [&](int op, int acc_rt, context& c, const void* initial, const xtb_operand& oop)
+            {
+                const int st = xtb_reduce_fin(op, acc_rt, &c.prog, c.leaves, nd, shape, na, axes, keep ? 1 : 0, initial, &oop, allreduce ? 1 : 0, fin);
+                if (st == XTB_ERR_AXIS)
+                {
+                    XTENSOR_THROW(std::runtime_error, xtb_last_error());
+                }
+                check(st);
+            };
+            if constexpr (is_array2<R>::value)
+            {
+                // xt::minmax: r[0] = std::min(r[0], v), r[1] = std::max(r[1], v) from {max(), lowest()}; std::min / std::max
+                // never take a NaN operand, so the two components are the NaN-skipping extremes merged once with the init
+                using T = typename is_array2<R>::element_type;
+                const R lo = std::get<0>(functors)(R{T(5), T(5)}, V(3)), hi = std::get<0>(functors)(R{T(5), T(5)}, V(7));
+                if (!(lo[0] == T(3) && lo[1] == T(5) && hi[0] == T(5) && hi[1] == T(7)))
+                {
+                    XTENSOR_THROW(std::runtime_error, "xtb200: only the minmax pair reducer can be lowered (no CPU fallback)");
+                }
+                const R init = std::get<1>(functors)();
+                using W = std::conditional_t<(sizeof(T) < 4), int, T>;   // the accumulator register type
+                for (int which = 0; which < 2; ++which)
+                {
+                    context c;
+                    emit_value(c, e, regtype(dtype_v<T>));
+                    const W iv = static_cast<W>(init[which]);
+                    run(which == 0 ? XTB_RED_NANMIN : XTB_RED_NANMAX, regtype(dtype_v<T>), c, &iv, describe_component<T>(out, which));
+                }
+            }
+            else
+            {
+                const reducer_plan pl = plan_reducer<FS, V>(functors);
+                context c;
+                emit_planned_operand<RF, R>(c, pl, e);
+                // xt::initial is handed over in the accumulator's REGISTER type (int for the narrow integers)
+                using W = std::conditional_t<(sizeof(R) < 4), int, R>;
+                W iv{};
+                const void* initial = nullptr;
+                if constexpr (!std::is_void<IV>::value)
+                {
+                    if (initial_value)
+                    {
+                        iv = static_cast<W>(static_cast<R>(*initial_value));
+                        initial = &iv;
+                    }
+                }
+                if (pl.zero_init && !initial)
+                {
+                    iv = W(0);
+                    initial = &iv;
+                }
+                run(pl.op, regtype(dtype_v<R>), c, initial, describe(out));
+            }
+        }
+
+        // run xreducer<F, CT, X, O> into `out` (any container with the strided data interface)
+        template <class R, class OUT>
+        void run_reducer(const R& r, OUT& out, bool allreduce = false, const xtb_finalize* fin = nullptr)
+        {
             std::int32_t axes[XTB_MAX_DIM] = {0};
             const int na = reducer_axes(r, axes);
             using options_t = typename reducer_traits<R>::options_type;
             constexpr bool keep = typename options_t::keep_dims();
-            const void* initial = nullptr;
-            acc_t init_v{};
             if constexpr (options_t::has_initial_value)
             {
-                init_v = static_cast<acc_t>(r.options().initial_value);
-                initial = &init_v;
+                const auto iv = r.options().initial_value;
+                launch_reducer(r.functors(), r.expression(), axes, na, keep, &iv, out, allreduce, fin);
             }
-            xtb_operand oop = describe(out);
-            check(xtb_reduce(op, regtype(dtype_v<acc_t>), &c.prog, c.leaves, nd, shape, na, axes, keep ? 1 : 0, initial, &oop,
-                             allreduce ? 1 : 0));
+            else
+            {
+                launch_reducer(r.functors(), r.expression(), axes, na, keep, static_cast<const void*>(nullptr), out, allreduce, fin);
+            }
+        }
+
+        // xt::mean / xt::variance / xt::average end in `sum(...) / scalar` (core/xmath.hpp:1827-1852, 2082-2105):
+        // xfunction<divides, xreducer<plus...>, xscalar>.  The division is the epilogue of the reduction's last store
+        // (xtb_reduce_fin; mean_functor::finalize, reducers/xblockwise_reducer_functors.hpp:146-186) -- one launch
+        // fewer and no temporary, same arithmetic: T(sum) / T(divisor) in the node's value type.
+        template <class E>
+        struct mean_node : std::false_type
+        {
+        };
+
+        template <class R, class S>
+        struct mean_node<xt::xfunction<xt::detail::divides, R, S>>
+            : std::bool_constant<is_reducer_node<std::decay_t<R>>::value && is_scalar_node<std::decay_t<S>>::value>
+        {
+        };
+
+        template <class E, class OUT>
+        bool run_mean_node(const E& e, OUT& out, bool allreduce = false)
+        {
+            using value_type = typename E::value_type;
+            using R = std::decay_t<std::tuple_element_t<0, std::decay_t<decltype(e.arguments())>>>;
+            using RF = std::decay_t<typename R::reduce_functor_type>;
+            if constexpr ((std::is_same<value_type, float>::value || std::is_same<value_type, double>::value)
+                          && reduce_op_of<RF>::value == XTB_RED_SUM && std::is_arithmetic<typename R::value_type>::value
+                          && std::is_same<typename OUT::value_type, value_type>::value)
+            {
+                const auto& red = std::get<0>(e.arguments());
+                if (!std::equal(red.shape().begin(), red.shape().end(), out.shape().begin(), out.shape().end()))
+                {
+                    return false;
+                }
+                xtb_finalize fin{};
+                fin.op = XTB_FIN_DIV;
+                fin.type = dtype_v<value_type>;
+                const value_type div = static_cast<value_type>(std::get<1>(e.arguments())());
+                std::memcpy(&fin.imm, &div, sizeof(div));
+                run_reducer(red, out, allreduce, &fin);
+                return true;
+            }
+            else
+            {
+                return false;
+            }
         }
 
         template <class R, class E>
@@ -1241,6 +1731,16 @@ namespace xt
             {
                 xtb::lower::run_reducer(rhs, lhs);
             }
+            else if constexpr (xtb::lower::mean_node<E2>::value)
+            {
+                if (!xtb::lower::run_mean_node(rhs, lhs))
+                {
+                    xtb::lower::context c;
+                    xtb::lower::emit_value(c, rhs, -1);
+                    xtb_operand out = xtb::lower::describe(lhs);
+                    xtb::check(xtb_assign(&c.prog, &out, c.leaves));
+                }
+            }
             else
             {
                 xtb::lower::context c;
@@ -1273,9 +1773,6 @@ namespace xt
         ))>;
         using options_t = reducer_options<result_type, std::decay_t<O>>;
         options_t options(raw_options);
-        constexpr int op = xtb::lower::reduce_op_of<reduce_functor_type>::value;
-        static_assert(op >= 0, "xtb200: only sum / prod / amax / amin (and nansum / nanprod) reducers can be lowered");
-        (void) f;
 
         const std::size_t nd = e.dimension();
         std::int32_t ax[XTB_MAX_DIM] = {0};
@@ -1305,28 +1802,15 @@ namespace xt
         }
         xtb::xarray<result_type> result;
         result.resize(out_shape);
-        xtb::lower::context c;
-        xtb::lower::emit_reducer_operand<reduce_functor_type>(c, e);
-        std::int64_t shape[XTB_MAX_DIM] = {0};
-        for (std::size_t d = 0; d < nd; ++d)
-        {
-            shape[d] = static_cast<std::int64_t>(e.shape()[d]);
-        }
-        const void* initial = nullptr;
-        result_type init_v{};
         if constexpr (options_t::has_initial_value)
         {
-            init_v = static_cast<result_type>(options.initial_value);
-            initial = &init_v;
+            const auto iv = options.initial_value;
+            xtb::lower::launch_reducer(f, e, ax, na, keep, &iv, result, false);
         }
-        xtb_operand oop = xtb::lower::describe(result);
-        const int st = xtb_reduce(op, xtb::regtype(xtb::dtype_v<result_type>), &c.prog, c.leaves, static_cast<int>(nd), shape, na, ax,
-                                  keep ? 1 : 0, initial, &oop, 0);
-        if (st == XTB_ERR_AXIS)
+        else
         {
-            XTENSOR_THROW(std::runtime_error, xtb_last_error());
+            xtb::lower::launch_reducer(f, e, ax, na, keep, static_cast<const void*>(nullptr), result, false);
         }
-        xtb::check(st);
         return result;
     }
 
@@ -1488,6 +1972,569 @@ namespace xtb
     {
         typename xt::temporary_type_from_tag<b200_expression_tag, E>::type tmp = e.derived_cast();
         return to_host(tmp);
+    }
+}
+
+namespace xt
+{
+    // ---------------------------------------------------------------- argmin / argmax
+    // The generic versions (misc/xsort.hpp:1150-1300) eval(e) and then walk the lanes with host iterators; these
+    // more-constrained overloads (same template heads, selected for device-tagged operands) run xtb_argreduce.
+    // Results are device containers of std::size_t: 0-d for the flat form, rank - 1 otherwise.
+    namespace detail
+    {
+        template <class E>
+        inline auto b200_argreduce(const E& e, int op, std::ptrdiff_t axis, bool flat)
+        {
+            auto&& ed = xt::eval(e);     // containers pass through, expressions become device temporaries
+            using ED = std::decay_t<decltype(ed)>;
+            xtb::xarray<std::size_t> result;
+            std::vector<std::size_t> shp;
+            int ax = -1;
+            xtb_operand in = xtb::lower::describe(ed);
+            if (!flat)
+            {
+                ax = static_cast<int>(normalize_axis(ed.dimension(), axis));
+                for (std::size_t d = 0; d < ed.dimension(); ++d)
+                {
+                    if (static_cast<int>(d) != ax)
+                    {
+                        shp.push_back(ed.shape()[d]);
+                    }
+                }
+            }
+            result.resize(shp);
+            xtb_operand out = xtb::lower::describe(result);
+            if (flat && !ed.is_contiguous())
+            {
+                // the flattened traversal of a strided view: a dense copy first, as eval() of a view would give
+                xtb::xarray<typename ED::value_type> dense = ed;
+                xtb_operand din = xtb::lower::describe(dense);
+                xtb::check(xtb_argreduce(op, &din, -1, &out));
+                return result;
+            }
+            xtb::check(xtb_argreduce(op, &in, ax, &out));
+            return result;
+        }
+    }
+
+    // ---------------------------------------------------------------- nanmean / nanvar on device operands
+    // The generic versions (core/xmath.hpp:2694-2842) wrap an rvalue operand in xshared_expression
+    // (detail::shared_forward), whose operand cannot be reached from outside, so a shared lazy NODE cannot be
+    // lowered.  These more-constrained overloads are the same compositions with a different sharing rule:
+    // an lvalue is referenced (as there), an rvalue container is shared (a shared container is still a strided
+    // leaf), and an rvalue lazy node is simply copied into both consumers -- it holds its leaves by reference
+    // and is evaluated, fused, inside each reduction kernel.
+    namespace detail
+    {
+        template <class T, class E, class F>
+        inline auto b200_twice(E&& e, F&& use)
+        {
+            using D = std::decay_t<E>;
+            if constexpr (std::is_lvalue_reference<E>::value)
+            {
+                return use(e, e);
+            }
+            else if constexpr (detail::is_container<D>::value)
+            {
+                auto sh = xt::make_xshared(std::move(e));
+                return use(sh, sh);
+            }
+            else
+            {
+                D copy(e);
+                return use(std::move(copy), std::move(e));
+            }
+        }
+    }
+
+    template <class T = void, class E, class X, class EVS = DEFAULT_STRATEGY_REDUCERS, XTL_REQUIRES(std::negation<is_reducer_options<X>>)>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto nanmean(E&& e, X&& axes, EVS es = EVS())
+    {
+        auto axes_copy = axes;
+        using value_type = typename std::conditional_t<std::is_same<T, void>::value, double, T>;
+        using sum_type = typename std::conditional_t<
+            std::is_same<T, void>::value,
+            typename std::common_type_t<typename std::decay_t<E>::value_type, value_type>,
+            T>;
+        return detail::b200_twice<T>(std::forward<E>(e), [&](auto&& a, auto&& b) {
+            return nansum<sum_type>(std::forward<decltype(a)>(a), std::forward<X>(axes), es)
+                   / xt::cast<value_type>(count_nonnan(std::forward<decltype(b)>(b), std::move(axes_copy), es));
+        });
+    }
+
+    template <class T = void, class E, class EVS = DEFAULT_STRATEGY_REDUCERS, XTL_REQUIRES(is_reducer_options<EVS>)>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto nanmean(E&& e, EVS es = EVS())
+    {
+        using value_type = typename std::conditional_t<std::is_same<T, void>::value, double, T>;
+        using sum_type = typename std::conditional_t<
+            std::is_same<T, void>::value,
+            typename std::common_type_t<typename std::decay_t<E>::value_type, value_type>,
+            T>;
+        return detail::b200_twice<T>(std::forward<E>(e), [&](auto&& a, auto&& b) {
+            return nansum<sum_type>(std::forward<decltype(a)>(a), es)
+                   / xt::cast<value_type>(count_nonnan(std::forward<decltype(b)>(b), es));
+        });
+    }
+
+    template <class T = void, class E, class X, class EVS = DEFAULT_STRATEGY_REDUCERS, XTL_REQUIRES(std::negation<is_reducer_options<X>>)>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto nanvar(E&& e, X&& axes, EVS es = EVS())
+    {
+        using result_type = typename std::conditional_t<std::is_same<T, void>::value, double, T>;
+        // the inner mean is evaluated once (a small device array), then viewed with keep_dims extents
+        auto axes_copy = axes;
+        using tmp_shape_t = get_strides_t<typename std::decay_t<E>::shape_type>;
+        tmp_shape_t keep_dim_shape = xtl::forward_sequence<tmp_shape_t, decltype(e.shape())>(e.shape());
+        for (const auto& el : axes)
+        {
+            keep_dim_shape[el] = 1;
+        }
+        return detail::b200_twice<T>(std::forward<E>(e), [&](auto&& a, auto&& b) {
+            auto inner_mean = xt::eval(nanmean<result_type>(std::forward<decltype(a)>(a), std::move(axes_copy)));
+            auto mrv = reshape_view<XTENSOR_DEFAULT_LAYOUT>(std::move(inner_mean), std::move(keep_dim_shape));
+            return nanmean<result_type>(square(cast<result_type>(std::forward<decltype(b)>(b)) - std::move(mrv)), std::forward<X>(axes), es);
+        });
+    }
+
+    template <class T = void, class E, class EVS = DEFAULT_STRATEGY_REDUCERS, XTL_REQUIRES(is_reducer_options<EVS>)>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto nanvar(E&& e, EVS es = EVS())
+    {
+        return detail::b200_twice<T>(std::forward<E>(e), [&](auto&& a, auto&& b) {
+            auto inner_mean = xt::eval(nanmean<T>(std::forward<decltype(a)>(a)));
+            return nanmean<T>(square(std::forward<decltype(b)>(b) - std::move(inner_mean)), es);
+        });
+    }
+
+    // xt::average(e, weights) over the whole array (core/xmath.hpp:1992-2004) reads the weight total on the host
+    // (`sum<T>(weights, immediate)()`); for device operands the total stays a 0-d device array and the division
+    // is elementwise -- the same arithmetic, sum(e * w) / sum(w)
+    template <class T = void, class E, class W, class EVS = DEFAULT_STRATEGY_REDUCERS, XTL_REQUIRES(is_reducer_options<EVS>)>
+        requires xtb::is_b200_expression<std::decay_t<E>>::value
+    inline auto average(E&& e, W&& weights, EVS ev = EVS())
+    {
+        if (weights.dimension() != e.dimension()
+            || !std::equal(weights.shape().begin(), weights.shape().end(), e.shape().begin()))
+        {
+            XTENSOR_THROW(std::runtime_error, "Weights need to have the same shape as expression.");
+        }
+        auto div = sum<T>(weights, evaluation_strategy::immediate);
+        return sum<T>(std::forward<E>(e) * std::forward<W>(weights), ev) / std::move(div);
+    }
+
+    template <layout_type L = XTENSOR_DEFAULT_TRAVERSAL, class E>
+        requires xtb::is_b200_expression<E>::value
+    inline auto argmin(const xexpression<E>& e)
+    {
+        return detail::b200_argreduce(e.derived_cast(), XTB_RED_MIN, 0, true);
+    }
+
+    template <layout_type L = XTENSOR_DEFAULT_TRAVERSAL, class E>
+        requires xtb::is_b200_expression<E>::value
+    inline auto argmin(const xexpression<E>& e, std::ptrdiff_t axis)
+    {
+        return detail::b200_argreduce(e.derived_cast(), XTB_RED_MIN, axis, false);
+    }
+
+    template <layout_type L = XTENSOR_DEFAULT_TRAVERSAL, class E>
+        requires xtb::is_b200_expression<E>::value
+    inline auto argmax(const xexpression<E>& e)
+    {
+        return detail::b200_argreduce(e.derived_cast(), XTB_RED_MAX, 0, true);
+    }
+
+    template <layout_type L = XTENSOR_DEFAULT_TRAVERSAL, class E>
+        requires xtb::is_b200_expression<E>::value
+    inline auto argmax(const xexpression<E>& e, std::ptrdiff_t axis)
+    {
+        return detail::b200_argreduce(e.derived_cast(), XTB_RED_MAX, axis, false);
+    }
+}
+
+namespace xtb
+{
+    // ---------------------------------------------------------------- host-resident operands, end to end
+    // xtb::assign_host(host_out, expr): evaluate `expr`, whose leaves are HOST containers (pinned memory from
+    // xtb::pinned_alloc makes the copies asynchronous), into the host container `host_out` through
+    // xtb_assign_host: the leading dimension is cut into chunks and H2D | kernel | D2H of consecutive chunks are
+    // pipelined on three streams, so the call costs about max(bytes in, bytes out) / PCIe bandwidth instead of
+    // to_device + kernel + to_host back to back.  `expr` is an ordinary xtensor expression over host containers;
+    // nothing is evaluated on the CPU.
+    template <class OUT, class E>
+    inline void assign_host(OUT& host_out, const xt::xexpression<E>& expr, std::int64_t chunk_bytes = 0)
+    {
+        const E& e = expr.derived_cast();
+        std::vector<std::size_t> shp(e.shape().begin(), e.shape().end());
+        if (!std::equal(shp.begin(), shp.end(), host_out.shape().begin(), host_out.shape().end()))
+        {
+            host_out.resize(shp);
+        }
+        lower::context c;
+        lower::emit_value(c, e, -1);
+        xtb_operand out = lower::describe(host_out);
+        check(xtb_assign_host(&c.prog, &out, c.leaves, chunk_bytes));
+    }
+
+    // page-locked host memory for the operands / result of assign_host (xtb_host_alloc)
+    template <class T>
+    struct pinned_allocator
+    {
+        using value_type = T;
+        pinned_allocator() noexcept = default;
+        template <class U> pinned_allocator(const pinned_allocator<U>&) noexcept {}
+        T* allocate(std::size_t n)
+        {
+            void* p = nullptr;
+            check(xtb_host_alloc(n * sizeof(T), &p));
+            return static_cast<T*>(p);
+        }
+        void deallocate(T* p, std::size_t) noexcept { xtb_host_free(p); }
+        template <class U> bool operator==(const pinned_allocator<U>&) const noexcept { return true; }
+        template <class U> bool operator!=(const pinned_allocator<U>&) const noexcept { return false; }
+    };
+
+    // host containers in pinned memory: ordinary xt::xtensor / xt::xarray with another allocator
+    template <class T, std::size_t N, xt::layout_type L = XTENSOR_DEFAULT_LAYOUT>
+    using pinned_xtensor = xt::xtensor_container<xt::uvector<T, pinned_allocator<T>>, N, L>;
+    template <class T, xt::layout_type L = XTENSOR_DEFAULT_LAYOUT>
+    using pinned_xarray = xt::xarray_container<xt::uvector<T, pinned_allocator<T>>, L>;
+
+    // ---------------------------------------------------------------- multi-GPU (one process per GPU)
+    // The reference's own partial -> merge -> finalize contract is xblockwise_reducer
+    // (reducers/xblockwise_reducer.hpp:154-185, functors xblockwise_reducer_functors.hpp:45-260).  Here the
+    // containers of one process hold a contiguous block of the LEADING axis; elementwise work and reductions
+    // over other axes need no exchange, a reduction over axis 0 merges one partial per rank.
+    namespace dist
+    {
+        // Star rendezvous over TCP on the launcher's MASTER_ADDR (rank 0 listens on MASTER_PORT + port_offset):
+        // used once, to hand the NCCL id and the peer-memory handles around.  Not on any data path.
+        class rendezvous
+        {
+        public:
+
+            rendezvous(int rank, int world, const std::string& addr, int port);
+            ~rendezvous();
+            rendezvous(const rendezvous&) = delete;
+            // every rank contributes n bytes; all ranks receive the world * n bytes in rank order
+            void allgather(const void* mine, std::size_t n, void* all);
+
+        private:
+
+            int m_rank, m_world;
+            int m_listen = -1;
+            std::vector<int> m_peers;   // rank 0: socket of every other rank; others: [0] = socket to rank 0
+        };
+
+        struct communicator
+        {
+            int rank = 0;
+            int world = 1;
+            bool peer_memory = false;   // small allreduces run as one kernel over NVLink peer memory
+        };
+
+        // Bring up the exchange: NCCL communicator through the C ABI and -- all ranks or none -- the NVLink
+        // peer-memory windows (xtb_comm_p2p_*).  Call after xtb_init(local device).
+        communicator init(int rank, int world, const std::string& master_addr, int port);
+        // RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT as set by torchrun; also selects the device
+        communicator init_from_env(int port_offset = 29);
+        inline void finalize() { xtb_comm_destroy(); }
+
+        // [begin, end) of a rank's block of the leading axis (remainder rows go to the low ranks)
+        inline std::pair<std::size_t, std::size_t> row_block(std::size_t rows, int rank, int world)
+        {
+            const std::size_t base = rows / world, rem = rows % world;
+            const std::size_t b = rank * base + std::min<std::size_t>(rank, rem);
+            return {b, b + base + (static_cast<std::size_t>(rank) < rem ? 1 : 0)};
+        }
+
+        // xtb::dist::allreduce(xt::sum(local, {0})): evaluate a reducer over the sharded axis and merge the per-rank
+        // partials in the same call (fused into the merge kernel over peer memory when attached, NCCL otherwise);
+        // every rank gets the identical result.  xt::initial is applied once, after the merge.
+        template <class R>
+            requires lower::is_reducer_node<R>::value
+        inline auto allreduce(const R& reducer)
+        {
+            xtb::xarray<typename R::value_type> out;
+            std::vector<std::size_t> shp(reducer.shape().begin(), reducer.shape().end());
+            out.resize(shp);
+            lower::run_reducer(reducer, out, true);
+            return out;
+        }
+
+        // mean over `axes` (which include the sharded axis 0) of a row-sharded expression: merged sum divided by
+        // the GLOBAL count, the division being the epilogue of the merge (mean_functor::finalize,
+        // xblockwise_reducer_functors.hpp:175-185).  T as in xt::mean<T>.
+        template <class T = void, class E, class X>
+        inline auto mean(const xt::xexpression<E>& local, const X& axes, std::size_t global_rows)
+        {
+            const E& e = local.derived_cast();
+            using value_type = std::conditional_t<std::is_same<T, void>::value, double, T>;
+            std::vector<std::size_t> ax(std::begin(axes), std::end(axes));
+            auto red = xt::sum<T>(e, ax);
+            double count = 1;
+            for (auto a : ax)
+            {
+                count *= static_cast<double>(a == 0 ? global_rows : e.shape()[a]);
+            }
+            xtb_finalize fin{};
+            fin.op = XTB_FIN_DIV;
+            fin.type = dtype_v<value_type>;
+            const value_type div = static_cast<value_type>(count);
+            std::memcpy(&fin.imm, &div, sizeof(div));
+            xtb::xarray<value_type> out;
+            std::vector<std::size_t> shp(red.shape().begin(), red.shape().end());
+            out.resize(shp);
+            const bool crosses = std::find(ax.begin(), ax.end(), std::size_t(0)) != ax.end();
+            lower::run_reducer(red, out, crosses, &fin);
+            return out;
+        }
+
+        // two-pass variance (core/xmath.hpp:2082-2105) of a row-sharded expression: the merged mean is broadcast
+        // back (every rank holds it), then mean(square(local - mean)) with a second merge
+        template <class T = void, class E, class X>
+        inline auto variance(const xt::xexpression<E>& local, const X& axes, std::size_t global_rows)
+        {
+            const E& e = local.derived_cast();
+            using value_type = std::conditional_t<std::is_same<T, void>::value, double, T>;
+            auto m = mean<T>(e, axes, global_rows);
+            std::vector<std::size_t> keep(e.shape().begin(), e.shape().end());
+            for (auto a : axes)
+            {
+                keep[static_cast<std::size_t>(a)] = 1;
+            }
+            auto mrv = xt::reshape_view(m, keep);
+            return mean<value_type>(xt::square(xt::cast<value_type>(e) - mrv), axes, global_rows);
+        }
+    }
+}
+
+// ---- rendezvous / bring-up (sockets: POSIX) ------------------------------------------------------------
+#include <arpa/inet.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdlib>
+#include <thread>
+
+namespace xtb
+{
+    namespace dist
+    {
+        namespace detail
+        {
+            inline void send_all(int fd, const void* p, std::size_t n)
+            {
+                const char* c = static_cast<const char*>(p);
+                while (n)
+                {
+                    const ssize_t k = ::send(fd, c, n, MSG_NOSIGNAL);
+                    if (k <= 0)
+                    {
+                        XTENSOR_THROW(std::runtime_error, "xtb200: rendezvous send failed");
+                    }
+                    c += k;
+                    n -= static_cast<std::size_t>(k);
+                }
+            }
+
+            inline void recv_all(int fd, void* p, std::size_t n)
+            {
+                char* c = static_cast<char*>(p);
+                while (n)
+                {
+                    const ssize_t k = ::recv(fd, c, n, 0);
+                    if (k <= 0)
+                    {
+                        XTENSOR_THROW(std::runtime_error, "xtb200: rendezvous receive failed");
+                    }
+                    c += k;
+                    n -= static_cast<std::size_t>(k);
+                }
+            }
+        }
+
+        inline rendezvous::rendezvous(int rank, int world, const std::string& addr, int port)
+            : m_rank(rank)
+            , m_world(world)
+        {
+            if (world <= 1)
+            {
+                return;
+            }
+            if (rank == 0)
+            {
+                m_listen = ::socket(AF_INET, SOCK_STREAM, 0);
+                int one = 1;
+                ::setsockopt(m_listen, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+                sockaddr_in sa{};
+                sa.sin_family = AF_INET;
+                sa.sin_addr.s_addr = htonl(INADDR_ANY);
+                sa.sin_port = htons(static_cast<std::uint16_t>(port));
+                if (::bind(m_listen, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) != 0 || ::listen(m_listen, world) != 0)
+                {
+                    XTENSOR_THROW(std::runtime_error, "xtb200: rendezvous cannot listen on port " + std::to_string(port));
+                }
+                m_peers.assign(static_cast<std::size_t>(world), -1);
+                for (int i = 1; i < world; ++i)
+                {
+                    const int fd = ::accept(m_listen, nullptr, nullptr);
+                    if (fd < 0)
+                    {
+                        XTENSOR_THROW(std::runtime_error, "xtb200: rendezvous accept failed");
+                    }
+                    std::int32_t r = -1;
+                    detail::recv_all(fd, &r, sizeof(r));
+                    if (r <= 0 || r >= world || m_peers[static_cast<std::size_t>(r)] >= 0)
+                    {
+                        XTENSOR_THROW(std::runtime_error, "xtb200: rendezvous got a bad rank");
+                    }
+                    m_peers[static_cast<std::size_t>(r)] = fd;
+                }
+            }
+            else
+            {
+                addrinfo hints{}, *res = nullptr;
+                hints.ai_family = AF_INET;
+                hints.ai_socktype = SOCK_STREAM;
+                if (::getaddrinfo(addr.c_str(), std::to_string(port).c_str(), &hints, &res) != 0 || !res)
+                {
+                    XTENSOR_THROW(std::runtime_error, "xtb200: rendezvous cannot resolve " + addr);
+                }
+                int fd = -1;
+                for (int attempt = 0; attempt < 600 && fd < 0; ++attempt)   // rank 0 may not be listening yet
+                {
+                    fd = ::socket(AF_INET, SOCK_STREAM, 0);
+                    if (::connect(fd, res->ai_addr, res->ai_addrlen) != 0)
+                    {
+                        ::close(fd);
+                        fd = -1;
+                        std::this_thread::sleep_for(std::chrono::milliseconds(100));
+                    }
+                }
+                ::freeaddrinfo(res);
+                if (fd < 0)
+                {
+                    XTENSOR_THROW(std::runtime_error, "xtb200: rendezvous cannot reach rank 0 at " + addr + ":" + std::to_string(port));
+                }
+                int one = 1;
+                ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+                const std::int32_t r = rank;
+                detail::send_all(fd, &r, sizeof(r));
+                m_peers.assign(1, fd);
+            }
+        }
+
+        inline rendezvous::~rendezvous()
+        {
+            for (int fd : m_peers)
+            {
+                if (fd >= 0)
+                {
+                    ::close(fd);
+                }
+            }
+            if (m_listen >= 0)
+            {
+                ::close(m_listen);
+            }
+        }
+
+        inline void rendezvous::allgather(const void* mine, std::size_t n, void* all)
+        {
+            char* out = static_cast<char*>(all);
+            if (m_world <= 1)
+            {
+                std::memcpy(out, mine, n);
+                return;
+            }
+            if (m_rank == 0)
+            {
+                std::memcpy(out, mine, n);
+                for (int r = 1; r < m_world; ++r)
+                {
+                    detail::recv_all(m_peers[static_cast<std::size_t>(r)], out + static_cast<std::size_t>(r) * n, n);
+                }
+                for (int r = 1; r < m_world; ++r)
+                {
+                    detail::send_all(m_peers[static_cast<std::size_t>(r)], out, n * static_cast<std::size_t>(m_world));
+                }
+            }
+            else
+            {
+                detail::send_all(m_peers[0], mine, n);
+                detail::recv_all(m_peers[0], out, n * static_cast<std::size_t>(m_world));
+            }
+        }
+
+        inline communicator init(int rank, int world, const std::string& master_addr, int port)
+        {
+            communicator cm;
+            cm.rank = rank;
+            cm.world = world;
+            if (world <= 1)
+            {
+                return cm;
+            }
+            rendezvous rv(rank, world, master_addr, port);
+            // NCCL id: created on rank 0, everybody takes rank 0's
+            std::vector<char> ids(128 * static_cast<std::size_t>(world), 0);
+            char mine[128] = {0};
+            if (rank == 0)
+            {
+                check(xtb_comm_unique_id(mine));
+            }
+            rv.allgather(mine, 128, ids.data());
+            check(xtb_comm_init(rank, world, ids.data()));
+            // peer-memory windows: every step is collective -- one rank that cannot export or map makes ALL fall back
+            if (world <= 8 && std::getenv("XTB_NO_P2P") == nullptr)
+            {
+                struct slot { char handle[64]; std::int32_t ok; };
+                slot me{};
+                me.ok = xtb_comm_p2p_handle(me.handle) == XTB_OK;
+                std::vector<slot> every(static_cast<std::size_t>(world));
+                rv.allgather(&me, sizeof(slot), every.data());
+                bool ok = true;
+                std::vector<char> handles(64 * static_cast<std::size_t>(world));
+                for (int r = 0; r < world; ++r)
+                {
+                    ok = ok && every[static_cast<std::size_t>(r)].ok;
+                    std::memcpy(handles.data() + 64 * r, every[static_cast<std::size_t>(r)].handle, 64);
+                }
+                std::int32_t attached = ok && xtb_comm_p2p_attach(handles.data(), world) == XTB_OK;
+                std::vector<std::int32_t> flags(static_cast<std::size_t>(world));
+                rv.allgather(&attached, sizeof(attached), flags.data());   // also the barrier before anyone's next allreduce
+                bool all_ok = true;
+                for (auto f : flags)
+                {
+                    all_ok = all_ok && f;
+                }
+                if (!all_ok)
+                {
+                    check(xtb_comm_p2p_attach(nullptr, 0));
+                }
+                cm.peer_memory = all_ok;
+            }
+            return cm;
+        }
+
+        inline communicator init_from_env(int port_offset)
+        {
+            auto env_int = [](const char* name, int dflt) {
+                const char* v = std::getenv(name);
+                return v ? std::atoi(v) : dflt;
+            };
+            const int rank = env_int("RANK", 0), world = env_int("WORLD_SIZE", 1), local = env_int("LOCAL_RANK", rank);
+            const char* addr = std::getenv("MASTER_ADDR");
+            check(xtb_init(local));
+            return init(rank, world, addr ? addr : "127.0.0.1", env_int("MASTER_PORT", 29500) + port_offset);
+        }
     }
 }
 

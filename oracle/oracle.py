@@ -34,6 +34,8 @@ def lib():
                                  C.POINTER(C.c_int32), i32, vp, C.POINTER(Operand), i32]
         L.xto_scan.restype = i32
         L.xto_scan.argtypes = [i32, i32, C.POINTER(Operand), i32, C.POINTER(Operand)]
+        L.xto_argreduce.restype = i32
+        L.xto_argreduce.argtypes = [i32, C.POINTER(Operand), i32, C.POINTER(Operand)]
         _LIB = L
     return _LIB
 

@@ -22,6 +22,8 @@
 #include <xtensor/core/xmath.hpp>
 #include <xtensor/core/xnoalias.hpp>
 #include <xtensor/misc/xmanipulation.hpp>
+#include <xtensor/misc/xsort.hpp>
+#include <xtensor/reducers/xnorm.hpp>
 #include <xtensor/reducers/xaccumulator.hpp>
 #include <xtensor/reducers/xreducer.hpp>
 #include <xtensor/views/xbroadcast.hpp>
@@ -373,6 +375,104 @@ extern "C"
             case 9: return cumsum_impl<float, float>(in, nd, shape, axis, out);
             case 10: return cumsum_impl<double, double>(in, nd, shape, axis, out);
         }
+        return -1;
+    }
+
+    // ---- argmin / argmax (misc/xsort.hpp:1237-1295), minmax (core/xmath.hpp:2195-2228), norms (reducers/xnorm.hpp) ----
+    extern "C++"
+    {
+        template <class T> int argfn_impl(int is_max, const void* in, int nd, const int64_t* shape, int axis, uint64_t* out)
+        {
+            try
+            {
+                xt::xarray<T> A = in_arr<T>(in, mk_shape(nd, shape));
+                xt::xarray<std::size_t> r;
+                if (axis < -64) { if (is_max) r = xt::argmax(A); else r = xt::argmin(A); }
+                else { if (is_max) r = xt::argmax(A, axis); else r = xt::argmin(A, axis); }
+                std::copy(r.begin(), r.end(), out);
+                return (int) r.size();
+            }
+            catch (std::exception& e) { g_err = e.what(); return -3; }
+        }
+        template <class T> int minmax_impl(const void* in, int nd, const int64_t* shape, void* out)
+        {
+            xt::xarray<T> A = in_arr<T>(in, mk_shape(nd, shape));
+            xt::xtensor<std::array<T, 2>, 0> r = xt::minmax(A);
+            static_cast<T*>(out)[0] = r()[0];
+            static_cast<T*>(out)[1] = r()[1];
+            return 2;
+        }
+        // norms over ONE axis (brace lists are what the reference's overload set accepts); name: l0 l1 sq l2 linf lp_to_p lp
+        template <class T, class R0, class R1> int normfn_impl(const std::string& name, const void* in, int nd, const int64_t* shape,
+                                                               int axis, double p, void* out)
+        {
+            try
+            {
+                xt::xarray<T> A = in_arr<T>(in, mk_shape(nd, shape));
+                const std::size_t ax[1] = {(std::size_t) axis};
+    #define XTREF_NORM(NAME, CALL)                                                                      \
+                if (name == NAME)                                                                       \
+                {                                                                                       \
+                    auto lazy = CALL;                                                                   \
+                    using R = typename decltype(lazy)::value_type;                                      \
+                    xt::xarray<R> r = lazy;                                                             \
+                    std::copy(r.begin(), r.end(), static_cast<R*>(out));                                \
+                    return (int) (r.size() * 16 + sizeof(R));                                           \
+                }
+                XTREF_NORM("l0", xt::norm_l0(A, ax))
+                XTREF_NORM("l1", xt::norm_l1(A, ax))
+                XTREF_NORM("sq", xt::norm_sq(A, ax))
+                XTREF_NORM("l2", xt::norm_l2(A, ax))
+                XTREF_NORM("linf", xt::norm_linf(A, ax))
+                XTREF_NORM("lp_to_p", xt::norm_lp_to_p(A, p, ax))
+                XTREF_NORM("lp", xt::norm_lp(A, p, ax))
+    #undef XTREF_NORM
+                g_err = "unknown norm " + name;
+                return -2;
+            }
+            catch (std::exception& e) { g_err = e.what(); return -3; }
+        }
+    }
+    // axis < -64: flattened
+    int xtref_argfn(int is_max, int dtype, const void* in, int nd, const int64_t* shape, int axis, uint64_t* out)
+    {
+        switch (dtype)
+        {
+            case 1: return argfn_impl<int8_t>(is_max, in, nd, shape, axis, out);
+            case 2: return argfn_impl<uint8_t>(is_max, in, nd, shape, axis, out);
+            case 3: return argfn_impl<int16_t>(is_max, in, nd, shape, axis, out);
+            case 5: return argfn_impl<int32_t>(is_max, in, nd, shape, axis, out);
+            case 7: return argfn_impl<int64_t>(is_max, in, nd, shape, axis, out);
+            case 8: return argfn_impl<uint64_t>(is_max, in, nd, shape, axis, out);
+            case 9: return argfn_impl<float>(is_max, in, nd, shape, axis, out);
+            case 10: return argfn_impl<double>(is_max, in, nd, shape, axis, out);
+        }
+        g_err = "unsupported dtype";
+        return -1;
+    }
+    int xtref_minmax(int dtype, const void* in, int nd, const int64_t* shape, void* out)
+    {
+        switch (dtype)
+        {
+            case 3: return minmax_impl<int16_t>(in, nd, shape, out);
+            case 5: return minmax_impl<int32_t>(in, nd, shape, out);
+            case 9: return minmax_impl<float>(in, nd, shape, out);
+            case 10: return minmax_impl<double>(in, nd, shape, out);
+        }
+        g_err = "unsupported dtype";
+        return -1;
+    }
+    // returns count * 16 + sizeof(result element), so that the caller learns the result type's width
+    int xtref_normfn(const char* name, int dtype, const void* in, int nd, const int64_t* shape, int axis, double p, void* out)
+    {
+        switch (dtype)
+        {
+            case 5: return normfn_impl<int32_t, void, void>(name, in, nd, shape, axis, p, out);
+            case 4: return normfn_impl<uint16_t, void, void>(name, in, nd, shape, axis, p, out);
+            case 9: return normfn_impl<float, void, void>(name, in, nd, shape, axis, p, out);
+            case 10: return normfn_impl<double, void, void>(name, in, nd, shape, axis, p, out);
+        }
+        g_err = "unsupported dtype";
         return -1;
     }
 }

@@ -248,3 +248,41 @@ def average(a, w, axes):
         raise RuntimeError(lib().xtref_last_error().decode())
     assert r == out.size
     return out
+
+
+_DT = {np.dtype(np.int8): 1, np.dtype(np.uint8): 2, np.dtype(np.int16): 3, np.dtype(np.uint16): 4, np.dtype(np.int32): 5,
+       np.dtype(np.int64): 7, np.dtype(np.uint64): 8, np.dtype(np.float32): 9, np.dtype(np.float64): 10}
+
+
+def argfn(name, a, axis=None):
+    """xt::argmin / xt::argmax (misc/xsort.hpp:1237-1295) of the real reference; axis None = flattened."""
+    a = np.ascontiguousarray(a)
+    shp = () if axis is None else tuple(s for d, s in enumerate(a.shape) if d != (axis % a.ndim))
+    out = np.empty(shp, np.uint64)
+    r = lib().xtref_argfn(int(name == "argmax"), _DT[a.dtype], _p(a), a.ndim, _i64(a.shape), -100 if axis is None else int(axis), _p(out))
+    if r < 0:
+        raise RuntimeError(lib().xtref_last_error().decode())
+    assert r == max(out.size, 1)
+    return out
+
+
+def minmax(a):
+    a = np.ascontiguousarray(a)
+    out = np.empty(2, a.dtype)
+    r = lib().xtref_minmax(_DT[a.dtype], _p(a), a.ndim, _i64(a.shape), _p(out))
+    if r < 0:
+        raise RuntimeError(lib().xtref_last_error().decode())
+    return out
+
+
+def normfn(name, a, axis, p=0.0):
+    """xt::norm_<name>(a, {axis}[, p]) (reducers/xnorm.hpp); the result dtype is whatever the reference computes."""
+    a = np.ascontiguousarray(a)
+    shp = tuple(s for d, s in enumerate(a.shape) if d != axis)
+    raw = np.empty(int(np.prod(shp, dtype=np.int64)) * 8, np.uint8)
+    r = lib().xtref_normfn(name.encode(), _DT[a.dtype], _p(a), a.ndim, _i64(a.shape), int(axis), C.c_double(p), _p(raw))
+    if r < 0:
+        raise RuntimeError(lib().xtref_last_error().decode())
+    n, width = r // 16, r % 16
+    assert n == int(np.prod(shp, dtype=np.int64))
+    return raw[: n * width], width, shp

@@ -256,6 +256,13 @@ template <class T> Val binary_t(int op, T x, T y) {
         case XTB_OP_LAND: return mk((bool) (x && y));
         case XTB_OP_MAXIMUM: return mk((T) (x > y ? x : y));  // xtl::select(t1 > t2, t1, t2) xmath.hpp:588-602
         case XTB_OP_MINIMUM: return mk((T) (x < y ? x : y));  // xmath.hpp:570-586
+        // detail::nan_min / nan_max, xmath.hpp:2333-2363
+        case XTB_OP_NANMIN:
+            if constexpr (std::is_floating_point<T>::value) return mk((T) (std::isnan(x) ? y : (std::isnan(y) ? x : (x < y ? x : y))));
+            else return mk((T) (x < y ? x : y));
+        case XTB_OP_NANMAX:
+            if constexpr (std::is_floating_point<T>::value) return mk((T) (std::isnan(x) ? y : (std::isnan(y) ? x : (x > y ? x : y))));
+            else return mk((T) (x > y ? x : y));
     }
     if constexpr (std::is_floating_point<T>::value) {
         switch (op) {
@@ -403,6 +410,12 @@ int xto_assign(const xtb_program* prog, const xtb_operand* out, const xtb_operan
 }
 
 static Val identity_of(int op, int rt) {
+    // nanmin / nanmax start from NaN (XTENSOR_REDUCER_FUNCTION(nanmin, detail::nan_min, ..., std::nan("0")), xmath.hpp:2427-2442)
+    if (op == XTB_RED_NANMIN || op == XTB_RED_NANMAX) {
+        if (rt == XTB_F32) return mk(std::numeric_limits<float>::quiet_NaN());
+        if (rt == XTB_F64) return mk(std::numeric_limits<double>::quiet_NaN());
+        op = (op == XTB_RED_NANMIN) ? XTB_RED_MIN : XTB_RED_MAX;
+    }
     switch (op) {
         case XTB_RED_SUM: return cast_to(mk((int32_t) 0), rt);
         case XTB_RED_PROD: return cast_to(mk((int32_t) 1), rt);
@@ -431,6 +444,8 @@ static int binop_of(int op) {
         case XTB_RED_SUM: return XTB_OP_ADD;
         case XTB_RED_PROD: return XTB_OP_MUL;
         case XTB_RED_MAX: return XTB_OP_MAXIMUM;
+        case XTB_RED_NANMIN: return XTB_OP_NANMIN;
+        case XTB_RED_NANMAX: return XTB_OP_NANMAX;
         default: return XTB_OP_MINIMUM;
     }
 }
@@ -729,6 +744,76 @@ int xto_scan(int op, int acc_type, const xtb_operand* in, int axis, const xtb_op
     for (int64_t i = 0; i < total; ++i) {
         store((char*) so.p, out->dtype, res[(size_t) i]);
         int d = ond;
+        while (d != 0) {
+            --d;
+            if (idx[d] != out->shape[d] - 1) { ++idx[d]; so.step(d); break; }
+            idx[d] = 0;
+            if (d != 0) so.reset(d);
+        }
+    }
+    return XTB_OK;
+}
+
+// argmin / argmax: detail::arg_func_impl (misc/xsort.hpp:1150-1231) and the flat overloads (:1237-1245, 1267-1275,
+// std::min_element / std::max_element).  Per lane along `axis`:
+//     val = x[0]; idx = 0;  for i = 1..n-1: if (cmp(x[i], val)) { val = x[i]; idx = i; }
+// cmp = std::less (argmin) / std::greater (argmax) on the element type -- ties keep the first index, a NaN never
+// replaces the running value, a NaN at x[0] is never replaced.  (std::min_element is the same loop with
+// `*it < *smallest`, std::max_element with `*largest < *it`.)
+int xto_argreduce(int op, const xtb_operand* in, int axis, const xtb_operand* out) {
+    xtb_operand x = *in;
+    if (axis < 0) {
+        int64_t total = 1;
+        for (int d = 0; d < in->ndim; ++d) total *= in->shape[d];
+        // flat: row-major traversal; gather through the stepper into a dense copy first
+        x.ndim = 1;
+        x.shape[0] = total;
+        axis = 0;
+    } else if (axis >= in->ndim) {
+        return fail(XTB_ERR_AXIS, "Axis out of bounds");
+    }
+    // dense row-major copy of the operand in its element type (what eval(e) gives)
+    int64_t total = 1;
+    for (int d = 0; d < in->ndim; ++d) total *= in->shape[d];
+    if (total == 0) return XTB_OK;
+    std::vector<Val> v((size_t) total);
+    {
+        Stepper s;
+        s.init(in, in->ndim, in->shape);
+        int64_t idx[XTB_MAX_DIM] = {0};
+        for (int64_t i = 0; i < total; ++i) {
+            v[(size_t) i] = load(s.p, in->dtype);
+            int d = in->ndim;
+            while (d != 0) {
+                --d;
+                if (idx[d] != in->shape[d] - 1) { ++idx[d]; s.step(d); break; }
+                idx[d] = 0;
+                if (d != 0) s.reset(d);
+            }
+        }
+    }
+    int64_t inner = 1;
+    for (int d = axis + 1; d < x.ndim; ++d) inner *= x.shape[d];
+    const int64_t n = x.shape[axis];
+    const int64_t outer = total / (inner * n);
+    const int cmp = op == XTB_RED_MIN ? XTB_OP_LT : XTB_OP_GT;
+    std::vector<uint64_t> res((size_t) (outer * inner));
+    for (int64_t o = 0; o < outer; ++o)
+        for (int64_t j = 0; j < inner; ++j) {
+            Val best = v[(size_t) (o * n * inner + j)];
+            uint64_t bi = 0;
+            for (int64_t i = 1; i < n; ++i) {
+                const Val& c = v[(size_t) ((o * n + i) * inner + j)];
+                if (binary(cmp, c, best).i32) { best = c; bi = (uint64_t) i; }
+            }
+            res[(size_t) (o * inner + j)] = bi;
+        }
+    Stepper so;
+    so.init(out, out->ndim, out->shape);
+    int64_t idx[XTB_MAX_DIM] = {0};
+    for (size_t i = 0; i < res.size(); ++i) {
+        store((char*) so.p, out->dtype, mk((uint64_t) res[i]));
+        int d = out->ndim;
         while (d != 0) {
             --d;
             if (idx[d] != out->shape[d] - 1) { ++idx[d]; so.step(d); break; }

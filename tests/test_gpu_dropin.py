@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("name", ["test_dropin"])
+@pytest.mark.parametrize("name", ["test_dropin", "test_dropin_reducers"])
 def test_cpp_dropin(gpu, name):
     exe = os.path.join(HERE, "cpp", "_build", name)
     assert os.path.exists(exe), f"{exe} missing: run `make -C tests/cpp` where /root/reference exists"

@@ -14,7 +14,7 @@ MAX_DIM, MAX_LEAVES, MAX_INSNS, MAX_IMMS = 8, 8, 48, 16
 # xtb_dtype
 BOOL, I8, U8, I16, U16, I32, U32, I64, U64, F32, F64 = range(11)
 # xtb_reduce_op
-RED_SUM, RED_PROD, RED_MAX, RED_MIN = range(4)
+RED_SUM, RED_PROD, RED_MAX, RED_MIN, RED_NANMIN, RED_NANMAX = range(6)
 # xtb_src
 SRC_STACK, SRC_LEAF, SRC_IMM, SRC_REV = 0, 1, 2, 4
 H2D, D2H, D2D = 1, 2, 3
@@ -27,7 +27,7 @@ OPCODES = dict(
     RAD2DEG=42, SQUARE=43, CUBE=44,
     ADD=64, SUB=65, MUL=66, DIV=67, MOD=68, LOR=69, LAND=70, BOR=71, BAND=72, BXOR=73, SHL=74, SHR=75,
     LT=76, LE=77, GT=78, GE=79, EQ=80, NE=81, FMOD=82, REMAINDER=83, FMAX=84, FMIN=85, FDIM=86, POW=87,
-    HYPOT=88, ATAN2=89, MAXIMUM=90, MINIMUM=91,
+    HYPOT=88, ATAN2=89, MAXIMUM=90, MINIMUM=91, NANMIN=92, NANMAX=93,
     WHERE=112, FMA=113, CLAMP=114,
 )
 
@@ -70,7 +70,7 @@ SYMBOLS = [
     "xtb_graph_begin", "xtb_graph_end", "xtb_graph_launch", "xtb_graph_destroy", "xtb_fork_begin", "xtb_fork_end", "xtb_fork_join",
     "xtb_assign", "xtb_assign_host", "xtb_reduce", "xtb_scan", "xtb_comm_unique_id", "xtb_comm_init", "xtb_comm_destroy",
     "xtb_comm_info", "xtb_comm_p2p_handle", "xtb_comm_p2p_attach", "xtb_allreduce", "xtb_launch_count", "xtb_last_kernel", "xtb_program_result_type",
-    "xtb_reduce_fin", "xtb_set_option", "xtb_get_option", "xtb_graph_kernel_count",
+    "xtb_reduce_fin", "xtb_set_option", "xtb_get_option", "xtb_graph_kernel_count", "xtb_argreduce",
 ]
 
 _LIB = None
@@ -126,6 +126,7 @@ def lib():
         "xtb_get_option": (C.c_longlong, [C.c_char_p]),
         "xtb_graph_kernel_count": (i32, [vp]),
         "xtb_scan": (i32, [i32, i32, C.POINTER(Operand), i32, C.POINTER(Operand)]),
+        "xtb_argreduce": (i32, [i32, C.POINTER(Operand), i32, C.POINTER(Operand)]),
         "xtb_comm_unique_id": (i32, [vp]),
         "xtb_comm_init": (i32, [i32, i32, vp]),
         "xtb_comm_destroy": (i32, []),

@@ -106,6 +106,8 @@ template <class T> XTB_DEV T p2p_op(int op, T a, T b) {
         case XTB_RED_SUM: return (T) (a + b);
         case XTB_RED_PROD: return (T) (a * b);
         case XTB_RED_MAX: return a > b ? a : b;          // math::maximum: (a > b) ? a : b
+        case XTB_RED_NANMIN: return (a != a) ? b : ((b != b) ? a : (a < b ? a : b));   // detail::nan_min
+        case XTB_RED_NANMAX: return (a != a) ? b : ((b != b) ? a : (a > b ? a : b));   // detail::nan_max
         default: return a < b ? a : b;
     }
 }
@@ -161,7 +163,7 @@ int comm_allreduce(DeviceCtx* ctx, void* buf, size_t count, int dtype, int op) {
     if (g_nccl.world <= 1 && !g_nccl.comm) return XTB_OK;  // single rank: nothing to merge
     if (!g_nccl.comm) XTB_FAIL(XTB_ERR_NCCL, "xtb_comm_init has not been called");
     const int dt = nccl_dtype(dtype), ro = nccl_op(op);
-    if (dt < 0 || ro < 0) XTB_FAIL(XTB_ERR_UNSUPPORTED, "allreduce of dtype %d / op %d", dtype, op);
+    if (dt < 0 || op < XTB_RED_SUM || op > XTB_RED_NANMAX) XTB_FAIL(XTB_ERR_UNSUPPORTED, "allreduce of dtype %d / op %d", dtype, op);
     if (count == 0) return XTB_OK;
     if (g_p2p.ready && count * (size_t) dtype_size(dtype) <= kP2pMaxBytes && dtype >= XTB_I32) {
         switch (dtype) {
@@ -173,6 +175,8 @@ int comm_allreduce(DeviceCtx* ctx, void* buf, size_t count, int dtype, int op) {
             default: return launch_p2p<double>(ctx, buf, count, op);
         }
     }
+    // NCCL has no NaN-skipping extremes: nan_min / nan_max merge through the peer-memory kernel only
+    if (ro < 0) XTB_FAIL(XTB_ERR_UNSUPPORTED, "allreduce op %d needs the peer-memory route (payload <= %d KB, xtb_comm_p2p_attach)", op, (int) (kP2pMaxBytes >> 10));
     XTB_NCCL(g_nccl.all_reduce(buf, buf, count, dt, ro, g_nccl.comm, ctx->stream));
     note_launch("ncclAllReduce");
     return XTB_OK;

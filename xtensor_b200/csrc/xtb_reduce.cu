@@ -19,6 +19,13 @@ bool comm_p2p_params(DeviceCtx* ctx, P2pParams* w);                             
 static uint64_t identity_bits(int op, int rt) {
     union { uint64_t u; double d; float f[2]; int32_t i32[2]; uint32_t u32[2]; int64_t i64; } v;
     v.u = 0;
+    // nan_min / nan_max start from NaN (XTENSOR_REDUCER_FUNCTION(nanmin, ..., std::nan("0")), xmath.hpp:2427-2442);
+    // for integer accumulators they are the plain extremes
+    if (op == XTB_RED_NANMIN || op == XTB_RED_NANMAX) {
+        if (rt == XTB_F32) { v.u32[0] = 0x7fc00000u; return v.u; }
+        if (rt == XTB_F64) { v.u = 0x7ff8000000000000ull; return v.u; }
+        op = (op == XTB_RED_NANMIN) ? XTB_RED_MIN : XTB_RED_MAX;
+    }
     switch (op) {
         case XTB_RED_SUM: break;
         case XTB_RED_PROD:
@@ -57,6 +64,8 @@ static int binop_of(int op) {
         case XTB_RED_PROD: return XTB_OP_MUL;
         case XTB_RED_MAX: return XTB_OP_MAXIMUM;
         case XTB_RED_MIN: return XTB_OP_MINIMUM;
+        case XTB_RED_NANMIN: return XTB_OP_NANMIN;
+        case XTB_RED_NANMAX: return XTB_OP_NANMAX;
         default: return -1;
     }
 }
@@ -154,6 +163,8 @@ static int merge_partials(const RdParams& fp, DeviceCtx* ctx, bool xchg, const P
         case XTB_OP_MUL: XTB_TRY(launch_merge_rt<XTB_OP_MUL>(fp.acc_rt, fp, ctx, xchg, xw)); break;
         case XTB_OP_MAXIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MAXIMUM>(fp.acc_rt, fp, ctx, xchg, xw)); break;
         case XTB_OP_MINIMUM: XTB_TRY(launch_merge_rt<XTB_OP_MINIMUM>(fp.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_NANMIN: XTB_TRY(launch_merge_rt<XTB_OP_NANMIN>(fp.acc_rt, fp, ctx, xchg, xw)); break;
+        case XTB_OP_NANMAX: XTB_TRY(launch_merge_rt<XTB_OP_NANMAX>(fp.acc_rt, fp, ctx, xchg, xw)); break;
         default: XTB_FAIL(XTB_ERR_INVALID, "merge: operator %d", fp.binop);
     }
     note_launch(name);

@@ -283,7 +283,7 @@ int validate_program(const xtb_program* p, const int32_t* leaf_dtypes, int* resu
                 if (op == XTB_OP_BITNOT && is_float_type(in.type)) XTB_FAIL(XTB_ERR_INVALID, "insn %d: ~ on float", pc);
             }
         } else if (op < XTB_OP_WHERE) {  // binary
-            if (op > XTB_OP_MINIMUM) XTB_FAIL(XTB_ERR_INVALID, "insn %d: unknown opcode %d", pc, op);
+            if (op > XTB_OP_NANMAX) XTB_FAIL(XTB_ERR_INVALID, "insn %d: unknown opcode %d", pc, op);
             const int kind = in.src & 3;
             int ty;
             if (kind == XTB_SRC_STACK) {

@@ -900,19 +900,58 @@ def count_nonnan(e, axes=None, keep_dims=False):
     return count_nonzero(logical_not(isnan(as_expr(e))), axes, keep_dims)
 
 
-def _nan_extreme(red, fill, e, axes, keep_dims):
-    # nan_min / nan_max start from NaN and skip NaN operands (core/xmath.hpp:2333-2363, 2427-2443): the
-    # extreme of the non-NaN values, NaN where there is none
+def nanmin(e, axes=None, keep_dims=False):
+    """XTENSOR_REDUCER_FUNCTION(nanmin, detail::nan_min, value_type, std::nan("0")) (core/xmath.hpp:2333-2346, 2427):
+    starts from NaN and skips NaN operands -- the minimum of the non-NaN values, NaN where there is none."""
+    return Reducer(capi.RED_NANMIN, as_expr(e), axes, keep_dims)
+
+
+def nanmax(e, axes=None, keep_dims=False):
+    """detail::nan_max (core/xmath.hpp:2348-2363, 2442)."""
+    return Reducer(capi.RED_NANMAX, as_expr(e), axes, keep_dims)
+
+
+def minmax(e):
+    """xt::minmax (core/xmath.hpp:2195-2228): {min, max} over the whole expression (a reducer over every axis whose
+    value type is std::array<value_type, 2>); returned as a 2-element array of e's dtype."""
     e = as_expr(e)
-    if e.dtype not in (F32, F64):
-        return red(e, axes, keep_dims)
-    m = red(where(isnan(e), _const_like(e, fill), e), axes, keep_dims)
-    n = count_nonnan(e, axes, keep_dims)
-    return where(n.eq(Scalar(np.uint64(0), U64)), _const_like(e, np.nan), m)
+    kind = _leaf_kind(e) or DeviceArray
+    out = _alloc_like(kind, (2,), e.dtype)
+    nd = len(e.shape)
+    # r[0] = std::min(r[0], v), r[1] = std::max(r[1], v) from {max(), lowest()}: std::min / std::max never take a NaN
+    # operand, i.e. the NaN-skipping extremes merged once with the init
+    npt = NP_OF[e.dtype]
+    lim = np.finfo(npt) if e.dtype in (F32, F64) else np.iinfo(npt if e.dtype != BOOL else np.uint8)
+    acc = NP_OF[regtype(e.dtype)]
+    for k, (op, init) in enumerate(((capi.RED_NANMIN, lim.max), (capi.RED_NANMAX, lim.min))):
+        _run_reducer(Reducer(op, e, list(range(nd)), initial=acc(init)), kind, out=out[k])
+    return out
 
 
-def nanmin(e, axes=None, keep_dims=False): return _nan_extreme(amin, np.inf, e, axes, keep_dims)
-def nanmax(e, axes=None, keep_dims=False): return _nan_extreme(amax, -np.inf, e, axes, keep_dims)
+def _arg(op, e, axis):
+    """xt::argmin / xt::argmax (misc/xsort.hpp:1237-1295): eval(e), then the first extreme along `axis` (or of the
+    flattened row-major traversal); result std::size_t."""
+    a = evaluate(as_expr(e))
+    kind = type(a)
+    if axis is None:
+        if a.strides != compute_strides(a.shape):
+            a = assign(_alloc_like(kind, a.shape, a.dtype), a)      # eval() of a strided view is a dense copy
+        out = _alloc_like(kind, (), U64)
+        ax = -1
+    else:
+        nd = len(a.shape)
+        ax = axis + nd if axis < 0 else axis
+        if not 0 <= ax < nd:
+            raise RuntimeError(f"Axis {axis} out of bounds")
+        out = _alloc_like(kind, tuple(s for d, s in enumerate(a.shape) if d != ax), U64)
+    be, pre = _backend_for(kind)
+    iop, oop = a.operand(), out.operand()
+    _check(kind, getattr(be, pre + "argreduce")(op, C.byref(iop), ax, C.byref(oop)))
+    return out
+
+
+def argmin(e, axis=None): return _arg(capi.RED_MIN, e, axis)
+def argmax(e, axis=None): return _arg(capi.RED_MAX, e, axis)
 
 
 def nanmean(e, axes=None, dtype=None, keep_dims=False):
@@ -940,6 +979,70 @@ def nanvar(e, axes=None, dtype=None):
 
 def nanstd(e, axes=None, dtype=None):
     return sqrt(nanvar(e, axes, dtype))
+
+
+# ---- norms (reducers/xnorm.hpp:369-620) ---------------------------------------------------------------
+# reducers  r + g(v)  (merge std::plus) or  std::max(r, |v|)  (merge math::maximum) from 0, with
+#   l0: g = (v != 0), result unsigned long long        l1: g = std::abs(v), result big_promote_type_t<V>
+#   sq: g = v * v (in V's promoted type), same result   linf: result decltype(std::abs(v)) (V itself when unsigned)
+#   lp_to_p: g = pow(rt(|v|), rt(p)), rt = real_promote_type_t<V>, result norm_type_t = double
+#   l2 = sqrt(sq), lp = pow(lp_to_p, 1 / p)
+def _big_promote(dt: int) -> int:
+    if dt in (F32, F64):
+        return F64
+    return U64 if dt in (BOOL, U8, U16, U32, U64) else I64
+
+
+def _is_unsigned(dt: int) -> bool:
+    return dt in (BOOL, U8, U16, U32, U64)
+
+
+def _abs_v(e: Expr) -> Expr:
+    return e if _is_unsigned(e.dtype) else abs(e)
+
+
+def norm_l0(e, axes=None, keep_dims=False):
+    e = as_expr(e)
+    return sum(cast(e.ne(_const_like(e, 0)), U64), axes, keep_dims)
+
+
+def norm_l1(e, axes=None, keep_dims=False):
+    e = as_expr(e)
+    return sum(cast(_abs_v(e), _big_promote(e.dtype)), axes, keep_dims)
+
+
+def norm_sq(e, axes=None, keep_dims=False):
+    e = as_expr(e)
+    return sum(cast(e * e, _big_promote(e.dtype)), axes, keep_dims)
+
+
+def norm_l2(e, axes=None, keep_dims=False):
+    return sqrt(norm_sq(e, axes, keep_dims))
+
+
+def norm_linf(e, axes=None, keep_dims=False):
+    """std::max<result_type>(r, std::abs(v)) never takes a NaN operand: the NaN-skipping maximum, merged once with
+    the reducer's own init 0."""
+    e = as_expr(e)
+    a = _abs_v(e)
+    return Reducer(capi.RED_NANMAX, a, axes, keep_dims, initial=NP_OF[regtype(a.dtype)](0))
+
+
+def norm_lp_to_p(e, p, axes=None, keep_dims=False):
+    e = as_expr(e)
+    if p == 0:
+        return sum(cast(e.ne(_const_like(e, 0)), F64), axes, keep_dims)
+    rt = e.dtype if e.dtype in (F32, F64) else F64
+    a = _abs_v(e)
+    a = a if a.dtype == rt else cast(a, rt)
+    g = pow(a, Scalar(NP_OF[rt](p), rt))
+    return sum(g if rt == F64 else cast(g, F64), axes, keep_dims)
+
+
+def norm_lp(e, p, axes=None, keep_dims=False):
+    if p == 0:
+        raise ValueError("norm_lp(): p must be nonzero, use norm_l0() instead.")
+    return pow(norm_lp_to_p(e, p, axes, keep_dims), Scalar(np.float64(1.0 / p), F64))
 
 
 def _scan(op, e, axis, dtype, out=None):
