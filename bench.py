@@ -391,6 +391,17 @@ def run_ours(args):
                  "exchange": ("k_reduce_merge + NVLink peer-memory exchange (one kernel)" if p2p_on else "nccl allreduce") if world > 1 else None}
     step.close()
     del step
+    # ---- the same step and the same end-to-end loop through the DROP-IN C++ header (tests/cpp/bench_dropin.cpp) ----
+    cpp = run_cpp_dropin(args, total_rows, rank, world)
+    barrier()
+    if rank == 0 and cpp is not None and "e2e_value" in cpp:
+        # the headline end-to-end number is the one a C++ user of the drop-in gets; the ctypes loop stays beside it
+        e2e = dict(e2e, ctypes_value=e2e["value"], ctypes_ms_per_step=e2e["ms_per_step"], value=cpp["e2e_value"],
+                   ms_per_step=cpp["e2e_ms_per_step"], steps=cpp["e2e_steps"],
+                   how="tests/cpp/bench_dropin.cpp, one process per GPU: xtb::copy_to_device(a, pinned host a); m = mean<float>(a,{0}) / "
+                       "v = variance<float>(a,{0}) through xtb::dist::*_into; xt::noalias(out) = xt::exp(a - m); xtb::copy_to_host of "
+                       "out / mean / variance into pinned host memory; wall clock, max over ranks; bytes per step are per rank. "
+                       "ctypes_value = the same loop through the ctypes mirror in this process")
     if not args.no_extra and not args.quick and world == 1:
         extra = other_configs(lib, xt, capi, args)
 
@@ -401,6 +412,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": CONFIG,
             "pct_of_8TBs_per_gpu": round(100 * value / world / 8000.0, 2),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "checks": checks, "step": step_info,
+            "cpp_dropin": cpp,
         }
         if total_rows != ROWS:
             line["config"] = dict(CONFIG, rows=total_rows, note="development run on a reduced row count")
@@ -412,6 +424,30 @@ def run_ours(args):
         dist.barrier()
         lib.xtb_comm_destroy()
         dist.destroy_process_group()
+
+
+def run_cpp_dropin(args, total_rows, rank, world):
+    """Run tests/cpp/_build/bench_dropin (the step written against include/xtb200/xtensor_b200.hpp) as this rank's
+    child: the children rendezvous among themselves (xtb::dist::init_from_env, MASTER_PORT + 29).  Rank 0's child
+    prints the JSON object that is returned; None when the binary is absent (it is built where /root/reference is)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "bench_dropin")
+    if not os.path.exists(exe):
+        return {"error": "tests/cpp/_build/bench_dropin not built"} if rank == 0 else None
+    n_e2e = 1 if args.quick else max(2, min(args.steps, 5))
+    try:
+        r = subprocess.run([exe, str(total_rows), str(args.steps), str(max(args.warmup, 3)), str(n_e2e)],
+                           capture_output=True, text=True, timeout=900)
+    except Exception as ex:
+        return {"error": repr(ex)}
+    if rank != 0:
+        return None
+    for ln in r.stdout.splitlines():
+        if ln.startswith("{"):
+            try:
+                return json.loads(ln)
+            except Exception:
+                pass
+    return {"error": f"rc={r.returncode} {r.stdout[-300:]} {r.stderr[-300:]}"}
 
 
 def run_e2e(args, lib, xt, capi, step, rank, world, barrier, max_over_ranks, nbytes):

@@ -1966,6 +1966,38 @@ namespace xtb
         return h;
     }
 
+    // In-place copies between an existing host container (pinned memory makes them asynchronous on the device
+    // side) and an existing device container of the same size: no allocation, the shapes must already agree.
+    template <class D, class H>
+    inline void copy_to_device(D& dev, const H& host)
+    {
+        using T = typename D::value_type;
+        static_assert(std::is_same<T, typename H::value_type>::value, "xtb200: copy_to_device needs equal value types");
+        if (dev.size() != host.size())
+        {
+            XTENSOR_THROW(std::runtime_error, "xtb200: copy_to_device: sizes differ");
+        }
+        if (host.size())
+        {
+            check(xtb_memcpy(dev.data(), const_cast<T*>(host.data()), host.size() * sizeof(T), XTB_H2D));
+        }
+    }
+
+    template <class H, class D>
+    inline void copy_to_host(H& host, const D& dev)
+    {
+        using T = typename D::value_type;
+        static_assert(std::is_same<T, typename H::value_type>::value, "xtb200: copy_to_host needs equal value types");
+        if (dev.size() != host.size())
+        {
+            XTENSOR_THROW(std::runtime_error, "xtb200: copy_to_host: sizes differ");
+        }
+        if (dev.size())
+        {
+            check(xtb_memcpy(host.data(), const_cast<T*>(dev.data()), dev.size() * sizeof(T), XTB_D2H));   // blocks
+        }
+    }
+
     // Evaluate any device expression into a new device container and bring it to the host.
     template <class E, std::enable_if_t<!xt::detail::is_container<E>::value, int> = 0>
     inline auto to_host(const xt::xexpression<E>& e)
@@ -2267,11 +2299,11 @@ namespace xtb
         // mean over `axes` (which include the sharded axis 0) of a row-sharded expression: merged sum divided by
         // the GLOBAL count, the division being the epilogue of the merge (mean_functor::finalize,
         // xblockwise_reducer_functors.hpp:175-185).  T as in xt::mean<T>.
-        template <class T = void, class E, class X>
-        inline auto mean(const xt::xexpression<E>& local, const X& axes, std::size_t global_rows)
+        template <class T = void, class OUT, class E, class X>
+        inline void mean_into(OUT& out, const xt::xexpression<E>& local, const X& axes, std::size_t global_rows)
         {
             const E& e = local.derived_cast();
-            using value_type = std::conditional_t<std::is_same<T, void>::value, double, T>;
+            using value_type = typename OUT::value_type;
             std::vector<std::size_t> ax(std::begin(axes), std::end(axes));
             auto red = xt::sum<T>(e, ax);
             double count = 1;
@@ -2284,29 +2316,49 @@ namespace xtb
             fin.type = dtype_v<value_type>;
             const value_type div = static_cast<value_type>(count);
             std::memcpy(&fin.imm, &div, sizeof(div));
-            xtb::xarray<value_type> out;
-            std::vector<std::size_t> shp(red.shape().begin(), red.shape().end());
-            out.resize(shp);
+            if (!std::equal(red.shape().begin(), red.shape().end(), out.shape().begin(), out.shape().end()))
+            {
+                std::vector<std::size_t> shp(red.shape().begin(), red.shape().end());
+                out.resize(shp);
+            }
             const bool crosses = std::find(ax.begin(), ax.end(), std::size_t(0)) != ax.end();
             lower::run_reducer(red, out, crosses, &fin);
+        }
+
+        template <class T = void, class E, class X>
+        inline auto mean(const xt::xexpression<E>& local, const X& axes, std::size_t global_rows)
+        {
+            using value_type = std::conditional_t<std::is_same<T, void>::value, double, T>;
+            xtb::xarray<value_type> out;
+            mean_into<T>(out, local, axes, global_rows);
             return out;
         }
 
         // two-pass variance (core/xmath.hpp:2082-2105) of a row-sharded expression: the merged mean is broadcast
-        // back (every rank holds it), then mean(square(local - mean)) with a second merge
-        template <class T = void, class E, class X>
-        inline auto variance(const xt::xexpression<E>& local, const X& axes, std::size_t global_rows)
+        // back (every rank holds it), then mean(square(local - mean)) with a second merge.  `m` = the merged mean
+        // over the same axes (dist::mean), kept by the caller for re-use (cfg5 needs it for exp(a - m) as well).
+        template <class T = void, class OUT, class E, class M, class X>
+        inline void variance_into(OUT& out, const xt::xexpression<E>& local, const M& m, const X& axes, std::size_t global_rows)
         {
             const E& e = local.derived_cast();
-            using value_type = std::conditional_t<std::is_same<T, void>::value, double, T>;
-            auto m = mean<T>(e, axes, global_rows);
+            using value_type = typename OUT::value_type;
             std::vector<std::size_t> keep(e.shape().begin(), e.shape().end());
             for (auto a : axes)
             {
                 keep[static_cast<std::size_t>(a)] = 1;
             }
             auto mrv = xt::reshape_view(m, keep);
-            return mean<value_type>(xt::square(xt::cast<value_type>(e) - mrv), axes, global_rows);
+            mean_into<value_type>(out, xt::square(e - mrv), axes, global_rows);   // as the reference: no cast (xmath.hpp:2102)
+        }
+
+        template <class T = void, class E, class X>
+        inline auto variance(const xt::xexpression<E>& local, const X& axes, std::size_t global_rows)
+        {
+            using value_type = std::conditional_t<std::is_same<T, void>::value, double, T>;
+            auto m = mean<T>(local, axes, global_rows);
+            xtb::xarray<value_type> out;
+            variance_into<T>(out, local, m, axes, global_rows);
+            return out;
         }
     }
 }
