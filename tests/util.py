@@ -55,3 +55,25 @@ def interpreter_only():
 def last_kernel():
     from xtensor_b200 import capi
     return capi.lib().xtb_last_kernel().decode()
+
+
+# ---- documented transcendental deviations ------------------------------------------------------------
+# The parity contract is <= 2 ulp against xtensor's CPU evaluation, which calls glibc's libm.  Five functor x dtype
+# pairs cannot meet it for a reason that is not the device's accuracy: glibc 2.39's own results are 3-5 ulp from
+# the correctly rounded value there (fp32 erfcf / tgammaf: the device evaluates in fp64 and rounds once, i.e. it is
+# within 1 ulp of the TRUE value; fp64 erfc / tgamma / lgamma: both libraries are a few ulp from the true value).
+# Matching them would mean reproducing glibc's rounding errors operation for operation, as was done for fp64
+# cbrt / expm1 / tanh (xtb_ops.cuh: glibc_cbrt / glibc_expm1 / glibc_tanh, now 0 ulp).  Recorded in DESIGN.md
+# section 5 and BASELINE.md; tests/test_gpu_assign.py::test_documented_ulp_deviations measures, for each pair, the
+# device's and glibc's distance from the true value (mpmath) and holds the device to the reference's own accuracy.
+ULP_DEVIATIONS = {("erfc", "f32"): 3, ("tgamma", "f32"): 5, ("erfc", "f64"): 5, ("tgamma", "f64"): 6, ("lgamma", "f64"): 4}
+# fp64 functors that restate glibc's algorithm: bit-identical
+ULP_EXACT_FP64 = {"cbrt", "expm1", "tanh"}
+
+
+def ulp_bar(name: str, tag: str, exact=()) -> int:
+    if name in exact:
+        return 0
+    if tag == "f64" and name in ULP_EXACT_FP64:
+        return 0
+    return ULP_DEVIATIONS.get((name, tag), 2)

@@ -1,7 +1,7 @@
 // xtb_static_i32.cu -- compile-time instantiations of the i32 expression
 // programs listed in xtb_static_programs.cuh (fully unrolled elementwise kernels).
 #include <utility>
-#include "xtb_ew.cuh"
+#include "xtb_ew_tma.cuh"
 
 namespace xtb {
 namespace {
@@ -22,6 +22,10 @@ template <int ID> int launch_one(const EwParams& p, DeviceCtx* ctx) {
 }
 
 template <int ID> int launch_tile_one(const EwParams& p, DeviceCtx* ctx) {
+    // every operand through TMA when the expression is regular (rank 2, aligned, one element size); else the
+    // register-staged tile kernel
+    const int r = launch_ew_tile_tma<StaticEval<Tbl, ID>, Slot>(p, ctx, kNames[ID]);
+    if (r != 1) return r;
     return launch_ew_tile<StaticEval<Tbl, ID>, Slot>(p, ctx, kNames[ID]);
 }
 
