@@ -13,8 +13,8 @@ lib = capi.lib()
 capi.check(lib.xtb_init(0))
 
 
-def timed(fn, iters=10):
-    for _ in range(3):
+def timed(fn, iters=int(os.environ.get("ITERS", "10"))):
+    for _ in range(int(os.environ.get("WARM", "3"))):
         fn()
     e0, e1 = C.c_void_p(), C.c_void_p()
     capi.check(lib.xtb_event_create(C.byref(e0)))
