@@ -257,10 +257,18 @@ int xtb_comm_p2p_attach(const void* handles, int world) {
 }
 
 int xtb_comm_destroy(void) {
+    // Every rank must have finished its last exchange before any rank frees its window (peers push into it):
+    // callers destroy collectively, after a barrier of their own or -- as here, when NCCL is up -- after one
+    // last collective on the communicator that is about to go away.
     if (g_p2p.local) {
+        DeviceCtx* ctx = nullptr;
+        if (g_nccl.comm && g_nccl.world > 1 && get_ctx(&ctx) == XTB_OK) {
+            g_nccl.all_reduce(g_p2p.local, g_p2p.local, 1, nccl_dtype(XTB_I32), 0, g_nccl.comm, ctx->stream);   // barrier
+        }
         cudaDeviceSynchronize();
-        for (int r = 0; r < g_nccl.world; ++r)
-            if (g_p2p.ready && r != g_nccl.rank && g_p2p.peer[r]) cudaIpcCloseMemHandle(g_p2p.peer[r]);
+        // mappings opened by an attach stay open across a detach (ready == false): close whatever is mapped
+        for (int r = 0; r < kP2pMaxWorld; ++r)
+            if (r != g_nccl.rank && g_p2p.peer[r] && g_p2p.peer[r] != g_p2p.local) cudaIpcCloseMemHandle(g_p2p.peer[r]);
         cudaFree(g_p2p.local);
         g_p2p = P2p();
     }
