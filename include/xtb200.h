@@ -117,6 +117,10 @@ typedef enum {
     XTB_OP_SIGN = 40,      /* math::sign_fun xmath.hpp:826-866 */
     XTB_OP_DEG2RAD = 41, XTB_OP_RAD2DEG = 42,                      /* xmath.hpp:619-672 */
     XTB_OP_SQUARE = 43, XTB_OP_CUBE = 44,                          /* xmath.hpp:1100-1127 */
+    /* order key of a 32-bit value (type = F32 / I32 / U32) in the HIGH half of a u64: a monotone map of x (arg = 0) or
+       of -x (arg = 1), -0.0 == +0.0, NaN -> 0xffffffff (never the minimum).  OR-ed with an index in the low half, a
+       MIN reduction over such keys is argmin / argmax with the first index winning ties (xtb_argreduce) */
+    XTB_OP_ORDKEY = 45,
     /* binary, xoperation.hpp:106-125 */
     XTB_OP_ADD = 64, XTB_OP_SUB = 65, XTB_OP_MUL = 66, XTB_OP_DIV = 67, XTB_OP_MOD = 68,
     XTB_OP_LOR = 69, XTB_OP_LAND = 70, XTB_OP_BOR = 71, XTB_OP_BAND = 72, XTB_OP_BXOR = 73,
@@ -302,7 +306,7 @@ int  xtb_allreduce(void* buf, size_t count, int dtype, int op);
 /* ---- process options ------------------------------------------------------- */
 /* The XTB_* environment switches are read once, at first use; afterwards they are changed through this call
  * (name = the variable without the XTB_ prefix, lower case: "no_static", "no_jit", "no_staged", "no_tma",
- * "jit_min_elems", "jit_verbose", "scan_variant", "tile_variant").  xtb_get_option returns -1 for unknown names. */
+ * "jit_min_elems", "jit_verbose", "scan_variant", "tile_variant", "arg_two_pass").  xtb_get_option returns -1 for unknown names. */
 int  xtb_set_option(const char* name, long long value);
 long long xtb_get_option(const char* name);
 

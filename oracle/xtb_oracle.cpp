@@ -231,6 +231,26 @@ template <class T> Val unary_int(int op, T x) {
 
 Val unary(int op, const Val& a, int arg) {
     if (op == XTB_OP_CAST) return cast_to(a, arg);
+    if (op == XTB_OP_ORDKEY) {      // see xtb200.h: order key of a 32-bit value in the high half of a u64
+        uint32_t k;
+        if (a.t == XTB_F32) {
+            if (a.f32 != a.f32) k = 0xffffffffu;
+            else {
+                const float z = a.f32 + 0.0f;
+                uint32_t b;
+                std::memcpy(&b, &z, 4);
+                k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                if (arg) k = ~k;
+            }
+        } else if (a.t == XTB_I32) {
+            k = (uint32_t) a.i32 ^ 0x80000000u;
+            if (arg) k = ~k;
+        } else {
+            k = a.u32;
+            if (arg) k = ~k;
+        }
+        return mk((uint64_t) k << 32);
+    }
     return visit(a, [op](auto x) -> Val {
         using T = decltype(x);
         if constexpr (std::is_floating_point<T>::value) return unary_float<T>(op, x);

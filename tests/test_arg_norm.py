@@ -156,6 +156,34 @@ def test_gpu_arg_large(xt, D, shape, axis, dt):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("key", ["i8", "u8", "i16", "i32", "f32", "f32_nan"])
+def test_gpu_arg_both_formulations(xt, D, gpu, key):
+    """<= 32-bit element types take the one-pass packed-key reduction; the two-pass formulation (what 64-bit types use)
+    must give the same indices."""
+    gpu.xtb_set_option(b"arg_two_pass", 1)
+    try:
+        _check_arg(xt, D, key)
+    finally:
+        gpu.xtb_set_option(b"arg_two_pass", 0)
+
+
+@pytest.mark.gpu
+def test_gpu_arg_nan_large(xt, D):
+    """NaN rules at sizes that split: a NaN in front of a lane pins index 0, other NaNs never win, all-NaN lanes give 0."""
+    rng = np.random.default_rng(8)
+    a = rng.integers(-50, 50, (3000, 700)).astype(np.float32)
+    a[rng.random(a.shape) < 0.2] = np.nan
+    a[0, ::3] = np.nan
+    a[:, 5] = np.nan
+    da = D(a)
+    for is_min, f in ((True, xt.argmin), (False, xt.argmax)):
+        want0 = np.array([_seq_arg(a[:, j], is_min) for j in range(a.shape[1])], np.uint64)
+        assert np.array_equal(f(da, 0).numpy(), want0)
+        want1 = np.array([_seq_arg(a[i, :], is_min) for i in range(0, a.shape[0], 7)], np.uint64)
+        assert np.array_equal(f(da, 1).numpy()[::7], want1)
+
+
+@pytest.mark.gpu
 def test_gpu_nanmin_large(xt, D):
     """nan_min / nan_max as native merges through the split + merge kernels (outer) and the warp / block kernels (inner)."""
     rng = np.random.default_rng(6)

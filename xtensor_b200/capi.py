@@ -24,7 +24,7 @@ OPCODES = dict(
     LOG1P=12, SQRT=13, CBRT=14, SIN=15, COS=16, TAN=17, ASIN=18, ACOS=19, ATAN=20, SINH=21, COSH=22,
     TANH=23, ASINH=24, ACOSH=25, ATANH=26, ERF=27, ERFC=28, TGAMMA=29, LGAMMA=30, CEIL=31, FLOOR=32,
     TRUNC=33, ROUND=34, NEARBYINT=35, RINT=36, ISFINITE=37, ISINF=38, ISNAN=39, SIGN=40, DEG2RAD=41,
-    RAD2DEG=42, SQUARE=43, CUBE=44,
+    RAD2DEG=42, SQUARE=43, CUBE=44, ORDKEY=45,
     ADD=64, SUB=65, MUL=66, DIV=67, MOD=68, LOR=69, LAND=70, BOR=71, BAND=72, BXOR=73, SHL=74, SHR=75,
     LT=76, LE=77, GT=78, GE=79, EQ=80, NE=81, FMOD=82, REMAINDER=83, FMAX=84, FMIN=85, FDIM=86, POW=87,
     HYPOT=88, ATAN2=89, MAXIMUM=90, MINIMUM=91, NANMIN=92, NANMAX=93,

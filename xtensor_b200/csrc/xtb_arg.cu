@@ -7,11 +7,15 @@
 //   * ties keep the FIRST index;
 //   * a NaN never replaces the running value (cmp is false), and if x[0] is NaN nothing ever replaces it:
 //     the result is 0 when x[0] is NaN, otherwise the first extreme among the non-NaN elements.
-// Device formulation (order independent, so it runs on the split / merged reduction kernels):
-//     m   = nan_min / nan_max over the axis            (the extreme of the non-NaN elements; keep_dims)
-//     idx = min over the axis of  ((x == m) || (isnan(x) && i == 0)) ? i : SIZE_MAX
-// two fused map-reduce launches of xtb_reduce (xtb_reduce.cuh); `i` is a small index vector broadcast
-// along the other dims.
+// Device formulations (order independent, so they run on the split / merged reduction kernels of xtb_reduce.cuh;
+// `i` is a small index vector broadcast along the other dims):
+//   * element types of <= 32 bits, ONE pass: a MIN reduction over packed 64-bit keys
+//         key = (isnan(x) && i == 0) ? 0 : (ordkey(x) << 32 | i)
+//     where ordkey is a monotone 32-bit image of x (of -x for argmax; -0.0 == +0.0; NaN -> 0xffffffff, XTB_OP_ORDKEY):
+//     the smallest key is the extreme value with the smallest index; the index is the key's low half;
+//   * 64-bit element types, two passes:
+//         m   = nan_min / nan_max over the axis            (the extreme of the non-NaN elements; keep_dims)
+//         idx = min over the axis of  ((x == m) || (isnan(x) && i == 0)) ? i : SIZE_MAX
 #include <vector>
 #include "xtb_common.hpp"
 
@@ -111,6 +115,38 @@ extern "C" int xtb_argreduce(int op, const xtb_operand* in, int axis, const xtb_
     for (int d = 0; d < nd; ++d) shape[d] = x.shape[d];
     const int32_t ax = axis;
 
+    const bool fp = rt == XTB_F32 || rt == XTB_F64;
+    xtb_operand o = *out;
+    o.dtype = XTB_U64;   // i64 storage holds the same bits for every valid index
+    if (rsz == 4 && n < (1ll << 32) && !options().arg_two_pass) {
+        // ---- one pass: MIN over packed (order key, index) ----
+        xtb_program pk{};
+        xtb_operand leaves[2] = {x, iota};
+        pk.n_leaves = 2;
+        pk.n_imms = 1;
+        pk.imms[0] = 0;
+        if (fp) {
+            emit(pk, XTB_OP_PUSH, x.dtype, XTB_SRC_LEAF, 0);
+            emit(pk, XTB_OP_ISNAN, rt);                                 // isnan(x)
+            emit(pk, XTB_OP_PUSH, XTB_U64, XTB_SRC_LEAF, 1);
+            emit(pk, XTB_OP_EQ, XTB_U64, XTB_SRC_IMM, 0);               // i == 0
+            emit(pk, XTB_OP_LAND, XTB_I32, XTB_SRC_STACK, 0);           // a NaN in front is never replaced: the best key
+            emit(pk, XTB_OP_PUSH, XTB_U64, XTB_SRC_IMM, 0);
+        }
+        emit(pk, XTB_OP_PUSH, x.dtype, XTB_SRC_LEAF, 0);
+        emit(pk, XTB_OP_ORDKEY, rt, 0, op == XTB_RED_MAX ? 1 : 0);
+        emit(pk, XTB_OP_BOR, XTB_U64, XTB_SRC_LEAF, 1);                 // | i
+        if (fp) emit(pk, XTB_OP_WHERE, XTB_U64);
+        XTB_TRY(xtb_reduce(XTB_RED_MIN, XTB_U64, &pk, leaves, nd, shape, 1, &ax, 0, nullptr, &o, 0));
+        // the index is the low half of the winning key
+        xtb_program pd{};
+        pd.n_leaves = 1;
+        pd.n_imms = 1;
+        pd.imms[0] = 0xffffffffull;
+        emit(pd, XTB_OP_PUSH, XTB_U64, XTB_SRC_LEAF, 0);
+        emit(pd, XTB_OP_BAND, XTB_U64, XTB_SRC_IMM, 0);
+        return xtb_assign(&pd, &o, &o);
+    }
     // pass 1: m = nan_min / nan_max(x) along the axis
     {
         xtb_program p1{};
@@ -120,7 +156,6 @@ extern "C" int xtb_argreduce(int op, const xtb_operand* in, int axis, const xtb_
     }
     // pass 2: first index whose element equals m (or index 0 when x[0] is NaN)
     {
-        const bool fp = rt == XTB_F32 || rt == XTB_F64;
         xtb_program p2{};
         xtb_operand leaves[3] = {x, m, iota};
         p2.n_leaves = 3;
@@ -140,8 +175,6 @@ extern "C" int xtb_argreduce(int op, const xtb_operand* in, int axis, const xtb_
         emit(p2, XTB_OP_PUSH, XTB_U64, XTB_SRC_LEAF, 2);
         emit(p2, XTB_OP_PUSH, XTB_U64, XTB_SRC_IMM, 0);
         emit(p2, XTB_OP_WHERE, XTB_U64);
-        xtb_operand o = *out;
-        o.dtype = XTB_U64;   // i64 storage holds the same bits for every valid index
         XTB_TRY(xtb_reduce(XTB_RED_MIN, XTB_U64, &p2, leaves, nd, shape, 1, &ax, 0, nullptr, &o, 0));
     }
     return XTB_OK;

@@ -62,6 +62,7 @@ struct Options {
     int scan_variant = 0;     // XTB_SCAN_VARIANT: development switch of xtb_scan
     int scan_nv = 0;          // XTB_SCAN_NV: 128-bit vectors per thread of k_scan_ahead (4 or 8)
     int tile_variant = 0;     // XTB_TILE_VARIANT: development switch of the transposed-leaf kernel
+    int arg_two_pass = 0;     // XTB_ARG_TWO_PASS: argmin / argmax of 32-bit types through the two-pass formulation (tests)
 };
 Options& options();
 

@@ -56,6 +56,7 @@ Options& options() {
         if (const char* e = getenv("XTB_SCAN_VARIANT")) g_options.scan_variant = atoi(e);
         if (const char* e = getenv("XTB_TILE_VARIANT")) g_options.tile_variant = atoi(e);
         if (const char* e = getenv("XTB_SCAN_NV")) g_options.scan_nv = atoi(e);
+        if (const char* e = getenv("XTB_ARG_TWO_PASS")) g_options.arg_two_pass = atoi(e);
     });
     return g_options;
 }
@@ -267,7 +268,7 @@ int validate_program(const xtb_program* p, const int32_t* leaf_dtypes, int* resu
         if (!is_reg_type(in.type)) XTB_FAIL(XTB_ERR_INVALID, "insn %d: type %d is not a register type", pc, in.type);
         w64 |= is64(in.type);
         if (op < XTB_OP_ADD) {  // unary
-            if (op < XTB_OP_CAST || op > XTB_OP_CUBE) XTB_FAIL(XTB_ERR_INVALID, "insn %d: unknown opcode %d", pc, op);
+            if (op < XTB_OP_CAST || op > XTB_OP_ORDKEY) XTB_FAIL(XTB_ERR_INVALID, "insn %d: unknown opcode %d", pc, op);
             if (n < 1) XTB_FAIL(XTB_ERR_INVALID, "insn %d: stack underflow", pc);
             if (st[n - 1] != in.type)
                 XTB_FAIL(XTB_ERR_INVALID, "insn %d: operand has type %d, insn says %d", pc, st[n - 1], in.type);
@@ -275,6 +276,11 @@ int validate_program(const xtb_program* p, const int32_t* leaf_dtypes, int* resu
                 if (in.arg >= XTB_DTYPE_COUNT) XTB_FAIL(XTB_ERR_INVALID, "insn %d: bad cast target", pc);
                 st[n - 1] = regtype_of(in.arg);
                 w64 |= is64(st[n - 1]);
+            } else if (op == XTB_OP_ORDKEY) {
+                if (in.type != XTB_F32 && in.type != XTB_I32 && in.type != XTB_U32) XTB_FAIL(XTB_ERR_INVALID, "insn %d: ORDKEY takes a 32-bit value", pc);
+                if (in.arg > 1) XTB_FAIL(XTB_ERR_INVALID, "insn %d: ORDKEY arg is 0 (min) or 1 (max)", pc);
+                st[n - 1] = XTB_U64;
+                w64 = true;
             } else if (is_pred_op(op)) {
                 st[n - 1] = XTB_I32;
             } else {
@@ -572,6 +578,7 @@ int xtb_set_option(const char* name, long long value) {
     else if (!strcmp(name, "scan_variant")) o.scan_variant = (int) value;
     else if (!strcmp(name, "tile_variant")) o.tile_variant = (int) value;
     else if (!strcmp(name, "scan_nv")) o.scan_nv = (int) value;
+    else if (!strcmp(name, "arg_two_pass")) o.arg_two_pass = (int) value;
     else XTB_FAIL(XTB_ERR_INVALID, "unknown option '%s'", name);
     return XTB_OK;
 }
@@ -588,6 +595,7 @@ long long xtb_get_option(const char* name) {
     if (!strcmp(name, "scan_variant")) return o.scan_variant;
     if (!strcmp(name, "tile_variant")) return o.tile_variant;
     if (!strcmp(name, "scan_nv")) return o.scan_nv;
+    if (!strcmp(name, "arg_two_pass")) return o.arg_two_pass;
     return -1;
 }
 

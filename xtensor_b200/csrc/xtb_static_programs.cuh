@@ -49,6 +49,7 @@ constexpr int result_type(const SP& p) {
         if (in.op == XTB_OP_PUSH) st[n++] = (in.src == XTB_SRC_LEAF) ? regtype_of(in.type) : in.type;
         else if (in.op < XTB_OP_ADD) {
             if (in.op == XTB_OP_CAST) st[n - 1] = regtype_of(in.arg);
+            else if (in.op == XTB_OP_ORDKEY) st[n - 1] = XTB_U64;
             else if (is_pred_op(in.op)) st[n - 1] = XTB_I32;
         } else if (in.op < XTB_OP_WHERE) {
             if ((in.src & 3) == XTB_SRC_STACK) --n;
