@@ -603,11 +603,20 @@ def other_configs(lib, xt, capi, args):
         # cfg3: fp32 (4096,4096,16) sum / amax over axis 0 and axis 2
         x = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (4096, 4096, 16)).astype(np.float32))
         nb = 4096 * 4096 * 16 * 4
-        out["cfg3_sum_axis0"] = timed(lambda: xt.evaluate(xt.sum(x, [0])), nb + 4096 * 16 * 4)
-        out["cfg3_amax_axis0"] = timed(lambda: xt.evaluate(xt.amax(x, [0])), nb + 4096 * 16 * 4)
-        out["cfg3_sum_axis2"] = timed(lambda: xt.evaluate(xt.sum(x, [2])), nb + 4096 * 4096 * 4)
-        out["cfg3_amax_axis2"] = timed(lambda: xt.evaluate(xt.amax(x, [2])), nb + 4096 * 4096 * 4)
-        out["cfg3_mean_axis0_fused_finalize"] = timed(lambda: xt.evaluate(xt.mean(x, [0], dtype=xt.F32)), nb + 4096 * 16 * 4)
+        o0, o2 = xt.DeviceArray.empty((4096, 16), xt.F32), xt.DeviceArray.empty((4096, 4096), xt.F32)
+        red = lambda r, o: xt._run_reducer(r, xt.DeviceArray, out=o)           # into an existing container, like cfg1 / 2 / 4
+        out["cfg3_sum_axis0"] = timed(lambda: red(xt.sum(x, [0]), o0), nb + 4096 * 16 * 4)
+        out["cfg3_amax_axis0"] = timed(lambda: red(xt.amax(x, [0]), o0), nb + 4096 * 16 * 4)
+        out["cfg3_sum_axis2"] = timed(lambda: red(xt.sum(x, [2]), o2), nb + 4096 * 4096 * 4)
+        out["cfg3_amax_axis2"] = timed(lambda: red(xt.amax(x, [2]), o2), nb + 4096 * 4096 * 4)
+        out["cfg3_mean_axis0_fused_finalize"] = timed(lambda: xt.assign(o0, xt.mean(x, [0], dtype=xt.F32)), nb + 4096 * 16 * 4)
+        # index-carrying reduction (xt::argmax over the strided axis): ONE pass over packed (order key, index) keys
+        oi = xt.DeviceArray.empty((4096, 16), xt.U64)
+        def argmax0():
+            iop, oop = x.operand(), oi.operand()
+            capi.check(lib.xtb_argreduce(capi.RED_MAX, C.byref(iop), 0, C.byref(oop)))
+        out["cfg3_argmax_axis0"] = timed(argmax0, nb + 4096 * 16 * 8)
+        del o0, o2, oi
         del x
         # cfg4: fp64 (8192,8192) transpose(a) + view(b, range(0,_,2), all())
         a = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (8192, 8192)))

@@ -1,3 +1,7 @@
-timeout 300 python tools/scan_bench.py 67108864:None:float32 33554432 64x1048576:1 --variant=0 --variant=-1000 --variant=36 2>&1 | tail -30
-ITERS=1 WARM=1 timeout 600 ncu --set full --clock-control none -k regex:k_scan -f -o /tmp/r02_scan python tools/scan_bench.py 67108864:None:float32 > /dev/null 2>&1
-python tools/ncu_summary.py /tmp/r02_scan.ncu-rep 2>/dev/null | grep -E "^==|time_duration|dram__bytes|warps_active|long_scoreboard_per|barrier_per|short_score|issue_active.avg|wait_per|no_instr|branch" | head -14
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/r02_pytest_gpu_c.log
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_d.json 2> gpurun_out/r02_bench_n1_d.err
+python bench.py --impl reference --gpus 1 --steps 5 --warmup 3 > gpurun_out/r02_bench_ref_d.json 2> gpurun_out/r02_bench_ref_d.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke_d.log 2>&1
+python tools/scan_bench.py > gpurun_out/r02_scan_bench.log 2>&1
+tail -4 gpurun_out/r02_pytest_gpu_c.log; cut -c1-400 gpurun_out/r02_bench_n1_d.json; tail -3 gpurun_out/r02_bench_n1_d.err; tail -2 gpurun_out/r02_smoke_d.log; cat gpurun_out/r02_scan_bench.log | awk '{print $1,$2,$4,$6,$7}'

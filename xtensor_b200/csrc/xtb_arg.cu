@@ -50,6 +50,7 @@ extern "C" int xtb_argreduce(int op, const xtb_operand* in, int axis, const xtb_
     if (out->dtype != XTB_U64 && out->dtype != XTB_I64) XTB_FAIL(XTB_ERR_INVALID, "argreduce writes std::size_t (u64 / i64) indices");
     DeviceCtx* ctx;
     XTB_TRY(get_ctx(&ctx));
+    XTB_LAUNCH_LOCK(ctx);
 
     // iteration space: the operand's own shape, or -- flat -- its row-major traversal as one dim
     xtb_operand x = *in;

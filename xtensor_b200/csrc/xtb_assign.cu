@@ -278,6 +278,7 @@ extern "C" int xtb_assign(const xtb_program* prog, const xtb_operand* out, const
         if (s.shape[d] == 0) return XTB_OK;  // nothing to assign
     DeviceCtx* ctx;
     XTB_TRY(get_ctx(&ctx));
+    XTB_LAUNCH_LOCK(ctx);
 
     sort_space_by(&s, OUT);
     collapse_space(&s);

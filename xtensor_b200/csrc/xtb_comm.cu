@@ -13,6 +13,7 @@
 // pushed into its own window in rank order -- one kernel, one one-way NVLink trip, no fences, and
 // bit-identical results on all ranks.
 #include <dlfcn.h>
+#include <mutex>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
 #include "xtb_p2p.cuh"
@@ -38,7 +39,10 @@ struct Nccl {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
 };
+// One communicator per process (the model is one process per GPU).  Bring-up, attach and destroy change this state
+// and are serialised by g_comm_mutex; collectives read it and are stream ordered on the calling device.
 static Nccl g_nccl;
+static std::mutex g_comm_mutex;
 
 static int load_nccl() {
     if (g_nccl.handle) return XTB_OK;
@@ -189,6 +193,7 @@ using namespace xtb;
 extern "C" {
 
 int xtb_comm_unique_id(void* id128) {
+    std::lock_guard<std::mutex> comm_lock(g_comm_mutex);
     if (!id128) XTB_FAIL(XTB_ERR_INVALID, "null id");
     XTB_TRY(load_nccl());
     NcclUniqueId id;
@@ -198,6 +203,7 @@ int xtb_comm_unique_id(void* id128) {
 }
 
 int xtb_comm_init(int rank, int world, const void* id128) {
+    std::lock_guard<std::mutex> comm_lock(g_comm_mutex);
     if (world < 1 || rank < 0 || rank >= world) XTB_FAIL(XTB_ERR_INVALID, "bad rank %d / world %d", rank, world);
     if (g_nccl.comm) XTB_FAIL(XTB_ERR_INVALID, "communicator already initialised");
     DeviceCtx* ctx;
@@ -218,6 +224,7 @@ int xtb_comm_init(int rank, int world, const void* id128) {
 }
 
 int xtb_comm_p2p_handle(void* handle64) {
+    std::lock_guard<std::mutex> comm_lock(g_comm_mutex);
     if (!handle64) XTB_FAIL(XTB_ERR_INVALID, "null handle");
     DeviceCtx* ctx;
     XTB_TRY(get_ctx(&ctx));
@@ -233,6 +240,7 @@ int xtb_comm_p2p_handle(void* handle64) {
 }
 
 int xtb_comm_p2p_attach(const void* handles, int world) {
+    std::lock_guard<std::mutex> comm_lock(g_comm_mutex);
     if (!handles && world == 0) {   // detach: back to NCCL for every payload (all ranks must do the same)
         g_p2p.ready = false;
         return XTB_OK;
@@ -257,6 +265,7 @@ int xtb_comm_p2p_attach(const void* handles, int world) {
 }
 
 int xtb_comm_destroy(void) {
+    std::lock_guard<std::mutex> comm_lock(g_comm_mutex);
     // Every rank must have finished its last exchange before any rank frees its window (peers push into it):
     // callers destroy collectively, after a barrier of their own or -- as here, when NCCL is up -- after one
     // last collective on the communicator that is about to go away.

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "../../include/xtb200.h"
 
@@ -48,7 +49,14 @@ struct DeviceCtx {
     // the stream whose work last touched `scratch`: a call on another stream first waits for it
     cudaStream_t scratch_stream = nullptr;
     cudaEvent_t scratch_ev = nullptr;
+    // One compute call (xtb_assign / xtb_reduce / xtb_scan / xtb_argreduce) is a SEQUENCE of launches that share this
+    // context's scratch buffer; host threads working on the same device take turns per call (the launches themselves
+    // are asynchronous, so the lock is held for microseconds).  Recursive: xtb_argreduce calls xtb_reduce.
+    // Stream selection (xtb_set_stream), fork sections and graph capture remain per-device state: drive them from one
+    // thread at a time.
+    std::recursive_mutex launch_mutex;
 };
+#define XTB_LAUNCH_LOCK(ctx) std::lock_guard<std::recursive_mutex> launch_lock__((ctx)->launch_mutex)
 // ---- process options -----------------------------------------------------------
 // Read from the environment ONCE (first use) and changeable through xtb_set_option; the dispatchers never
 // call getenv.  Names are the environment variables without the XTB_ prefix, lower case.

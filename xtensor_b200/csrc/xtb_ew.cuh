@@ -689,11 +689,8 @@ static int launch_ew_staged(const EwParams& p, DeviceCtx* ctx) {
     const int64_t per_block = 256 * kStageItems;
     const unsigned grid = (unsigned) ((p.total_vec + per_block - 1) / per_block);
     const size_t smem = (size_t) std::max(p.n_leaves, 1) * kStageItems * 256 * sizeof(uint4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_ew_staged<S, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, XTB_MAX_LEAVES * kStageItems * 256 * (int) sizeof(uint4));
-        attr_set = true;
-    }
+    // per launch, not once per process: the attribute belongs to the current device's context
+    cudaFuncSetAttribute(k_ew_staged<S, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, XTB_MAX_LEAVES * kStageItems * 256 * (int) sizeof(uint4));
     char name[96];
     snprintf(name, sizeof(name), "k_ew_staged<interp,S%d,V%d>", (int) sizeof(S) * 8, V);
     k_ew_staged<S, V><<<grid, 256, smem, ctx->stream>>>(p);

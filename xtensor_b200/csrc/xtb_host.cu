@@ -8,6 +8,7 @@
 // their sum.  Operands that do not span the leading dimension (broadcast / lower rank) are
 // uploaded once.  Host buffers should be pinned (xtb_host_alloc) for the copies to be async.
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include "xtb_common.hpp"
 #include "xtb_ops.cuh"
@@ -20,7 +21,10 @@ struct HostPipe {
     cudaEvent_t in_done[kSlots] = {}, k_done[kSlots] = {}, out_done[kSlots] = {};
     bool ready = false;
 };
+// one pipeline (two copy streams + events) per device; a call holds the device's mutex from its first chunk to its
+// last, so two host threads assigning on the same device take turns instead of sharing streams and events
 static HostPipe g_pipe[16];
+static std::mutex g_pipe_mutex[16];
 
 static int pipe_for(DeviceCtx* ctx, HostPipe** pp) {
     HostPipe& p = g_pipe[ctx->device];
@@ -59,6 +63,8 @@ extern "C" int xtb_assign_host(const xtb_program* prog, const xtb_operand* out, 
         if (!dense_row_major(&leaves[k])) XTB_FAIL(XTB_ERR_UNSUPPORTED, "xtb_assign_host: leaf %d must be dense row-major", k);
     DeviceCtx* ctx;
     XTB_TRY(get_ctx(&ctx));
+    if (ctx->device < 0 || ctx->device >= 16) XTB_FAIL(XTB_ERR_UNSUPPORTED, "xtb_assign_host: device index %d", ctx->device);
+    std::lock_guard<std::mutex> pipe_lock(g_pipe_mutex[ctx->device]);
     HostPipe* pipe;
     XTB_TRY(pipe_for(ctx, &pipe));
     const int nd = out->ndim;

@@ -462,6 +462,7 @@ extern "C" int xtb_reduce_fin(int op, int acc_type, const xtb_program* prog, con
     if (K == 0) return XTB_OK;
     DeviceCtx* ctx;
     XTB_TRY(get_ctx(&ctx));
+    XTB_LAUNCH_LOCK(ctx);
     in.op = op;
     if (fin && fin->op != XTB_FIN_NONE) {
         in.fin_op = fin->op;

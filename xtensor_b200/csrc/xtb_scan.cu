@@ -505,16 +505,16 @@ template <class T> XTB_DEV T slot_wait(const char* slots, uint32_t i) {
     return v;
 }
 
-template <class T, int NV, int OP>
-__global__ void __launch_bounds__(kScanThreads, NV <= 4 ? 5 : 3) k_scan_ahead(const __grid_constant__ ScanParams p, const __grid_constant__ LbTree tr) {
+template <class T, int NV, int OP, int TH>
+__global__ void __launch_bounds__(TH, (NV <= 4 ? 5 : 3) * (256 / TH)) k_scan_ahead(const __grid_constant__ ScanParams p, const __grid_constant__ LbTree tr) {
     constexpr int VEC = 16 / (int) sizeof(T);
     constexpr int WARP_ELEMS = 32 * NV * VEC;
-    constexpr int TILE = kScanThreads * NV * VEC;
+    constexpr int TILE = TH * NV * VEC;
     constexpr T ident = sident<OP, T>();
     __shared__ __align__(128) T s_tile[TILE];              // the reduce-visit tile lands here (bulk copy: no registers in flight)
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ T s_red[kScanWarpsPerTile];
-    __shared__ T s_warp[kScanWarpsPerTile];
+    __shared__ T s_red[(TH / 32)];
+    __shared__ T s_warp[(TH / 32)];
     __shared__ T s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t k = blockIdx.x;
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kScanThreads, NV <= 4 ? 5 : 3) k_scan_ahead(co
         load_tile(row_ptr(jrow), jtrow, x);
     }
     // ---- (3) tree maintenance for tile m = k - D / 2: everything it reads was published D / 2 tiles ago ----
-    if (warp == kScanWarpsPerTile - 1 && k >= tr.ahead / 2 && k - tr.ahead / 2 < p.total_tiles) {
+    if (warp == (TH / 32) - 1 && k >= tr.ahead / 2 && k - tr.ahead / 2 < p.total_tiles) {
         uint32_t row, trow;
         tile_pos(k - tr.ahead / 2, row, trow);
         if ((trow + 1) % kLbFan == 0) {                    // (most tiles stop here)
@@ -674,9 +674,9 @@ __global__ void __launch_bounds__(kScanThreads, NV <= 4 ? 5 : 3) k_scan_ahead(co
     __syncthreads();                                       // s_warp, s_prefix; also: the mbarrier is initialised
     if (do_scan) {
         // ---- (2c) offsets of the warps, apply, store (striped): leaves before tile k has even arrived ----
-        T wv = lane < kScanWarpsPerTile ? s_warp[lane] : ident;
+        T wv = lane < (TH / 32) ? s_warp[lane] : ident;
 #pragma unroll
-        for (int d = 1; d < kScanWarpsPerTile; d <<= 1) {
+        for (int d = 1; d < (TH / 32); d <<= 1) {
             const T y = shfl_up_t<T>(wv, d);
             if (lane >= d) wv = sop<OP, T>(y, wv);
         }
@@ -740,9 +740,9 @@ __global__ void __launch_bounds__(kScanThreads, NV <= 4 ? 5 : 3) k_scan_ahead(co
     if (lane == 0) s_red[warp] = t;
     __syncthreads();
     if (warp == 0) {
-        T v = lane < kScanWarpsPerTile ? s_red[lane] : ident;
+        T v = lane < (TH / 32) ? s_red[lane] : ident;
 #pragma unroll
-        for (int mk = 1; mk < kScanWarpsPerTile; mk <<= 1) v = sop<OP, T>(v, shfl_xor_t<T>(v, mk));
+        for (int mk = 1; mk < (TH / 32); mk <<= 1) v = sop<OP, T>(v, shfl_xor_t<T>(v, mk));
         if (lane == 0 && ktrow + 1 < p.tiles_per_row) slot_publish<T>(tr.slots, tr.level_off[0] + krow * tr.units[0] + ktrow, v);
     }
 }
@@ -1554,17 +1554,17 @@ __global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ Sc
 }
 
 // rows longer than one staged tile: reduce ahead, scan from L2 (k_scan_ahead)
-template <class T, int NV> static int launch_scan_ahead(ScanParams q, DeviceCtx* ctx) {
+template <class T, int NV, int TH> static int launch_scan_ahead(ScanParams q, DeviceCtx* ctx) {
     using C = ScanTile<T>;
-    const int64_t te = (int64_t) kScanThreads * NV * (16 / (int64_t) sizeof(T));       // 16 KB tiles
+    const int64_t te = (int64_t) TH * NV * (16 / (int64_t) sizeof(T));       // 16 KB tiles (256 threads x 4 vectors)
     const int64_t tpr = (q.n + te - 1) / te;
     const int64_t tiles = tpr * q.rows;
     LbTree tr;
     memset(&tr, 0, sizeof(tr));
-    // look-ahead distance: 24 MB = 1536 tiles -- more than twice the ~740 CTAs in flight, so that a tile's scan visit
+    // look-ahead distance: 24-32 MB = 1536-2048 tiles -- more than twice the ~740-890 CTAs in flight, so that a tile's scan visit
     // never meets aggregates that are still being computed; it has to stay in the 126 MB L2 next to as many
     // bytes of stores.  At most half the work.
-    int64_t ahead_mb = options().scan_variant > 0 ? options().scan_variant : 24;
+    int64_t ahead_mb = options().scan_variant > 0 ? options().scan_variant : (TH == 128 && NV == 8 ? 32 : 24);
     int64_t ahead = std::min<int64_t>((ahead_mb << 20) / (te * (int64_t) sizeof(T)), std::max<int64_t>(64, tiles / 2)) / 64 * 64;
     if (ahead < 64) ahead = 64;
     tr.ahead = (uint32_t) ahead;
@@ -1587,8 +1587,8 @@ template <class T, int NV> static int launch_scan_ahead(ScanParams q, DeviceCtx*
     XTB_TRY(ensure_scratch(ctx, bytes, &scratch));
     tr.slots = (char*) scratch;
     XTB_CUDA(cudaMemsetAsync(scratch, 0, bytes, ctx->stream));
-    if (q.op == XTB_RED_PROD) k_scan_ahead<T, NV, XTB_RED_PROD><<<(unsigned) (tiles + ahead), kScanThreads, 0, ctx->stream>>>(q, tr);
-    else k_scan_ahead<T, NV, XTB_RED_SUM><<<(unsigned) (tiles + ahead), kScanThreads, 0, ctx->stream>>>(q, tr);
+    if (q.op == XTB_RED_PROD) k_scan_ahead<T, NV, XTB_RED_PROD, TH><<<(unsigned) (tiles + ahead), TH, 0, ctx->stream>>>(q, tr);
+    else k_scan_ahead<T, NV, XTB_RED_SUM, TH><<<(unsigned) (tiles + ahead), TH, 0, ctx->stream>>>(q, tr);
     note_launch("k_scan_ahead[reduce ahead, scan from L2]");
     return check_launch("k_scan_ahead");
 }
@@ -1627,7 +1627,13 @@ template <class T> static int launch_scan(const ScanParams& p, DeviceCtx* ctx, b
     const int64_t row_bytes = q.n * (int64_t) sizeof(T);
     // rows longer than one staged tile: reduce ahead, scan from L2 (k_scan_ahead)
     // rows longer than one staged tile: reduce ahead, scan from L2 (k_scan_ahead)
-    if (q.n * (int64_t) sizeof(T) > 64 * 1024) return options().scan_nv == 8 ? launch_scan_ahead<T, 8>(q, ctx) : launch_scan_ahead<T, 4>(q, ctx);
+    if (q.n * (int64_t) sizeof(T) > 64 * 1024) {
+        // 4-warp CTAs, 8 vectors per thread (16 KB tiles), 32 MB of look-ahead: the CTA barrier of the scan visit waits for
+        // the slowest of 4 warps instead of 8 (measured on 2^26 fp32: 5.55 TB/s vs 5.33 with 8-warp CTAs / 4 vectors / 24 MB;
+        // sweep in profiles/r02_scan_sweep.log).  scan_nv = 4 / tile_variant = 256 select the other shapes.
+        if (options().tile_variant == 256) return options().scan_nv == 8 ? launch_scan_ahead<T, 8, 256>(q, ctx) : launch_scan_ahead<T, 4, 256>(q, ctx);
+        return options().scan_nv == 4 ? launch_scan_ahead<T, 4, 128>(q, ctx) : launch_scan_ahead<T, 8, 128>(q, ctx);
+    }
     // staged super-tile configuration: threads per CTA / CTAs per SM / super-tile bytes
     // staged super-tiles: long rows (several tiles, look-back) use 8 scan warps + the look-back warp on 64 KB,
     // 3 CTAs per SM; rows of one tile use 4 warps on up to 32 KB, 6 CTAs per SM
@@ -1707,6 +1713,7 @@ extern "C" int xtb_scan(int op, int acc_type, const xtb_operand* in, int axis, c
     if (total == 0) return XTB_OK;
     DeviceCtx* ctx;
     XTB_TRY(get_ctx(&ctx));
+    XTB_LAUNCH_LOCK(ctx);
 
     ScanParams p;
     memset(&p, 0, sizeof(p));
