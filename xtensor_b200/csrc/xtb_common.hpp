@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <cuda_runtime.h>
 #include "../../include/xtb200.h"
 
@@ -71,6 +72,8 @@ struct Options {
     int scan_nv = 0;          // XTB_SCAN_NV: 128-bit vectors per thread of k_scan_ahead (4 or 8)
     int tile_variant = 0;     // XTB_TILE_VARIANT: development switch of the transposed-leaf kernel
     int arg_two_pass = 0;     // XTB_ARG_TWO_PASS: argmin / argmax of 32-bit types through the two-pass formulation (tests)
+    int reduce_split = 0;     // XTB_REDUCE_SPLIT: development override of the row-split count of k_reduce_outer
+    int no_pdl = 0;           // XTB_NO_PDL: launch every kernel fully serialised (no programmatic dependent launch)
 };
 Options& options();
 
@@ -80,6 +83,29 @@ int get_ctx(DeviceCtx** ctx);
 int ensure_scratch(DeviceCtx* ctx, size_t bytes, void** ptr);
 void note_launch(const char* kernel_name, int n = 1);
 int check_launch(const char* what);
+
+// ---- programmatic dependent launch ----------------------------------------------
+// The bandwidth-bound kernels of a pipeline (reduce -> merge -> reduce -> merge, map) are tens to hundreds of
+// microseconds long, so the 2-4 us between two dependent launches is worth removing: a kernel that starts with
+// pdl_enter() (xtb_ops.cuh: griddepcontrol.launch_dependents + griddepcontrol.wait) may be launched with the
+// programmatic-stream-serialization attribute; its CTAs then become resident while the previous kernel's last CTAs
+// drain and wait, on the device, for that kernel's completion and memory flush.  Works eagerly and under stream
+// capture (the edge becomes a programmatic graph edge).  ONLY for kernels whose every thread executes pdl_enter()
+// before touching global memory.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = options().no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- iteration-space canonicaliser --------------------------------------------
 // Operands (leaves + out) are re-expressed over one common iteration space:

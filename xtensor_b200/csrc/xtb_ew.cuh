@@ -281,6 +281,7 @@ XTB_DEV void ew_body(const EwParams& p) {
 
 template <class Eval, class S, int V, int ND, int ITEMS>
 __global__ void __launch_bounds__(256) k_ew(const __grid_constant__ EwParams p) {
+    pdl_enter();
     if (p.fast) ew_body<Eval, S, V, ND, ITEMS, true>(p);
     else ew_body<Eval, S, V, ND, ITEMS, false>(p);
 }
@@ -324,9 +325,9 @@ static int launch_ew_nd(const EwParams& p, DeviceCtx* ctx, const char* evname) {
     q.fast = fast;
     snprintf(name, sizeof(name), "k_ew<%s,S%d,V%d,ND%d>%s", evname, (int) sizeof(S) * 8, V, nd, fast ? "[fast]" : "");
     switch (nd) {
-        case 1: k_ew<Eval, S, V, 1, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;
-        case 2: k_ew<Eval, S, V, 2, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;
-        default: k_ew<Eval, S, V, 3, ITEMS><<<grid, 256, 0, ctx->stream>>>(q); break;
+        case 1: launch_pdl(k_ew<Eval, S, V, 1, ITEMS>, grid, 256, 0, ctx->stream, q); break;
+        case 2: launch_pdl(k_ew<Eval, S, V, 2, ITEMS>, grid, 256, 0, ctx->stream, q); break;
+        default: launch_pdl(k_ew<Eval, S, V, 3, ITEMS>, grid, 256, 0, ctx->stream, q); break;
     }
     note_launch(name);
     return check_launch(name);

@@ -131,11 +131,11 @@ struct ReducePlanIn {
 template <int BINOP, int ACC_RT>
 static void launch_merge(const RdParams& fp, DeviceCtx* ctx, bool xchg, const P2pParams& xw) {
     if (xchg) {
-        k_reduce_merge<BINOP, ACC_RT, true><<<(unsigned) ((fp.K + 127) / 128), kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+        launch_pdl(k_reduce_merge<BINOP, ACC_RT, true>, (unsigned) ((fp.K + 127) / 128), kMergeWarps * 32, 0, ctx->stream, fp, xw);
     } else if (fp.K < 128) {
-        k_reduce_merge_few<BINOP, ACC_RT><<<(unsigned) fp.K, 256, 0, ctx->stream>>>(fp);
+        launch_pdl(k_reduce_merge_few<BINOP, ACC_RT>, (unsigned) fp.K, 256, 0, ctx->stream, fp);
     } else {
-        k_reduce_merge<BINOP, ACC_RT, false><<<(unsigned) ((fp.K + 127) / 128), kMergeWarps * 32, 0, ctx->stream>>>(fp, xw);
+        launch_pdl(k_reduce_merge<BINOP, ACC_RT, false>, (unsigned) ((fp.K + 127) / 128), kMergeWarps * 32, 0, ctx->stream, fp, xw);
     }
 }
 template <int BINOP>
@@ -287,25 +287,44 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
         p.kvec_total = (p.K / KL) * kvpr;
         if (p.kvec_total >= 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "too many outputs");
         p.chunk = p.R;
-        if (p.kvec_total < target_threads && p.R > 32) {
-            int64_t want = target_threads / std::max<int64_t>(p.kvec_total, 1);
+        // Row splits.  Measured on the B200 (tools/split_sweep.py, profiles/r02_split_sweep.log): a CTA of this kernel
+        // streams ~15 GB/s when the GPU is saturated and 40 GB/s alone, all CTAs of a wave finish within a few percent
+        // of each other, so what costs time is a last wave with only a few CTAs in it (a few CTAs over a multiple of
+        // the resident count: up to +40 %), and long CTAs (a ragged end).  Hence: WHOLE waves of sm_count x 3 resident
+        // CTAs -- two for a pass of about a gigabyte, four from 2 GB, eight (CTAs of ~2.4 MB at 8 GB) from 4 GB; every
+        // CTA costs one 4 KB partial row that the merge kernel reads back, which is what caps the count.
+        const int64_t gx = (p.kvec_total + 255) / 256;
+        const int64_t slots = (int64_t) ctx->sm_count * 3;
+        if (gx < slots * 2 && p.R > 32) {
+            const double pass_bytes = (double) p.R * (double) p.K * dtype_size(p.leaf[0].dtype);
+            const double wb = pass_bytes / ((double) slots * 768.0 * 1024.0);
+            const int64_t waves = wb >= 10.0 ? 8 : (wb >= 5.0 ? 4 : (wb >= 1.5 ? 2 : 1));
+            // gx column blocks rarely divide a wave: take the first wave count >= `waves` that fills >= 93 %
+            int64_t want = 1;
+            double best_fill = 0.0;
+            for (int64_t w = waves; w <= 2 * waves + 1; ++w) {
+                const int64_t n = std::max<int64_t>(1, slots * w / gx);
+                const double fill = (double) (gx * n) / (double) (slots * w);
+                if (fill > best_fill) { best_fill = fill; want = n; }
+                if (fill >= 0.93) break;
+            }
             int64_t maxsplit = p.R / 16;
             int64_t ns = std::max<int64_t>(1, std::min(want, maxsplit));
             ns = std::min<int64_t>(ns, 4096);
+            if (options().reduce_split > 0) ns = std::max<int64_t>(1, std::min<int64_t>(options().reduce_split, maxsplit));
             if (ns > 1) {
                 p.chunk = (p.R + ns - 1) / ns;
                 p.chunk = (p.chunk + kRdFlush - 1) / kRdFlush * kRdFlush;   // whole summation blocks per split
                 p.nsplit = (int) ((p.R + p.chunk - 1) / p.chunk);
-                // the merge pass reads partials[nsplit][K] with 128-bit loads: keep rows 16-byte multiples
-                // (trailing empty splits write the identity)
-                const int q = 16 / dtype_size(p.acc_rt);
-                p.nsplit = (p.nsplit + q - 1) / q * q;
             }
         }
         // Split rows are already summed out of the reference's order: use blocked summation there, which keeps
         // every fp32 chain short (<= kRdFlush terms per level).  Unsplit, the kernel adds row after row exactly
         // like reduce_immediate (xreducer.hpp:512-551) and stays bit-identical to it.
         p.two_level = p.nsplit > 1 ? 1 : 0;
+        bool all_vec = V > 1 && p.nr == 1 && KL % V == 0;
+        for (int k = 0; k < in.n_leaves; ++k) all_vec = all_vec && p.leaf[k].mode == MODE_VEC;
+        p.outer_fast = all_vec ? 1 : 0;
     }
 
     // ---- cross-GPU merge of the result (the reduced axis is the sharded one) ----

@@ -67,6 +67,7 @@ struct RdParams {
     // Set whenever the result is not the reference's sequential order anyway (split rows, lanes sharing an
     // output); an unsplit strided-axis reduction keeps the reference's order bit for bit.
     int32_t two_level;
+    int32_t outer_fast;     // outer kernel: whole batches may use the unpredicated loader (RdFastLoader)
     // finalize step fused into the last store (mean_functor::finalize, xblockwise_reducer_functors.hpp:146-186):
     //   0 none, 1: out = T(acc) / imm, 2: out = sqrt(T(acc) / imm), T = fin_rt (XTB_F32 / XTB_F64)
     int32_t fin_op;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(kMergeWarps * 32) k_reduce_merge(const __grid_
     using S = typename MergeSlot<ACC_RT>::type;
     constexpr int asz = dtype_size(ACC_RT);
     __shared__ S sm[kMergeWarps][128];
+    pdl_enter();
     uint32_t epoch = 0;
     if constexpr (XCHG) epoch = p2p_epoch(xw);
     constexpr int U = 8;
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(256) k_reduce_merge_few(const __grid_constant_
     using S = typename MergeSlot<ACC_RT>::type;
     constexpr int asz = dtype_size(ACC_RT);
     __shared__ S sm[256];
+    pdl_enter();
     const int t = threadIdx.x;
     const int64_t k = blockIdx.x;
     S acc[1] = {(S) p.identity_bits};
@@ -415,6 +418,26 @@ template <class Eval, class S, int V, int U, int K, int INV = 0> struct RdLeafLo
                     for (int v = 0; v < V; ++v) pf.pre[K][u][v] = (v < nvalid[u]) ? load_elem<S>(addr[u] + v * step, dt) : S(0);
             }
             RdLeafLoader<Eval, S, V, U, K + 1, INV>::run(p, nvalid, gather_stride_elems_sel, pf, addr_of, skip_invariant);
+        }
+    }
+};
+
+// Whole batches of the outer kernel (host-verified: every leaf vector-accessed, every thread owns whole vectors,
+// one reduced dim): U unpredicated 128-bit loads per leaf from `row0 + u * rstep`, nothing else -- the general
+// loader above spends ~35 instructions per load on liveness and address arithmetic, which is what limited the
+// fused map-reduce kernels (variance, amax) below the plain sum.
+template <class Eval, class S, int V, int U, int K, int INV = 0> struct RdFastLoader {
+    template <class PF, int NL>
+    static XTB_DEV void run(const char* const (&row0)[NL], const int64_t (&rstep)[NL], PF& pf, bool skip_invariant) {
+        if constexpr (K < Eval::kLeaves) {
+            constexpr int dt = Eval::template leaf_dtype<K>();
+            if constexpr (((INV >> K) & 1) != 0) {
+                if (!skip_invariant) load_vec<S, V>(row0[K], dt, pf.inv[K]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) load_vec<S, V>(row0[K] + u * rstep[K], dt, pf.pre[K][u]);
+            }
+            RdFastLoader<Eval, S, V, U, K + 1, INV>::template run<PF, NL>(row0, rstep, pf, skip_invariant);
         }
     }
 };
@@ -765,7 +788,32 @@ XTB_DEV void reduce_outer_body(const RdParams& p) {
                 static_assert(U == kRdFlush, "one block per staged batch");
                 RdTotal<Acc, S, V> total;
                 total.init(p);
-                for (int64_t r = rbeg; r < rend; r += U) {
+                int64_t r = rbeg;
+                if (p.outer_fast) {
+                    const char* row0[NL];
+                    int64_t rs[NL];
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) {
+                        rs[k] = rstep[k];
+                        row0[k] = base[k] + r * rs[k];
+                    }
+                    for (; r + U <= rend; r += U) {
+                        RdFastLoader<Eval, S, V, U, 0, INV>::template run<decltype(pf), NL>(row0, rs, pf, r != rbeg);
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) row0[k] += U * rs[k];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            pf.u = u;
+                            S x[V];
+                            Eval::template run<S, V>(p.prog, pf, x);
+                            Acc::template cast_in<S, V>(p, x);
+                            Acc::template step<S, V>(p, acc, x);
+                        }
+                        if (p.two_level) total.flush(p, acc);
+                    }
+                }
+                const int64_t rslow = r;   // the invariant leaves are staged by whichever loop runs first
+                for (; r < rend; r += U) {
                     int nvalid[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) nvalid[u] = (r + u < rend) ? f.nvalid : 0;
@@ -775,7 +823,7 @@ XTB_DEV void reduce_outer_body(const RdParams& p) {
                         const int64_t koff = rd_kept_offset(p, ko0, L.kstride);
                         const int64_t ru = nvalid[u] > 0 ? r + u : rbeg;
                         return L.ptr + (koff + ru * L.rstride[0]) * sz;
-                    }, r != rbeg);
+                    }, r != rbeg || rslow != rbeg);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (nvalid[u] > 0) {
@@ -845,11 +893,13 @@ XTB_DEV void reduce_outer_body(const RdParams& p) {
 // compile-time one-leaf programs: 3 CTAs per SM (<= 80 registers) keep 96 KB of rows in flight per SM
 template <class Eval, class Acc, class S, int V>
 __global__ void __launch_bounds__(256, Eval::kPrefetch ? (Eval::kLeaves >= 2 ? 2 : 3) : 1) k_reduce_outer(const __grid_constant__ RdParams p) {
+    pdl_enter();
     reduce_outer_body<Eval, Acc, S, V, 0>(p);
 }
 // invariant leaves (the mean in square(a - mean)) staged once; 80 registers -> 3 CTAs per SM
 template <class Eval, class Acc, class S, int V, int INV>
 __global__ void __launch_bounds__(256, 3) k_reduce_outer_inv(const __grid_constant__ RdParams p) {
+    pdl_enter();
     reduce_outer_body<Eval, Acc, S, V, INV>(p);
 }
 
@@ -915,10 +965,10 @@ static int launch_reduce(const RdParams& p, DeviceCtx* ctx, bool inner, const ch
                    p.leaf[0].rstride[0] != 0 && p.kshape[p.nk - 1] % V == 0;
             if (inv1) {
                 snprintf(name, sizeof(name), "k_reduce_outer<%s,S%d,V%d,inv1>[split=%d]", evname, (int) sizeof(S) * 8, V, p.nsplit);
-                k_reduce_outer_inv<Eval, Acc, S, V, 2><<<grid, 256, 0, ctx->stream>>>(p);
+                launch_pdl(k_reduce_outer_inv<Eval, Acc, S, V, 2>, grid, 256, 0, ctx->stream, p);
             }
         }
-        if (!inv1) k_reduce_outer<Eval, Acc, S, V><<<grid, 256, 0, ctx->stream>>>(p);
+        if (!inv1) launch_pdl(k_reduce_outer<Eval, Acc, S, V>, grid, 256, 0, ctx->stream, p);
     }
     note_launch(name);
     return check_launch(name);

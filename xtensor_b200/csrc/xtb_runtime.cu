@@ -57,6 +57,8 @@ Options& options() {
         if (const char* e = getenv("XTB_TILE_VARIANT")) g_options.tile_variant = atoi(e);
         if (const char* e = getenv("XTB_SCAN_NV")) g_options.scan_nv = atoi(e);
         if (const char* e = getenv("XTB_ARG_TWO_PASS")) g_options.arg_two_pass = atoi(e);
+        g_options.no_pdl = flag("XTB_NO_PDL");
+        if (const char* e = getenv("XTB_REDUCE_SPLIT")) g_options.reduce_split = atoi(e);
     });
     return g_options;
 }
@@ -579,6 +581,8 @@ int xtb_set_option(const char* name, long long value) {
     else if (!strcmp(name, "tile_variant")) o.tile_variant = (int) value;
     else if (!strcmp(name, "scan_nv")) o.scan_nv = (int) value;
     else if (!strcmp(name, "arg_two_pass")) o.arg_two_pass = (int) value;
+    else if (!strcmp(name, "no_pdl")) o.no_pdl = (int) value;
+    else if (!strcmp(name, "reduce_split")) o.reduce_split = (int) value;
     else XTB_FAIL(XTB_ERR_INVALID, "unknown option '%s'", name);
     return XTB_OK;
 }
@@ -596,6 +600,8 @@ long long xtb_get_option(const char* name) {
     if (!strcmp(name, "tile_variant")) return o.tile_variant;
     if (!strcmp(name, "scan_nv")) return o.scan_nv;
     if (!strcmp(name, "arg_two_pass")) return o.arg_two_pass;
+    if (!strcmp(name, "no_pdl")) return o.no_pdl;
+    if (!strcmp(name, "reduce_split")) return o.reduce_split;
     return -1;
 }
 
