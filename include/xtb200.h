@@ -306,7 +306,7 @@ int  xtb_allreduce(void* buf, size_t count, int dtype, int op);
 /* ---- process options ------------------------------------------------------- */
 /* The XTB_* environment switches are read once, at first use; afterwards they are changed through this call
  * (name = the variable without the XTB_ prefix, lower case: "no_static", "no_jit", "no_staged", "no_tma",
- * "jit_min_elems", "jit_verbose", "scan_variant", "tile_variant", "arg_two_pass", "no_pdl").  xtb_get_option returns -1 for unknown names. */
+ * "jit_min_elems", "jit_verbose", "scan_variant", "tile_variant", "arg_two_pass", "no_pdl", "no_decompose").  xtb_get_option returns -1 for unknown names. */
 int  xtb_set_option(const char* name, long long value);
 long long xtb_get_option(const char* name);
 

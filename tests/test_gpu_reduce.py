@@ -188,3 +188,69 @@ def test_fused_map_reduce_and_views(xt, gpu):
     assert_bit_exact(g, a[::2, 1:63].sum(axis=1))
     g, w = both(xt, lambda A: xt.sum(xt.sum(A, [0]) * F32(2)), a)  # reducer inside an expression
     assert float(g) == float(a.sum() * 2)
+
+
+# ---- reductions rewritten into two passes (xtb_reduce.cu: reduce_decomposed) and scalar-access kernels ----------
+DECOMP_CASES = [
+    # narrow: innermost kept, < 1024 outputs
+    ((1 << 15, 64), [0]), ((40000, 33), [0]), ((1 << 20, 3), [0]), ((100003, 16), [0]), ((512, 512, 16), [0, 1]),
+    ((300, 70, 50, 6), [0, 2]), ((70001, 20), [0]),
+    # mixed: innermost reduced together with an outer axis, kept dim between
+    ((512, 256, 16), [0, 2]), ((64, 32, 40, 16), [0, 3]), ((64, 32, 40, 16), [1, 3]), ((300, 17, 257), [0, 2]),
+]
+
+
+@pytest.mark.parametrize("shape,axes", DECOMP_CASES)
+@pytest.mark.parametrize("dtype", [F32, np.int32, F64])
+def test_decomposed_reductions_bit_exact(xt, gpu, shape, axes, dtype):
+    """Two-pass formulation == single-pass kernels == numpy on integer-valued data (sum, amax, keep_dims, initial, mean)."""
+    a = ints(shape, dtype, -4, 4, seed=11)
+    A = xt.DeviceArray.from_numpy(a)
+    for red, npf in (("sum", np.sum), ("amax", np.max)):
+        got = xt.evaluate(getattr(xt, red)(A, axes)).numpy()
+        assert_bit_exact(got, npf(a, axis=tuple(axes)).astype(dtype))
+        gpu.xtb_set_option(b"no_decompose", 1)
+        try:
+            single = xt.evaluate(getattr(xt, red)(A, axes)).numpy()
+        finally:
+            gpu.xtb_set_option(b"no_decompose", 0)
+        assert_bit_exact(got, single)
+    kd = xt.evaluate(xt.sum(A, axes, keep_dims=True)).numpy()
+    assert_bit_exact(kd, a.sum(axis=tuple(axes), keepdims=True).astype(dtype))
+    ini = xt.evaluate(xt.sum(A, axes, initial=dtype(100))).numpy()
+    assert_bit_exact(ini, (a.sum(axis=tuple(axes)) + 100).astype(dtype))
+    if dtype != np.int32:
+        mean = xt.evaluate(xt.mean(A, axes)).numpy()
+        n = np.prod([shape[x] for x in axes])
+        assert mean.dtype == F64
+        assert_bit_exact(mean, a.sum(axis=tuple(axes)).astype(F64) / F64(n))
+
+
+def test_decomposed_fused_map_with_broadcast_leaf(xt, gpu):
+    """sum(square(a - m), {0}) with m broadcast along the split axis (variance second pass on a narrow matrix)."""
+    a = ints((1 << 16, 48), F32, -4, 4, seed=5)
+    m = ints((48,), F32, -2, 2, seed=6)
+    got = xt.evaluate(xt.sum(xt.square(xt.DeviceArray.from_numpy(a) - xt.DeviceArray.from_numpy(m)), [0])).numpy()
+    assert_bit_exact(got, np.square(a - m).sum(axis=0).astype(F32))
+    v = xt.evaluate(xt.variance(xt.DeviceArray.from_numpy(a), [0])).numpy()
+    want = np.square(a - a.mean(axis=0, dtype=F64)).mean(axis=0)
+    assert np.allclose(v, want, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape,axes", [((2047, 1022), [0]), ((2047, 1022), [1]), ((513, 255, 15), [0]), ((513, 255, 15), [2]),
+                                        ((1025, 1023), [0, 1]), ((300001, 7), [0])])
+@pytest.mark.parametrize("dtype", [F32, F64, np.int32])
+def test_unaligned_shapes_use_compiled_kernels(xt, gpu, shape, axes, dtype):
+    """Odd extents (row pitch not a multiple of 16 bytes) run the scalar-access instantiation of the same kernels,
+    not the interpreter, and match numpy bit for bit."""
+    a = ints(shape, dtype, -4, 4, seed=12)
+    A = xt.DeviceArray.from_numpy(a)
+    for red, npf in (("sum", np.sum), ("amax", np.max)):
+        got = xt.evaluate(getattr(xt, red)(A, axes)).numpy()
+        assert "interp" not in last_kernel(), last_kernel()
+        assert_bit_exact(got, npf(a, axis=tuple(axes)).astype(dtype))
+    # an offset view of an aligned container: base misaligned by one element
+    b = ints((1024, 1024), dtype, -4, 4, seed=13)
+    B = xt.DeviceArray.from_numpy(b)
+    got = xt.evaluate(xt.sum(xt.view(B, slice(None), slice(1, None)), [0])).numpy()
+    assert_bit_exact(got, b[:, 1:].sum(axis=0).astype(dtype))

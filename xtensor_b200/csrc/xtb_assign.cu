@@ -54,7 +54,9 @@ static int dispatch_ew(const xtb_program* prog, const EwParams& p, DeviceCtx* ct
         }
     }
     // no ahead-of-time instantiation: specialise the same kernel template for this program at run time
-    if (!no_static && ew_nd_ok(p) && V == (w64 ? 2 : 4) && jit_program_ok(prog) && p.out.dtype == (int) p.out_rt &&
+    // (V == 1: no operand can be accessed with 128-bit vectors -- broadcast expressions over odd inner extents,
+    // offset views; the same kernel with coalesced scalar access instead of the interpreter)
+    if (!no_static && ew_nd_ok(p) && (V == (w64 ? 2 : 4) || V == 1) && jit_program_ok(prog) && p.out.dtype == (int) p.out_rt &&
         jit_worthwhile(p.total_vec * V)) {
         JitSpec spec;
         spec.kind = JIT_EW;

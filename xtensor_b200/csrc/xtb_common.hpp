@@ -73,6 +73,8 @@ struct Options {
     int tile_variant = 0;     // XTB_TILE_VARIANT: development switch of the transposed-leaf kernel
     int arg_two_pass = 0;     // XTB_ARG_TWO_PASS: argmin / argmax of 32-bit types through the two-pass formulation (tests)
     int reduce_split = 0;     // XTB_REDUCE_SPLIT: development override of the row-split count of k_reduce_outer
+    int reduce_g = 0;         // XTB_REDUCE_G: development override of the lanes per output of the contiguous-axis kernels (32 / 256)
+    int no_decompose = 0;     // XTB_NO_DECOMPOSE: single-pass reductions only (tests: both formulations agree)
     int no_pdl = 0;           // XTB_NO_PDL: launch every kernel fully serialised (no programmatic dependent launch)
 };
 Options& options();

@@ -72,15 +72,15 @@ static int binop_of(int op) {
 
 static int run_reduce_kernel(const xtb_program* prog, const RdParams& p, DeviceCtx* ctx, bool inner, bool w64, int V) {
     const bool no_static = options().no_static != 0;
-    if (!no_static && p.in_rt == p.acc_rt && V == (w64 ? 2 : 4) && p.K < 0x7fffffff) {
-        const StaticReduceTable t = static_reduce_table();
+    if (!no_static && p.in_rt == p.acc_rt && (V == (w64 ? 2 : 4) || V == 1) && p.K < 0x7fffffff) {
+        const StaticReduceTable t = V == 1 ? static_reduce_table_v1() : static_reduce_table();
         for (int i = 0; i < t.n; ++i) {
             const StaticReduceEntry& e = t.entries[i];
             if (e.binop == p.binop && e.acc_rt == p.acc_rt && sprogs::is64(*e.prog) == w64 && sprog_matches(*e.prog, prog))
                 return e.launch(p, ctx, inner);
         }
     }
-    if (!no_static && p.in_rt == p.acc_rt && V == (w64 ? 2 : 4) && p.K < 0x7fffffff && jit_program_ok(prog) &&
+    if (!no_static && p.in_rt == p.acc_rt && (V == (w64 ? 2 : 4) || V == 1) && p.K < 0x7fffffff && jit_program_ok(prog) &&
         jit_worthwhile(p.K * std::max<int64_t>(p.R, 1))) {
         // run-time specialisation of the reduction kernel for this (program, reducer, accumulator)
         const RdLaunch g = reduce_geometry(p, ctx, inner, p.out_dtype == p.acc_rt);
@@ -246,7 +246,12 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
         L.mode = classify(L.ptr, L.dtype, L.kstride, L.rstride);
         any_vec |= L.mode == MODE_VEC;
     }
-    if (!any_vec) V = 1;
+    if (!any_vec && V > 1) {
+        // no leaf can be read with 128-bit loads (odd pitch, offset view): scalar access, where any unit-stride
+        // leaf counts as "vector" again and the unpredicated loaders apply
+        V = 1;
+        for (int k = 0; k < in.n_leaves; ++k) p.leaf[k].mode = classify(p.leaf[k].ptr, p.leaf[k].dtype, p.leaf[k].kstride, p.leaf[k].rstride);
+    }
 
     if (in.empty) p.R = 0;
     // parallelisation
@@ -260,13 +265,28 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
         p.vpr_div = make_fastdiv(p.vpr);
         p.rvec_total = (p.R / RL) * vpr;
         if (p.nr > 1 && p.rvec_total >= 0x7fffffff) XTB_FAIL(XTB_ERR_UNSUPPORTED, "reduction too large for split axes");
+        {
+            bool all_vec = p.nr == 1 && RL % V == 0;
+            for (int k = 0; k < in.n_leaves; ++k) all_vec = all_vec && p.leaf[k].mode == MODE_VEC;
+            p.inner_fast = all_vec ? 1 : 0;
+        }
         int G = 1;
         while (G < 32 && G < p.rvec_total) G <<= 1;
         if (p.rvec_total > 32 * 8 && p.K * 32 < target_threads) G = 256;
+        if (options().reduce_g == 32 && G == 256) G = 32;
+        if (options().reduce_g == 256 && p.rvec_total > 32 * 8) G = 256;
         p.G = G;
         p.chunk = p.rvec_total;
         if (G == 256 && p.K * 256 < target_threads && p.rvec_total > 256 * 16) {
-            int64_t want = target_threads / (p.K * 256);
+            // whole waves of resident CTAs (64 registers: 4 per SM), as for the row-streaming kernel below: measured
+            // on a 2^26 full reduction, 592 CTAs 5.07 TB/s, 1024 CTAs 4.66, 296 CTAs 3.9 (tools/reduce_bench.py)
+            const int64_t slots = (int64_t) ctx->sm_count * 4;
+            const double pass_bytes = (double) p.R * (double) p.K * dtype_size(p.leaf[0].dtype);
+            const int64_t waves = pass_bytes >= 1.5 * (double) slots * 768.0 * 1024.0 ? 2 : 1;
+            const int q = 16 / dtype_size(p.acc_rt);
+            int64_t want = std::max<int64_t>(1, slots * waves / p.K);
+            if (want > q) want = want / q * q;      // partial rows stay 16-byte multiples without overshooting the wave
+            if (options().reduce_split > 0) want = options().reduce_split;
             int64_t maxsplit = p.rvec_total / (256 * 8);
             int64_t ns = std::max<int64_t>(1, std::min(want, maxsplit));
             ns = std::min<int64_t>(ns, 1024);
@@ -274,7 +294,6 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
                 p.chunk = (p.rvec_total + ns - 1) / ns;
                 p.chunk = (p.chunk + 255) / 256 * 256;  // whole block strides
                 p.nsplit = (int) ((p.rvec_total + p.chunk - 1) / p.chunk);
-                const int q = 16 / dtype_size(p.acc_rt);
                 p.nsplit = (p.nsplit + q - 1) / q * q;
             }
         }
@@ -322,7 +341,7 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
         // every fp32 chain short (<= kRdFlush terms per level).  Unsplit, the kernel adds row after row exactly
         // like reduce_immediate (xreducer.hpp:512-551) and stays bit-identical to it.
         p.two_level = p.nsplit > 1 ? 1 : 0;
-        bool all_vec = V > 1 && p.nr == 1 && KL % V == 0;
+        bool all_vec = p.nr == 1 && KL % V == 0;
         for (int k = 0; k < in.n_leaves; ++k) all_vec = all_vec && p.leaf[k].mode == MODE_VEC;
         p.outer_fast = all_vec ? 1 : 0;
     }
@@ -399,6 +418,200 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
 
 using namespace xtb;
 
+// ---- decomposition of reductions the single-pass kernels serve badly ------------------------------------------
+// Two shapes of problem are rewritten into two calls of xtb_reduce_fin over a small accumulator-typed temporary
+// (pure descriptor work; measured before: 0.4 TB/s and 2.6 TB/s, tools/reduce_bench.py):
+//   narrow : the innermost dim is kept but there are < 1024 outputs in all (sum over axis 0 of (2^20, 64), over axes
+//            {0,1} of (4096,4096,16)): a thread owns 4 outputs, so a CTA of the row-streaming kernel would be mostly
+//            idle.  The outermost reduced axis (extent E) is split into (E / m, m) and only its outer part is reduced
+//            first, which keeps rows of m x (everything behind it) >= 32 K elements -- the shape the kernel is good
+//            at; the (m, ...) temporary is reduced by the second call.  E need not be a multiple of m: the E mod m
+//            trailing positions are reduced into an extra slice of the temporary.
+//   mixed  : the innermost dim is reduced together with an outer one and a kept dim lies between them (axes {0,2} of
+//            (4096,4096,16)): lanes sharing an output would gather 64-byte pieces a row pitch apart.  The reduced
+//            axes in front of the last kept dim are reduced first (row streaming, everything behind stays), the rest
+//            on the temporary.
+// Both passes use the caller's reducer; xt::initial, the finalize step and the cross-GPU merge belong to the second.
+// The result is a different (still fixed) summation order, as for every split reduction; integer results are exact.
+static thread_local int t_decompose_depth = 0;
+
+static int reduce_decomposed(int op, int acc_type, const xtb_program* prog, const xtb_operand* leaves, int ndim,
+                             const int64_t* shape, int n_axes, const int32_t* axes, int keep_dims, const void* initial,
+                             const xtb_operand* out, int allreduce, const xtb_finalize* fin, bool* handled) {
+    *handled = false;
+    if (options().no_decompose || t_decompose_depth >= 2 || n_axes == 0 || ndim + 1 > XTB_MAX_DIM || prog->n_leaves < 1) return XTB_OK;
+    bool red[XTB_MAX_DIM] = {false};
+    for (int i = 0; i < n_axes; ++i) red[axes[i]] = true;
+    int64_t N = 1, K = 1;
+    int li = -1, a0 = -1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] <= 0) return XTB_OK;
+        N *= shape[d];
+        if (!red[d]) K *= shape[d];
+        if (shape[d] > 1) {
+            li = d;
+            if (red[d] && a0 < 0) a0 = d;
+        }
+    }
+    if (a0 < 0 || N < (1ll << 20)) return XTB_OK;
+    bool kept_after_a0 = false;
+    for (int d = a0 + 1; d < ndim; ++d) kept_after_a0 = kept_after_a0 || (!red[d] && shape[d] > 1);
+    const bool mixed = red[li] && kept_after_a0;
+    const bool narrow = !red[li] && K < 1024;
+    if (!mixed && !narrow) return XTB_OK;
+
+    // axes of the first pass (indices in the ORIGINAL space) and the split of a0
+    bool peel[XTB_MAX_DIM] = {false};
+    int64_t m = 1;
+    if (mixed) {
+        int last_kept = -1;
+        for (int d = 0; d < ndim; ++d)
+            if (!red[d] && shape[d] > 1) last_kept = d;
+        int64_t shrink = 1;
+        for (int d = 0; d < last_kept; ++d)
+            if (red[d] && shape[d] > 1) { peel[d] = true; shrink *= shape[d]; }
+        if (shrink < 4) return XTB_OK;
+    } else {
+        int64_t after = 1;
+        bool other_reduced = false;
+        for (int d = a0 + 1; d < ndim; ++d) {
+            after *= shape[d];
+            other_reduced = other_reduced || (red[d] && shape[d] > 1);
+        }
+        peel[a0] = true;
+        if (after < 16384) {
+            m = 32768 / after;
+            const int64_t E = shape[a0];
+            if (E < 4 * m) m = E / 4;
+            if (m < 2) {
+                if (!other_reduced) return XTB_OK;
+                m = 1;
+            } else {
+                // a nearby divisor of E avoids the remainder slice
+                for (int64_t c = m; c >= std::max<int64_t>(2, m / 2); --c)
+                    if (E % c == 0) { m = c; break; }
+            }
+        } else if (!other_reduced) {
+            return XTB_OK;
+        }
+    }
+    const int64_t E = shape[a0];
+    const int64_t q = m > 1 ? E / m : E, rem = m > 1 ? E - q * m : 0;
+    const bool split = m > 1;
+    const int nd1 = ndim + (split ? 1 : 0);
+    auto map_dim = [&](int d) { return (split && d > a0) ? d + 1 : d; };   // original dim -> dim of the split space (a0 -> its outer part)
+
+    // every leaf at full rank with explicit strides (0 where it broadcasts)
+    xtb_operand l1[XTB_MAX_LEAVES], l1r[XTB_MAX_LEAVES];
+    int64_t shape1[XTB_MAX_DIM], tshape[XTB_MAX_DIM];
+    for (int d = 0; d < ndim; ++d) shape1[map_dim(d)] = shape[d];
+    if (split) { shape1[a0] = q; shape1[a0 + 1] = m; }
+    for (int k = 0; k < prog->n_leaves; ++k) {
+        int64_t st[XTB_MAX_DIM];
+        char what[32];
+        snprintf(what, sizeof(what), "leaf %d", k);
+        XTB_TRY(align_operand(&leaves[k], ndim, shape, st, what));
+        xtb_operand o = leaves[k];
+        o.ndim = nd1;
+        for (int d = 0; d < ndim; ++d) {
+            const int e = map_dim(d);
+            o.shape[e] = st[d] == 0 ? 1 : shape[d];
+            o.stride[e] = st[d];
+        }
+        if (split) {
+            const bool b = st[a0] == 0;
+            o.shape[a0] = b ? 1 : q;
+            o.stride[a0] = b ? 0 : st[a0] * m;
+            o.shape[a0 + 1] = b ? 1 : m;
+            o.stride[a0 + 1] = b ? 0 : st[a0];
+        }
+        l1[k] = o;
+        if (rem > 0) {
+            // the E mod m trailing positions of a0: outer extent rem, inner extent 1
+            xtb_operand r = o;
+            const bool b = st[a0] == 0;
+            r.offset += b ? 0 : q * m * st[a0];
+            r.shape[a0] = b ? 1 : rem;
+            r.stride[a0] = b ? 0 : st[a0];
+            r.shape[a0 + 1] = 1;
+            r.stride[a0 + 1] = 0;
+            l1r[k] = r;
+        }
+    }
+    // temporary: the split space with the peeled axes reduced to 1 (keep_dims), dense, accumulator-typed
+    int32_t axes1[XTB_MAX_DIM];
+    int na1 = 0;
+    for (int d = 0; d < ndim; ++d)
+        if (peel[d]) axes1[na1++] = map_dim(d);
+    for (int d = 0; d < nd1; ++d) tshape[d] = shape1[d];
+    for (int i = 0; i < na1; ++i) tshape[axes1[i]] = 1;
+    const int64_t mslices = split ? m + (rem > 0 ? 1 : 0) : 1;
+    if (split) tshape[a0 + 1] = mslices;
+    int64_t tn = 1;
+    for (int d = 0; d < nd1; ++d) tn *= tshape[d];
+    const int asz = dtype_size(acc_type);
+    struct Tmp { void* p = nullptr; ~Tmp() { if (p) xtb_free(p); } } tmp;
+    XTB_TRY(xtb_malloc((size_t) tn * asz, &tmp.p));
+    xtb_operand t{};
+    t.base = tmp.p;
+    t.dtype = acc_type;
+    t.ndim = nd1;
+    {
+        int64_t stv = 1;
+        for (int d = nd1 - 1; d >= 0; --d) {
+            t.shape[d] = tshape[d];
+            t.stride[d] = tshape[d] == 1 ? 0 : stv;
+            stv *= tshape[d];
+        }
+    }
+    struct Depth { Depth() { ++t_decompose_depth; } ~Depth() { --t_decompose_depth; } } depth_guard;
+    // pass 1 (and the remainder slice)
+    {
+        xtb_operand t1 = t;
+        if (split) t1.shape[a0 + 1] = m;
+        XTB_TRY(xtb_reduce_fin(op, acc_type, prog, l1, nd1, shape1, na1, axes1, 1, nullptr, &t1, 0, nullptr));
+        if (rem > 0) {
+            int64_t shr[XTB_MAX_DIM];
+            for (int d = 0; d < nd1; ++d) shr[d] = shape1[d];
+            shr[a0] = rem;
+            shr[a0 + 1] = 1;
+            xtb_operand tr = t;
+            tr.offset += m * t.stride[a0 + 1];
+            tr.shape[a0 + 1] = 1;
+            tr.stride[a0 + 1] = 0;
+            XTB_TRY(xtb_reduce_fin(op, acc_type, prog, l1r, nd1, shr, na1, axes1, 1, nullptr, &tr, 0, nullptr));
+        }
+    }
+    // pass 2: the caller's reducer over the temporary (identity map), every original reduced axis plus the inner part of a0
+    xtb_program p2{};
+    p2.n_leaves = 1;
+    p2.insns[p2.n_insns++] = xtb_insn{(uint8_t) XTB_OP_PUSH, (uint8_t) acc_type, (uint8_t) XTB_SRC_LEAF, 0};
+    int32_t axes2[XTB_MAX_DIM];
+    int na2 = 0;
+    for (int d = 0; d < nd1; ++d) {
+        bool r2 = split && d == a0 + 1;
+        for (int i = 0; i < n_axes && !r2; ++i) r2 = map_dim(axes[i]) == d;
+        if (r2) axes2[na2++] = d;
+    }
+    xtb_operand o2 = *out;
+    if (split && keep_dims) {
+        // the caller's output has no dim for the inner part of a0: insert an extent-1 dim
+        if (out->ndim != ndim) XTB_FAIL(XTB_ERR_SHAPE, "reducer output has rank %d, expected %d", out->ndim, ndim);
+        o2.ndim = nd1;
+        for (int d = 0; d < ndim; ++d) {
+            o2.shape[map_dim(d)] = out->shape[d];
+            o2.stride[map_dim(d)] = out->stride[d];
+        }
+        o2.shape[a0] = out->shape[a0];
+        o2.stride[a0] = out->stride[a0];
+        o2.shape[a0 + 1] = 1;
+        o2.stride[a0 + 1] = 0;
+    }
+    XTB_TRY(xtb_reduce_fin(op, acc_type, &p2, &t, nd1, tshape, na2, axes2, keep_dims, initial, &o2, allreduce, fin));
+    *handled = true;
+    return XTB_OK;
+}
+
 extern "C" int xtb_reduce(int op, int acc_type, const xtb_program* prog, const xtb_operand* leaves, int ndim,
                           const int64_t* shape, int n_axes, const int32_t* axes, int keep_dims, const void* initial,
                           const xtb_operand* out, int allreduce) {
@@ -437,6 +650,11 @@ extern "C" int xtb_reduce_fin(int op, int acc_type, const xtb_program* prog, con
         w64 = true;
     }
 
+    {
+        bool handled = false;
+        XTB_TRY(reduce_decomposed(op, acc_type, prog, leaves, ndim, shape, n_axes, axes, keep_dims, initial, out, allreduce, fin, &handled));
+        if (handled) return XTB_OK;
+    }
     ReducePlanIn in;
     in.prog = prog;
     in.n_leaves = prog->n_leaves;

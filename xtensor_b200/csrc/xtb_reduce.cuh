@@ -68,6 +68,7 @@ struct RdParams {
     // output); an unsplit strided-axis reduction keeps the reference's order bit for bit.
     int32_t two_level;
     int32_t outer_fast;     // outer kernel: whole batches may use the unpredicated loader (RdFastLoader)
+    int32_t inner_fast;     // inner kernels (one reduced dim): the same for whole batches of a lane's vectors
     // finalize step fused into the last store (mean_functor::finalize, xblockwise_reducer_functors.hpp:146-186):
     //   0 none, 1: out = T(acc) / imm, 2: out = sqrt(T(acc) / imm), T = fin_rt (XTB_F32 / XTB_F64)
     int32_t fin_op;
@@ -470,7 +471,32 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
             static_assert(U == kRdInnerFlush, "one block per staged batch");
             RdTotal<Acc, S, V> total;
             total.init(p);
-            for (int64_t j = jbeg + lane; j < jend; j += (int64_t) stride * U) {
+            int64_t j = jbeg + lane;
+            if (p.inner_fast) {
+                // whole batches: unpredicated 128-bit loads (same batches, same order as the general loop below)
+                const char* row0[NL];
+                int64_t rs[NL];
+#pragma unroll
+                for (int k = 0; k < NL; ++k) {
+                    rs[k] = (int64_t) stride * vstep[k];
+                    row0[k] = base[k] + j * vstep[k];
+                }
+                for (; j + (int64_t) (U - 1) * stride < jend; j += (int64_t) stride * U) {
+                    RdFastLoader<Eval, S, V, U, 0>::template run<decltype(pf), NL>(row0, rs, pf, false);
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) row0[k] += U * rs[k];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        pf.u = u;
+                        S x[V];
+                        Eval::template run<S, V>(p.prog, pf, x);
+                        Acc::template cast_in<S, V>(p, x);
+                        Acc::template step<S, V>(p, acc, x);
+                    }
+                    total.flush(p, acc);
+                }
+            }
+            for (; j < jend; j += (int64_t) stride * U) {
                 int nvalid[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -986,7 +1012,8 @@ struct StaticReduceTable {
     const StaticReduceEntry* entries;
     int n;
 };
-StaticReduceTable static_reduce_table();
+StaticReduceTable static_reduce_table();      // V = 4 (32-bit slots) / 2 (64-bit slots)
+StaticReduceTable static_reduce_table_v1();   // V = 1
 
 #endif  // XTB_RTC
 

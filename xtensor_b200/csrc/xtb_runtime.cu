@@ -58,6 +58,8 @@ Options& options() {
         if (const char* e = getenv("XTB_SCAN_NV")) g_options.scan_nv = atoi(e);
         if (const char* e = getenv("XTB_ARG_TWO_PASS")) g_options.arg_two_pass = atoi(e);
         g_options.no_pdl = flag("XTB_NO_PDL");
+        g_options.no_decompose = flag("XTB_NO_DECOMPOSE");
+        if (const char* e = getenv("XTB_REDUCE_G")) g_options.reduce_g = atoi(e);
         if (const char* e = getenv("XTB_REDUCE_SPLIT")) g_options.reduce_split = atoi(e);
     });
     return g_options;
@@ -582,6 +584,8 @@ int xtb_set_option(const char* name, long long value) {
     else if (!strcmp(name, "scan_nv")) o.scan_nv = (int) value;
     else if (!strcmp(name, "arg_two_pass")) o.arg_two_pass = (int) value;
     else if (!strcmp(name, "no_pdl")) o.no_pdl = (int) value;
+    else if (!strcmp(name, "no_decompose")) o.no_decompose = (int) value;
+    else if (!strcmp(name, "reduce_g")) o.reduce_g = (int) value;
     else if (!strcmp(name, "reduce_split")) o.reduce_split = (int) value;
     else XTB_FAIL(XTB_ERR_INVALID, "unknown option '%s'", name);
     return XTB_OK;
@@ -601,6 +605,8 @@ long long xtb_get_option(const char* name) {
     if (!strcmp(name, "scan_nv")) return o.scan_nv;
     if (!strcmp(name, "arg_two_pass")) return o.arg_two_pass;
     if (!strcmp(name, "no_pdl")) return o.no_pdl;
+    if (!strcmp(name, "no_decompose")) return o.no_decompose;
+    if (!strcmp(name, "reduce_g")) return o.reduce_g;
     if (!strcmp(name, "reduce_split")) return o.reduce_split;
     return -1;
 }

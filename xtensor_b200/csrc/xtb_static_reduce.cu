@@ -1,56 +1,4 @@
-// xtb_static_reduce.cu -- compile-time instantiations of the reduction kernels for
-// the common (expression, reducer, accumulator) combinations: plain sum / prod /
-// amax / amin of f32, f64, i32 containers and sum(square(a - m)) (the second pass
-// of xt::variance, include/xtensor/core/xmath.hpp:2082-2105).
-#include <utility>
-#include "xtb_reduce.cuh"
-
-namespace xtb {
-namespace {
-
-struct Combo {
-    sprogs::SP prog;
-    int binop, acc_rt;
-};
-struct Tbl {
-    static constexpr sprogs::SP progs[] = {sprogs::copy_f32, sprogs::copy_f64, sprogs::copy_i32,
-                                           sprogs::sq_sub_f32, sprogs::sq_sub_f64, sprogs::square_f32,
-                                           sprogs::square_f64};
-};
-static const char* const kProgNames[] = {"copy_f32", "copy_f64", "copy_i32", "sq_sub_f32", "sq_sub_f64",
-                                         "square_f32", "square_f64"};
-struct ComboId {
-    int prog, binop, acc_rt;
-};
-constexpr ComboId kCombos[] = {
-    {0, XTB_OP_ADD, XTB_F32}, {0, XTB_OP_MUL, XTB_F32}, {0, XTB_OP_MAXIMUM, XTB_F32}, {0, XTB_OP_MINIMUM, XTB_F32},
-    {1, XTB_OP_ADD, XTB_F64}, {1, XTB_OP_MUL, XTB_F64}, {1, XTB_OP_MAXIMUM, XTB_F64}, {1, XTB_OP_MINIMUM, XTB_F64},
-    {2, XTB_OP_ADD, XTB_I32}, {2, XTB_OP_MUL, XTB_I32}, {2, XTB_OP_MAXIMUM, XTB_I32}, {2, XTB_OP_MINIMUM, XTB_I32},
-    {3, XTB_OP_ADD, XTB_F32}, {4, XTB_OP_ADD, XTB_F64}, {5, XTB_OP_ADD, XTB_F32}, {6, XTB_OP_ADD, XTB_F64},
-};
-constexpr int kCount = (int) (sizeof(kCombos) / sizeof(kCombos[0]));
-
-template <int C> int launch_one(const RdParams& p, DeviceCtx* ctx, bool inner) {
-    constexpr ComboId c = kCombos[C];
-    constexpr bool k64 = sprogs::is64(Tbl::progs[c.prog]);
-    using Slot = std::conditional_t<k64, uint64_t, uint32_t>;
-    return launch_reduce<StaticEval<Tbl, c.prog>, StaticAcc<c.binop, c.acc_rt>, Slot, (k64 ? 2 : 4)>(
-        p, ctx, inner, kProgNames[c.prog]);
-}
-
-StaticReduceEntry g_entries[kCount];
-template <int... I> void fill(std::integer_sequence<int, I...>) {
-    ((g_entries[I] = StaticReduceEntry{&Tbl::progs[kCombos[I].prog], kCombos[I].binop, kCombos[I].acc_rt,
-                                       kProgNames[kCombos[I].prog], &launch_one<I>}),
-     ...);
-}
-
-}  // namespace
-
-StaticReduceTable static_reduce_table() {
-    static const bool once = (fill(std::make_integer_sequence<int, kCount>{}), true);
-    (void) once;
-    return StaticReduceTable{g_entries, kCount};
-}
-
-}  // namespace xtb
+// xtb_static_reduce.cu -- ahead-of-time reduction kernels, 128-bit vector access (see xtb_static_reduce_impl.cuh)
+#define XTB_SR_SCALAR 0
+#define XTB_SR_TABLE static_reduce_table
+#include "xtb_static_reduce_impl.cuh"
