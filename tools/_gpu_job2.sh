@@ -1,4 +1,11 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_reduce.py tests/test_nan_functions.py tests/test_arg_norm.py tests/test_zz_fullsize.py tests/test_gpu_dropin.py tests/test_gpu_golden.py -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02_decomp_pytest.log
-tail -5 gpurun_out/r02_decomp_pytest.log
-python tools/reduce_bench.py 2>&1 | tee gpurun_out/r02_reduce_bench3.log | cut -c1-150
+python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02_pytest_gpu_f.log
+tail -3 gpurun_out/r02_pytest_gpu_f.log
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_f.json 2> gpurun_out/r02_bench_n1_f.err
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r02_bench_n1_f.json').read().strip().splitlines()[-1])
+print(d['ms_per_step'], d['value'])
+for k,v in d['other_configs'].items():
+    if 'GBs' in v: print(k, v['GBs'], v['frac_of_measured_peak'], v['ms'], v['kernel'][:50])
+P

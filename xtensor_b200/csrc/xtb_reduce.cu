@@ -341,9 +341,12 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
         // every fp32 chain short (<= kRdFlush terms per level).  Unsplit, the kernel adds row after row exactly
         // like reduce_immediate (xreducer.hpp:512-551) and stays bit-identical to it.
         p.two_level = p.nsplit > 1 ? 1 : 0;
-        bool all_vec = p.nr == 1 && KL % V == 0;
-        for (int k = 0; k < in.n_leaves; ++k) all_vec = all_vec && p.leaf[k].mode == MODE_VEC;
-        p.outer_fast = all_vec ? 1 : 0;
+        bool all_vec = p.nr == 1 && KL % V == 0, some_vec = false;
+        for (int k = 0; k < in.n_leaves; ++k) {
+            all_vec = all_vec && (p.leaf[k].mode == MODE_VEC || p.leaf[k].mode == MODE_BCAST);
+            some_vec = some_vec || p.leaf[k].mode == MODE_VEC;
+        }
+        p.outer_fast = all_vec && some_vec ? 1 : 0;
     }
 
     // ---- cross-GPU merge of the result (the reduced axis is the sharded one) ----

@@ -429,16 +429,24 @@ template <class Eval, class S, int V, int U, int K, int INV = 0> struct RdLeafLo
 // fused map-reduce kernels (variance, amax) below the plain sum.
 template <class Eval, class S, int V, int U, int K, int INV = 0> struct RdFastLoader {
     template <class PF, int NL>
-    static XTB_DEV void run(const char* const (&row0)[NL], const int64_t (&rstep)[NL], PF& pf, bool skip_invariant) {
+    static XTB_DEV void run(const RdParams& p, const char* const (&row0)[NL], const int64_t (&rstep)[NL], PF& pf, bool skip_invariant) {
         if constexpr (K < Eval::kLeaves) {
             constexpr int dt = Eval::template leaf_dtype<K>();
             if constexpr (((INV >> K) & 1) != 0) {
                 if (!skip_invariant) load_vec<S, V>(row0[K], dt, pf.inv[K]);
+            } else if (p.leaf[K].mode == MODE_BCAST) {
+                // one element per row, the same for the thread's V outputs (the index vector of argmin / argmax)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const S v0 = load_elem<S>(row0[K] + u * rstep[K], dt);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) pf.pre[K][u][v] = v0;
+                }
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) load_vec<S, V>(row0[K] + u * rstep[K], dt, pf.pre[K][u]);
             }
-            RdFastLoader<Eval, S, V, U, K + 1, INV>::template run<PF, NL>(row0, rstep, pf, skip_invariant);
+            RdFastLoader<Eval, S, V, U, K + 1, INV>::template run<PF, NL>(p, row0, rstep, pf, skip_invariant);
         }
     }
 };
@@ -482,7 +490,7 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
                     row0[k] = base[k] + j * vstep[k];
                 }
                 for (; j + (int64_t) (U - 1) * stride < jend; j += (int64_t) stride * U) {
-                    RdFastLoader<Eval, S, V, U, 0>::template run<decltype(pf), NL>(row0, rs, pf, false);
+                    RdFastLoader<Eval, S, V, U, 0>::template run<decltype(pf), NL>(p, row0, rs, pf, false);
 #pragma unroll
                     for (int k = 0; k < NL; ++k) row0[k] += U * rs[k];
 #pragma unroll
@@ -824,7 +832,7 @@ XTB_DEV void reduce_outer_body(const RdParams& p) {
                         row0[k] = base[k] + r * rs[k];
                     }
                     for (; r + U <= rend; r += U) {
-                        RdFastLoader<Eval, S, V, U, 0, INV>::template run<decltype(pf), NL>(row0, rs, pf, r != rbeg);
+                        RdFastLoader<Eval, S, V, U, 0, INV>::template run<decltype(pf), NL>(p, row0, rs, pf, r != rbeg);
 #pragma unroll
                         for (int k = 0; k < NL; ++k) row0[k] += U * rs[k];
 #pragma unroll
