@@ -412,6 +412,15 @@ namespace xtl
 
     template <class T> inline T&& value(T&& v) { return std::forward<T>(v); }
     template <class T> inline bool has_value(T&&) { return true; }
+
+    // ------------------------------------------------------------------ xplatform.hpp (io/xnpy.hpp reads the byte order)
+    enum class endian { big_endian, little_endian, mixed };
+    inline endian endianness()
+    {
+        const std::uint32_t probe = 0x01020304u;
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(&probe);
+        return b[0] == 4 ? endian::little_endian : (b[0] == 1 ? endian::big_endian : endian::mixed);
+    }
 }
 
 #endif

@@ -11,6 +11,7 @@
 #include <random>
 
 #include <xtb200/xtensor_b200.hpp>
+#include <xtb200/xtb_npy.hpp>
 #include <xtensor/generators/xbuilder.hpp>
 
 static int g_failed = 0;
@@ -263,6 +264,20 @@ int main()
         bool threw = false;
         try { xtb::xtensor<float, 2> dc = da + db; } catch (const xt::broadcast_error&) { threw = true; }
         CHECK(threw);
+    }
+    // .npy fixtures <-> device containers (io/xnpy.hpp:740-800 through xtb::load_npy / xtb::dump_npy)
+    {
+        xt::xarray<float> a = rnd<float>(41, -2, 2, 37, 19);
+        const std::string in = "/tmp/xtb200_dropin_in.npy", out = "/tmp/xtb200_dropin_out.npy";
+        xt::dump_npy(in, a);
+        xtb::xarray<float> da = xtb::load_npy<float>(in);
+        CHECK(same_bits(xtb::to_host(da), a));
+        xtb::dump_npy(out, da * 2.0f + 1.0f);                // a lazy device expression is evaluated on the device first
+        xt::xarray<float> back = xt::load_npy<float>(out);
+        xt::xarray<float> want = a * 2.0f + 1.0f;
+        CHECK(same_bits(back, want));
+        std::remove(in.c_str());
+        std::remove(out.c_str());
     }
     xtb::sync();
     std::printf("%s (%d failures, %lld kernel launches)\n", g_failed ? "FAILED" : "OK", g_failed, (long long) xtb_launch_count(0));

@@ -93,3 +93,14 @@ def test_foreign_device_memory(xt, gpu):
     finally:
         for p in ptrs:
             gpu.xtb_free(p)
+
+
+def test_npy_fixture_round_trip(xt, gpu, tmp_path):
+    """.npy -> device -> expression -> .npy (SURVEY 8(f) row 2; the C++ side is xtb::load_npy / dump_npy, test_dropin.cpp)."""
+    a = np.random.default_rng(3).integers(-9, 10, (33, 17)).astype(np.float32)
+    src, dst = str(tmp_path / "a.npy"), str(tmp_path / "b.npy")
+    np.save(src, a)
+    d = xt.DeviceArray.from_npy(src)
+    assert d.shape == a.shape and np.array_equal(d.numpy(), a)
+    xt.evaluate(d * np.float32(2) + np.float32(1)).to_npy(dst)
+    assert np.array_equal(np.load(dst), a * 2 + 1)

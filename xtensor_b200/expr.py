@@ -432,6 +432,15 @@ class DeviceArray(Array):
             capi.check(capi.lib().xtb_sync())
         return d
 
+    @staticmethod
+    def from_npy(path: str) -> "DeviceArray":
+        """.npy fixture -> device (mirror of xtb::load_npy, include/xtb200/xtb_npy.hpp)."""
+        return DeviceArray.from_numpy(np.load(path))
+
+    def to_npy(self, path: str) -> None:
+        """device -> .npy (mirror of xtb::dump_npy)."""
+        np.save(path, self.numpy())
+
     def base_ptr(self) -> int:
         return self.owner.ptr
 
