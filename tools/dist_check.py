@@ -103,6 +103,21 @@ def main():
                 if not np.array_equal(got.numpy().astype(np.float64), fn(fl, axis=0).astype(np.float64)):
                     fails.append(f"sharded {name} {npdt.__name__} cols {cols_}")
 
+    # reductions the planner rewrites into two passes (narrow: < 1024 outputs; mixed: outer + innermost axis): the
+    # cross-GPU merge, xt::initial and the finalize step belong to the second pass
+    for shape_, axes_ in (((4096 * world + 7, 48), [0]), ((300 * world + 1, 70, 50, 6), [0, 2]), ((512 * world, 64, 16), [0, 2])):
+        fl = np.random.default_rng(len(shape_)).integers(-8, 9, shape_).astype(np.float32)
+        b_, e_ = shard.row_block(shape_[0], rank, world)
+        loc = xt.DeviceArray.from_numpy(fl[b_:e_])
+        got = xt._run_reducer(xt.sum(loc, axes_, initial=np.float32(10)), xt.DeviceArray, allreduce=True)
+        checks += 1
+        if not np.array_equal(got.numpy(), fl.sum(axis=tuple(axes_), dtype=np.float64).astype(np.float32) + np.float32(10)):
+            fails.append(f"sharded two-pass sum {shape_} {axes_}")
+        got = xt._run_reducer(xt.amax(loc, axes_), xt.DeviceArray, allreduce=True)
+        checks += 1
+        if not np.array_equal(got.numpy(), fl.max(axis=tuple(axes_))):
+            fails.append(f"sharded two-pass amax {shape_} {axes_}")
+
     s_sum, mean_, s_sq, var_ = (xt.DeviceArray.empty((cols,), xt.F32) for _ in range(4))
     o = xt.DeviceArray.empty((e - b, cols), xt.F32)
     n_rows = np.float32(rows)

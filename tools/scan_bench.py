@@ -34,6 +34,9 @@ CASES = [
     ((8192, 8192), 1, np.float32), ((8192, 8192), 0, np.float32), ((8192, 8192), 1, np.float64), ((8192, 8192), 0, np.float64),
     ((1 << 20, 64), 1, np.float32), ((1 << 17, 512), 1, np.float32), ((64, 1 << 20), 1, np.float32), ((64, 1 << 20), 0, np.float32),
     ((1 << 20, 64), 0, np.float32), ((256, 512, 512), 1, np.float32), ((1 << 26,), None, np.uint8),
+    # odd extents: row pitch not a multiple of 16 bytes
+    (((1 << 26) + 3,), None, np.float32), ((8191, 8190), 1, np.float32), ((8191, 8190), 0, np.float32),
+    ((4095, 4097, 15), 1, np.float32), ((4095, 4097), 0, np.float64), ((4095, 4097), 1, np.float64), ((255, 513, 511), 2, np.float32),
 ]
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
 variants = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--variant=")] or [0]
