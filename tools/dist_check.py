@@ -105,7 +105,7 @@ def main():
 
     # reductions the planner rewrites into two passes (narrow: < 1024 outputs; mixed: outer + innermost axis): the
     # cross-GPU merge, xt::initial and the finalize step belong to the second pass
-    for shape_, axes_ in (((4096 * world + 7, 48), [0]), ((300 * world + 1, 70, 50, 6), [0, 2]), ((512 * world, 64, 16), [0, 2])):
+    for shape_, axes_ in (((32768 * world + 7, 48), [0]), ((300 * world + 1, 70, 50, 6), [0, 2]), ((2048 * world, 64, 16), [0, 2])):
         fl = np.random.default_rng(len(shape_)).integers(-8, 9, shape_).astype(np.float32)
         b_, e_ = shard.row_block(shape_[0], rank, world)
         loc = xt.DeviceArray.from_numpy(fl[b_:e_])
