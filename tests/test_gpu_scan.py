@@ -191,3 +191,26 @@ def test_column_walkers(xt, gpu, shape, axis, dtype):
         b[0] = -0.0                                            # out[0] = in[0]: a leading -0.0 survives
         g, w = both(xt, b, axis)
         assert_bit_exact(g, w)
+
+
+@pytest.mark.parametrize("shape,axis", [((300, 4001), 0), ((129, 5003), 0), ((1000, 3999), 0), ((2, 257, 3001), 1),
+                                        ((131, 37, 111), 0), ((4097, 4095), 0)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+def test_unaligned_strided_axis_walkers(xt, gpu, shape, axis, dtype):
+    """Odd row pitch (no tensor map possible): the cp.async walkers accumulate every column in the reference's order,
+    so random floating-point data is bit-exact against the oracle, cumprod included."""
+    from util import last_kernel
+    rng = np.random.default_rng(9)
+    a = (rng.uniform(-1, 1, shape) if np.issubdtype(dtype, np.floating) else rng.integers(-3, 4, shape)).astype(dtype)
+    g, w = both(xt, a, axis)
+    assert "colwalk_plain" in last_kernel(), last_kernel()
+    assert_bit_exact(g, w)
+    b = (rng.uniform(0.9, 1.1, shape) if np.issubdtype(dtype, np.floating) else rng.integers(1, 2, shape)).astype(dtype)
+    g, w = both(xt, b, axis, fn="cumprod")
+    assert_bit_exact(g, w)
+    # a view whose base is off by one element (aligned pitch, unaligned base)
+    if len(shape) == 2:
+        c = (rng.uniform(-1, 1, (shape[0], 4100)) if np.issubdtype(dtype, np.floating) else rng.integers(-3, 4, (shape[0], 4100))).astype(dtype)
+        gv = xt.cumsum(xt.view(xt.DeviceArray.from_numpy(c), slice(None), slice(1, None)), 0).numpy()
+        wv = xt.cumsum(xt.view(xt.HostArray.from_numpy(c), slice(None), slice(1, None)), 0).numpy()
+        assert_bit_exact(gv, wv)

@@ -1521,6 +1521,143 @@ template <class T> static int scan_colwalk(const ScanParams& p, DeviceCtx* ctx) 
     return check_launch("k_scan_colwalk");
 }
 
+// ---- strided axis, many columns, pitch or base not 16-byte aligned: the same walkers without the TMA unit --------
+// Odd extents ((8191, 8190) along axis 0: the row pitch is 32760 bytes) cannot be described by a tensor map.  The
+// walker keeps its shape -- producer warp, consumer warp, shared-memory ring of 32-row boxes, every column accumulated
+// in the reference's order -- but the producer fills a box with element-sized cp.async (lane = column: one coalesced
+// 128-byte row per instruction) and signals the box through cp.async.mbarrier.arrive; the consumer adds down its column
+// and stores each running value straight to the dense output (coalesced rows).  A strip is 32 columns wide.
+constexpr int kCpRows = 32;
+
+template <class T, int OP>
+__global__ void __launch_bounds__(64) k_scan_colwalk_plain(const __grid_constant__ ScanParams p, const __grid_constant__ ColWalkParams c,
+                                                            int64_t outer_stride) {
+    extern __shared__ __align__(128) unsigned char cwp_smem[];
+    __shared__ __align__(8) unsigned long long s_full[16], s_empty[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t stage_bytes = (uint32_t) (kCpRows * 32 * (int) sizeof(T));
+    const uint32_t walker = blockIdx.x;
+    const uint32_t o = walker / (uint32_t) c.strips;
+    const uint32_t strip = walker - o * (uint32_t) c.strips;
+    const int64_t col = (int64_t) strip * 32 + lane;
+    const bool live = col < p.inner;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < c.stages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_u32(&s_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_empty[s])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        // ---- producer: every lane copies its column's element of each row of the box ----
+        const char* src = p.in + ((int64_t) o * outer_stride + col) * (int64_t) sizeof(T);
+        const int64_t sstep = p.in_axis_stride * (int64_t) sizeof(T);
+        int s = 0;
+        uint32_t round = 0;
+        for (int it = 0; it < c.chunks; ++it) {
+            if (round > 0) mbar_wait(smem_u32(&s_empty[s]), (round + 1) & 1u);
+            const int64_t r0 = (int64_t) it * kCpRows;
+            const int nr = (int) (p.n - r0 < kCpRows ? p.n - r0 : kCpRows);
+            const uint32_t dst = smem_u32(cwp_smem + (size_t) s * stage_bytes) + (uint32_t) lane * (uint32_t) sizeof(T);
+            if (live) {
+                if (nr == kCpRows) {
+#pragma unroll
+                    for (int r = 0; r < kCpRows; ++r)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + (uint32_t) (r * 32 * (int) sizeof(T))),
+                                     "l"(src + (r0 + r) * sstep), "n"((int) sizeof(T)) : "memory");
+                } else {
+                    for (int r = 0; r < nr; ++r)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + (uint32_t) (r * 32 * (int) sizeof(T))),
+                                     "l"(src + (r0 + r) * sstep), "n"((int) sizeof(T)) : "memory");
+                }
+            }
+            // arrives on the box's barrier once this lane's copies have landed (the 32 lanes are the barrier's count)
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_full[s])) : "memory");
+            if (++s == c.stages) {
+                s = 0;
+                ++round;
+            }
+        }
+        return;
+    }
+    // ---- consumer: lane owns one column ----
+    T acc = sident<OP, T>();
+    T* out = (T*) p.out + (int64_t) o * p.n * p.inner + col;
+    int s = 0;
+    uint32_t round = 0;
+    for (int it = 0; it < c.chunks; ++it) {
+        mbar_wait(smem_u32(&s_full[s]), round & 1u);
+        const T* q = (const T*) (cwp_smem + (size_t) s * stage_bytes) + lane;
+        const int64_t r0 = (int64_t) it * kCpRows;
+        const int nr = (int) (p.n - r0 < kCpRows ? p.n - r0 : kCpRows);
+        if (live) {
+            T* dst = out + r0 * p.inner;
+            if (nr == kCpRows && it > 0) {
+#pragma unroll
+                for (int r = 0; r < kCpRows; ++r) {
+                    acc = sop<OP, T>(acc, q[r * 32]);
+                    dst[(int64_t) r * p.inner] = acc;
+                }
+            } else {
+                for (int r = 0; r < nr; ++r) {
+                    // out[0] = in[0] (a leading -0.0 survives)
+                    acc = (it == 0 && r == 0) ? q[0] : sop<OP, T>(acc, q[r * 32]);
+                    dst[(int64_t) r * p.inner] = acc;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[s])) : "memory");
+        if (++s == c.stages) {
+            s = 0;
+            ++round;
+        }
+    }
+}
+
+template <class T> static int scan_colwalk_plain(const ScanParams& p, DeviceCtx* ctx) {
+    const int64_t asz = sizeof(T);
+    bool ok = std::is_same<T, float>::value ? p.in_dtype == XTB_F32
+            : std::is_same<T, double>::value ? p.in_dtype == XTB_F64
+            : sizeof(T) == 4 ? (p.in_dtype == XTB_I32 || p.in_dtype == XTB_U32)
+                             : (p.in_dtype == XTB_I64 || p.in_dtype == XTB_U64);
+    ok = ok && (uintptr_t) p.in % asz == 0 && (uintptr_t) p.out % asz == 0 && p.in_axis_stride > 0 && p.n_outer <= 1 && p.n >= 4 * kCpRows;
+    int64_t expect = 1;
+    for (int d = p.n_inner - 1; d >= 0 && ok; --d) {
+        if (p.inner_shape[d] != 1 && p.inner_stride[d] != expect) ok = false;
+        expect *= p.inner_shape[d];
+    }
+    const int64_t outer_stride = p.n_outer == 1 && p.outer_shape[0] > 1 ? p.outer_stride[0] : p.n * p.in_axis_stride;
+    ok = ok && outer_stride > 0;
+    if (!ok) return 1;
+    ColWalkParams c;
+    c.W = 32;
+    c.strips = (int32_t) ((p.inner + 31) / 32);
+    const int64_t walkers = (int64_t) c.strips * p.rows;
+    // one walker streams ~40 GB/s: worth it only with about a walker per SM or more
+    if (walkers < ctx->sm_count * 3 / 4 || walkers >= 0x7fffffffLL || p.inner >= 0x7fffffffLL || p.n >= 0x7fffffffLL) return 1;
+    c.box_rows = kCpRows;
+    c.chunks = (int32_t) ((p.n + kCpRows - 1) / kCpRows);
+    const int64_t stage_bytes = (int64_t) kCpRows * 32 * asz;
+    // a walker reads 128-byte row pieces a pitch apart: latency-bound, so a deep ring (measured on (8191, 8190) fp32:
+    // 8 boxes 3.0 TB/s, 12 boxes 2.9, 16 boxes 4.3; fp64 (4095, 4097): 4 boxes 3.4, 12 boxes 4.4, 16 boxes 4.5)
+    int64_t stages = asz == 4 ? 16 : 12;
+    if (options().scan_variant < 0) stages = std::max<int64_t>(2, std::min<int64_t>(-options().scan_variant, 16));
+    stages = std::min<int64_t>(stages, std::max<int64_t>(2, c.chunks));
+    c.stages = (int32_t) stages;
+    const size_t smem = (size_t) stages * (size_t) stage_bytes;
+    if (p.op == XTB_RED_PROD) {
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_colwalk_plain<T, XTB_RED_PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        k_scan_colwalk_plain<T, XTB_RED_PROD><<<(unsigned) walkers, 64, smem, ctx->stream>>>(p, c, outer_stride);
+    } else {
+        XTB_CUDA(cudaFuncSetAttribute(k_scan_colwalk_plain<T, XTB_RED_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        k_scan_colwalk_plain<T, XTB_RED_SUM><<<(unsigned) walkers, 64, smem, ctx->stream>>>(p, c, outer_stride);
+    }
+    note_launch("k_scan_colwalk_plain[cp.async ring, reference order]");
+    return check_launch("k_scan_colwalk_plain");
+}
+
 // ---- strided axis: one thread per column ------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(256) k_scan_columns(const __grid_constant__ ScanParams p) {
@@ -1780,6 +1917,14 @@ extern "C" int xtb_scan(int op, int acc_type, const xtb_operand* in, int axis, c
                 case XTB_I64: case XTB_U64: r = scan_colwalk<unsigned long long>(p, ctx); break;
                 case XTB_F32: r = scan_colwalk<float>(p, ctx); break;
                 default: r = scan_colwalk<double>(p, ctx); break;
+            }
+            if (r <= 0) return r;
+            // the same walkers without TMA (unaligned pitch / base)
+            switch (acc_type) {
+                case XTB_I32: case XTB_U32: r = scan_colwalk_plain<uint32_t>(p, ctx); break;
+                case XTB_I64: case XTB_U64: r = scan_colwalk_plain<unsigned long long>(p, ctx); break;
+                case XTB_F32: r = scan_colwalk_plain<float>(p, ctx); break;
+                default: r = scan_colwalk_plain<double>(p, ctx); break;
             }
             if (r <= 0) return r;
             switch (acc_type) {
