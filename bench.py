@@ -616,8 +616,20 @@ def other_configs(lib, xt, capi, args):
             iop, oop = x.operand(), oi.operand()
             capi.check(lib.xtb_argreduce(capi.RED_MAX, C.byref(iop), 0, C.byref(oop)))
         out["cfg3_argmax_axis0"] = timed(argmax0, nb + 4096 * 16 * 8)
-        del o0, o2, oi
+        # beyond the named axes: reductions the planner rewrites into two passes (reduce_decomposed)
+        o01, o02 = xt.DeviceArray.empty((16,), xt.F32), xt.DeviceArray.empty((4096,), xt.F32)
+        out["cfg3_shape_sum_axes01_narrow_two_pass"] = timed(lambda: red(xt.sum(x, [0, 1]), o01), nb + 16 * 4)
+        out["cfg3_shape_sum_axes02_mixed_two_pass"] = timed(lambda: red(xt.sum(x, [0, 2]), o02), nb + 4096 * 4)
+        del o0, o2, oi, o01, o02
         del x
+        # odd extents: the row pitch (32760 bytes) rules out 128-bit vectors and tensor maps
+        xo = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (8191, 8190)).astype(np.float32))
+        oo0, oo1, yo = xt.DeviceArray.empty((8190,), xt.F32), xt.DeviceArray.empty((8191,), xt.F32), xt.DeviceArray.empty((8191, 8190), xt.F32)
+        nbo = 8191 * 8190 * 4
+        out["odd_8191x8190_sum_axis0"] = timed(lambda: red(xt.sum(xo, [0]), oo0), nbo)
+        out["odd_8191x8190_sum_axis1"] = timed(lambda: red(xt.sum(xo, [1]), oo1), nbo)
+        out["odd_8191x8190_cumsum_axis0"] = timed(lambda: xt.cumsum(xo, 0, out=yo), 2 * nbo)
+        del xo, oo0, oo1, yo
         # cfg4: fp64 (8192,8192) transpose(a) + view(b, range(0,_,2), all())
         a = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (8192, 8192)))
         b = xt.DeviceArray.from_numpy(rng.uniform(-1, 1, (16384, 8192)))
