@@ -323,7 +323,8 @@ static int plan_and_launch(ReducePlanIn& in, DeviceCtx* ctx) {
             double best_fill = 0.0;
             for (int64_t w = waves; w <= 2 * waves + 1; ++w) {
                 const int64_t n = std::max<int64_t>(1, slots * w / gx);
-                const double fill = (double) (gx * n) / (double) (slots * w);
+                const int64_t ctas = gx * n;
+                const double fill = (double) ctas / (double) ((ctas + slots - 1) / slots * slots);   // of the waves it really takes
                 if (fill > best_fill) { best_fill = fill; want = n; }
                 if (fill >= 0.93) break;
             }
