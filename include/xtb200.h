@@ -306,7 +306,13 @@ int  xtb_allreduce(void* buf, size_t count, int dtype, int op);
 /* ---- process options ------------------------------------------------------- */
 /* The XTB_* environment switches are read once, at first use; afterwards they are changed through this call
  * (name = the variable without the XTB_ prefix, lower case: "no_static", "no_jit", "no_staged", "no_tma",
- * "jit_min_elems", "jit_verbose", "scan_variant", "tile_variant", "arg_two_pass", "no_pdl", "no_decompose").  xtb_get_option returns -1 for unknown names. */
+ * "jit_min_elems", "jit_verbose", "scan_variant", "scan_nv", "tile_variant", "arg_two_pass";
+ *   "no_pdl"       1: every kernel launch fully serialised (default: the reduce / merge / map kernels of a pipeline
+ *                  use programmatic dependent launch);
+ *   "no_decompose" 1: single-pass reductions only (default: narrow and mixed-axis reductions run as two passes);
+ *   "reduce_split", "reduce_g": development overrides of the reduction planner (row-split count / lanes per output)).
+ * Changing an option does not change results beyond the documented summation-order freedom of split reductions.
+ * xtb_get_option returns -1 for unknown names. */
 int  xtb_set_option(const char* name, long long value);
 long long xtb_get_option(const char* name);
 

@@ -111,3 +111,20 @@ def test_no_cpu_fallback_without_gpu():
     op.ndim = 1
     op.shape[0] = 4
     assert lib.xtb_assign(C.byref(prog), C.byref(op), None) == capi.ERR_NO_DEVICE
+
+
+def test_process_options_round_trip():
+    """Every switch the header documents is known to the library (no device needed), unknown names are rejected."""
+    lib = capi.lib()
+    doc = open(os.path.join(ROOT, "include", "xtb200.h")).read()
+    names = ["no_static", "no_jit", "no_staged", "no_tma", "jit_min_elems", "jit_verbose", "scan_variant", "scan_nv",
+             "tile_variant", "arg_two_pass", "no_pdl", "no_decompose", "reduce_split", "reduce_g"]
+    for n in names:
+        assert f'"{n}"' in doc, f"{n} is not documented in include/xtb200.h"
+        old = lib.xtb_get_option(n.encode())
+        assert old >= 0, n
+        assert lib.xtb_set_option(n.encode(), old + 1) == 0
+        assert lib.xtb_get_option(n.encode()) == old + 1
+        assert lib.xtb_set_option(n.encode(), old) == 0
+    assert lib.xtb_get_option(b"no_such_option") == -1
+    assert lib.xtb_set_option(b"no_such_option", 1) != 0
