@@ -354,6 +354,28 @@ int main()
         CHECK(same_bits(xtb::to_host(dc), c));
     }
 
+    // shapes the planner rewrites into two passes (narrow: < 1024 outputs; mixed: outer + innermost axis) and odd
+    // extents (scalar-access kernels), through the unchanged xtensor calls; integer-valued data: exact in any order
+    {
+        xt::xarray<float> a = rnd_int<float>(51, -4, 4, {70001, 20});                 // narrow, remainder slice (70001 is prime-ish)
+        xtb::xarray<float> da = xtb::to_device(a);
+        { xtb::xarray<float> d = xt::sum(da, {0}); xt::xarray<float> h = xt::sum(a, {0}); CHECK(same_bits(xtb::to_host(d), h)); }
+        { xtb::xarray<float> d = xt::amax(da, {0}); xt::xarray<float> h = xt::amax(a, {0}); CHECK(same_bits(xtb::to_host(d), h)); }
+        { xtb::xarray<double> d = xt::mean(da, {0}); xt::xarray<double> h = xt::mean(a, {0}); CHECK(same_bits(xtb::to_host(d), h)); }
+        { xtb::xarray<float> d = xt::sum(da, {0}, xt::keep_dims | xt::initial(7.0f)); xt::xarray<float> h = xt::sum(a, {0}, xt::keep_dims | xt::initial(7.0f));
+          CHECK(same_bits(xtb::to_host(d), h)); }
+        xt::xarray<double> b = rnd_int<double>(52, -4, 4, {300, 17, 257});              // mixed: axes {0, 2}, kept dim between
+        xtb::xarray<double> db = xtb::to_device(b);
+        { xtb::xarray<double> d = xt::sum(db, {0, 2}); xt::xarray<double> h = xt::sum(b, {0, 2}); CHECK(same_bits(xtb::to_host(d), h)); }
+        { xtb::xarray<std::size_t> d = xt::count_nonzero(db, {0, 2}); xt::xarray<std::size_t> h = xt::count_nonzero(b, {0, 2}); CHECK(same_bits(xtb::to_host(d), h)); }
+        xt::xarray<int> c = rnd_int<int>(53, -9, 9, {2047, 1022});                       // odd row pitch: 4088 bytes
+        xtb::xarray<int> dc = xtb::to_device(c);
+        { xtb::xarray<int> d = xt::sum(dc, {0}); xt::xarray<int> h = xt::sum(c, {0}); CHECK(same_bits(xtb::to_host(d), h)); }
+        { xtb::xarray<int> d = xt::amin(dc, {1}); xt::xarray<int> h = xt::amin(c, {1}); CHECK(same_bits(xtb::to_host(d), h)); }
+        CHECK(std::strstr(xtb_last_kernel(), "interp") == nullptr);
+        { xtb::xarray<int> d = xt::cumsum(dc, 0); xt::xarray<int> h = xt::cumsum(c, 0); CHECK(same_bits(xtb::to_host(d), h)); }
+    }
+
     if (g_failed) { std::printf("%d check(s) FAILED\n", g_failed); return 1; }
     std::printf("OK test_dropin_reducers\n");
     return 0;
