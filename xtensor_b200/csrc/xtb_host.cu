@@ -65,7 +65,7 @@ extern "C" int xtb_assign_host(const xtb_program* prog, const xtb_operand* out, 
     XTB_TRY(get_ctx(&ctx));
     if (ctx->device < 0 || ctx->device >= 16) XTB_FAIL(XTB_ERR_UNSUPPORTED, "xtb_assign_host: device index %d", ctx->device);
     std::lock_guard<std::mutex> pipe_lock(g_pipe_mutex[ctx->device]);
-    HostPipe* pipe;
+    HostPipe* pipe = nullptr;
     XTB_TRY(pipe_for(ctx, &pipe));
     const int nd = out->ndim;
     int64_t total = 1;
