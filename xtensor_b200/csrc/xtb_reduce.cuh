@@ -489,6 +489,26 @@ XTB_DEV S rd_inner_partial(const RdParams& p, uint32_t ko, int64_t jbeg, int64_t
                     rs[k] = (int64_t) stride * vstep[k];
                     row0[k] = base[k] + j * vstep[k];
                 }
+                if constexpr (V == 1) {
+                    // scalar access (odd pitches): a lane's load is 4 or 8 bytes, so four times as many stay in flight;
+                    // the summation blocks are the same kRdInnerFlush elements, hence the same result
+                    constexpr int UB = 4 * U;
+                    PreFetch<NL, UB, S, V> pfw;
+                    for (; j + (int64_t) (UB - 1) * stride < jend; j += (int64_t) stride * UB) {
+                        RdFastLoader<Eval, S, V, UB, 0>::template run<decltype(pfw), NL>(p, row0, rs, pfw, false);
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) row0[k] += UB * rs[k];
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+                            pfw.u = u;
+                            S x[V];
+                            Eval::template run<S, V>(p.prog, pfw, x);
+                            Acc::template cast_in<S, V>(p, x);
+                            Acc::template step<S, V>(p, acc, x);
+                            if ((u + 1) % U == 0) total.flush(p, acc);
+                        }
+                    }
+                }
                 for (; j + (int64_t) (U - 1) * stride < jend; j += (int64_t) stride * U) {
                     RdFastLoader<Eval, S, V, U, 0>::template run<decltype(pf), NL>(p, row0, rs, pf, false);
 #pragma unroll
