@@ -111,6 +111,20 @@ def test_no_cpu_fallback_without_gpu():
     op.ndim = 1
     op.shape[0] = 4
     assert lib.xtb_assign(C.byref(prog), C.byref(op), None) == capi.ERR_NO_DEVICE
+    # reductions too -- single pass, and a shape the planner would rewrite into two passes (narrow: 4 outputs)
+    rp = capi.Program()
+    rp.n_insns = 1
+    rp.n_leaves = 1
+    rp.insns[0] = capi.Insn(0, capi.F32, capi.SRC_LEAF, 0)
+    for rows in (64, 1 << 20):
+        leaf, out = capi.Operand(), capi.Operand()
+        leaf.dtype = out.dtype = capi.F32
+        leaf.ndim, out.ndim = 2, 1
+        leaf.shape[0], leaf.shape[1], leaf.stride[0], leaf.stride[1] = rows, 4, 4, 1
+        out.shape[0], out.stride[0] = 4, 1
+        shape = (C.c_int64 * 2)(rows, 4)
+        axes = (C.c_int32 * 1)(0)
+        assert lib.xtb_reduce(capi.RED_SUM, capi.F32, C.byref(rp), C.byref(leaf), 2, shape, 1, axes, 0, None, C.byref(out), 0) == capi.ERR_NO_DEVICE
 
 
 def test_process_options_round_trip():
